@@ -1,0 +1,5 @@
+class SummaryWriter:
+    def __init__(self, *a, **k):
+        pass
+    def __getattr__(self, name):
+        return lambda *a, **k: None
