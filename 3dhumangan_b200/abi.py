@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_size_t, c_void_p
 
 import torch
 
@@ -25,6 +25,12 @@ SIGNATURES = {
     "hg_check_device": (c_int, []),
     "hg_packed_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "hg_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "hg_vertex_ik": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "hg_geo_features": (c_int, [c_void_p] * 12 + [c_int] * 6 + [c_float, c_int] + [c_void_p] * 6),
+    "hg_spade_conv": (c_int, [c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_long] + [c_void_p] * 12 + [c_int] * 7 + [c_void_p]),
+    "hg_bn_finalize": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
+                               c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "hg_synth_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "hg_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
@@ -105,3 +111,71 @@ def linear(X, Wimg, Nb, N, bias=None, passes=3, out=None):
         check(lib().hg_linear(c_void_p(X.data_ptr()), X.stride(0), M, K, ptr(Wimg), Nb, N, ptr(bias),
                               ptr(out), out.stride(0), passes, stream()), "hg_linear")
     return out
+
+
+def vertex_ik(fk, lbs):
+    """fk [B,24,4,4], lbs [B,V,24] -> [B,V,16] blended inverse transforms (smpl.py:217-218)."""
+    B, V = lbs.shape[0], lbs.shape[1]
+    fk = fk.float().contiguous()
+    lbs = lbs.float().contiguous()
+    out = torch.empty(B, V, 16, dtype=torch.float32, device=fk.device)
+    with torch.cuda.device_of(fk):
+        check(lib().hg_vertex_ik(ptr(fk), ptr(lbs), B, V, ptr(out), stream()), "hg_vertex_ik")
+    return out
+
+
+def geo_features(cond_vertices, tpose, skeletons, vik, *, input_scaler, legacy_mode=False, points_in=None,
+                 xs=None, ys=None, zs=None, focals=None, scales=None, cam2world=None, jitter=None,
+                 want_points=False, want_nearest=False):
+    """Ray sampling (or given points) + K=1 nearest vertex + 31-d features -> point records [B,N,36].
+
+    Returns dict(rec, z_vals, points, nearest, nearest_d2) (optional outputs None unless requested)."""
+    dev = cond_vertices.device
+    B, V = cond_vertices.shape[0], cond_vertices.shape[1]
+    f = lambda t: None if t is None else t.float().contiguous()
+    if points_in is not None:
+        points_in = f(points_in)
+        N, Rw, Rh, S = points_in.shape[1], 0, 0, 0
+    else:
+        Rw, Rh, S = xs.numel(), ys.numel(), zs.numel()
+        N = Rw * Rh * S
+    rec = torch.empty(B, N, 36, dtype=torch.float32, device=dev)
+    z_vals = torch.empty(B, N, dtype=torch.float32, device=dev) if points_in is None else None
+    pts = torch.empty(B, N, 3, dtype=torch.float32, device=dev) if want_points else None
+    near = torch.empty(B, N, dtype=torch.int32, device=dev) if want_nearest else None
+    d2 = torch.empty(B, N, dtype=torch.float32, device=dev) if want_nearest else None
+    keep = [f(t) for t in (xs, ys, zs, focals, scales, cam2world, jitter, points_in, skeletons, cond_vertices, tpose, vik)]
+    with torch.cuda.device_of(rec):
+        check(lib().hg_geo_features(*[ptr(t) for t in keep], B, Rw, Rh, S, V, N, float(input_scaler),
+                                    int(bool(legacy_mode)), ptr(rec), ptr(z_vals), ptr(pts), ptr(near), ptr(d2),
+                                    stream()), "hg_geo_features")
+    return {"rec": rec, "z_vals": z_vals, "points": pts, "nearest": near, "nearest_d2": d2}
+
+
+def spade_conv(x, x_bstride, wimg, bias, out, *, B, Hg, Wg, mod=None, scsh=None, p_lr=None, p_stride=0, p_bias=None,
+               wgb=None, bgb=None, skip=None, stats=None, rgb_w=None, rgb_b=None, rgb_in=None, rgb_out=None,
+               Rh=0, Rw=0, passes=3):
+    """One SPADE half-block (see csrc/synth.cu).  All tensors fp32 CUDA; `stats` is a float64 view [>=512]."""
+    with torch.cuda.device_of(out):
+        check(lib().hg_spade_conv(ptr(x), int(x_bstride), ptr(mod), ptr(scsh), ptr(p_lr), int(p_stride), ptr(p_bias),
+                                  ptr(wgb), ptr(bgb), ptr(wimg), ptr(bias), ptr(skip), ptr(out), ptr(stats),
+                                  ptr(rgb_w), ptr(rgb_b), ptr(rgb_in), ptr(rgb_out), B, 256, Hg, Wg, Rh, Rw, passes,
+                                  stream()), "hg_spade_conv")
+    return out
+
+
+def bn_finalize(stats, weight, bias, running_mean, running_var, training, *, count=0.0, count_dev=None, gb=None, B=0,
+                scsh=None, mod=None, eps=1e-5, momentum=0.1):
+    with torch.cuda.device_of(weight):
+        check(lib().hg_bn_finalize(ptr(stats), float(count), ptr(count_dev), ptr(weight), ptr(bias), ptr(running_mean),
+                                   ptr(running_var), int(bool(training)), float(eps), float(momentum), ptr(gb), B, 256,
+                                   ptr(scsh), ptr(mod), stream()), "hg_bn_finalize")
+
+
+def synth_input(w, bias, ic, jc, x0, stats, batch):
+    """x0[C,HW] = sin(w[:,0]*i + w[:,1]*j + b) and batch-multiplied BN statistics (map3d_layers.py:260-275)."""
+    C = w.shape[0]
+    with torch.cuda.device_of(x0):
+        check(lib().hg_synth_input(ptr(w), ptr(bias), ptr(ic), ptr(jc), C, ic.numel(), jc.numel(), ptr(x0), ptr(stats),
+                                   batch, stream()), "hg_synth_input")
+    return x0

@@ -1,0 +1,673 @@
+// SPADE synthesis backbone: one kernel launch per SPADE half-block
+//     x_out = Conv1x1_SN( lrelu_0.2( BN(x) * (1 + gamma) + beta ) ) + b  [+ x_skip]  [-> ToRGB accumulate]
+// (SPADE2d.forward lib/components/map3d_layers.py:176-190, SPADEBlock.forward :218-238,
+//  ToRGB :346-352, SynthesisNetwork.forward lib/generators/map3d_generator.py:58-97.)
+//
+// Activations live in HBM as fp32 planes [B, C=256, HW] (the reference's NCHW).  A CTA owns tiles
+// of 128 consecutive pixels of one image: 8 "row" warps build the bf16(x3) A operand in shared
+// memory (BN scale/shift, SPADE modulation, LeakyReLU fused into the operand producer), one
+// thread issues tcgen05.mma against weight tiles streamed from L2 by the bulk-copy engine, and
+// the row warps drain the fp32 accumulator from TMEM: bias, residual, ToRGB, per-channel
+// sum / sum-of-squares for the NEXT BatchNorm (so the SyncBN statistics never need a separate pass
+// over the activation), coalesced plane stores.
+//
+// Two variants:
+//   const-style : gamma/beta are per-sample vectors (blocks whose style map is spatially
+//                 constant, 12 of 18 half-blocks in 'mixed'/'isolated' mode).  Pipelined:
+//                 operand production of tile t+1 overlaps the MMAs of tile t (2 TMEM accumulators).
+//   pixel-style : gamma/beta come from a second GEMM on relu(bilinear_up(P_lr)) where
+//                 P_lr = W_shared . feature_maps + b at RENDER resolution (W_shared commutes with
+//                 the bilinear up-sample), so the 28x larger up-sampled style map of
+//                 map3d_generator.py:244-245 is never materialised.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace hg {
+
+constexpr int kC = 256;             // channels (hidden_dim == feature_dim == 256)
+constexpr int kSynThreads = 320;    // warps 0-7 rows, 8 MMA, 9 weight producer
+constexpr int kSynStages = 2;
+constexpr uint32_t kAChunk = 128 * 128;   // [128 x 64] bf16
+constexpr uint32_t kBStage = 256 * 128;   // [256 x 64] bf16
+
+struct SpadeArgs {
+  const float* x;        // [B or 1, C, HW]
+  long x_bstride;        // C*HW, or 0 when x is shared by the whole batch (synthesis input)
+  const float* mod;      // const-style: [B,2,C] (g1, g0): y = lrelu(x*g1 + g0)
+  const float* scsh;     // pixel-style: [2,C] BN scale, shift
+  const float* p_lr;     // pixel-style: [B, Rh*Rw, p_stride>=128] pre-activation of mlp_shared at render res
+  long p_stride;         //              row stride of p_lr in floats (multiple of 4)
+  const float* p_bias;   // pixel-style: [B,128] per-sample constant added after interpolation (or null)
+  const uint8_t* wgb;    // pixel-style: packed [512 x 128] gamma/beta weights (2 N-blocks, interleaved)
+  const float* bgb;      // pixel-style: [512] bias in the same interleaved order (gamma part includes +1)
+  const uint8_t* wimg;   // packed conv weight [256 x 256] (already divided by sigma)
+  const float* bias;     // [C]
+  const float* skip;     // [B,C,HW] residual or null
+  float* out;            // [B,C,HW]
+  double* stats;         // [2,C] accumulated sum / sumsq of out, or null
+  const float* rgb_w;    // [3,C] or null
+  const float* rgb_b;    // [3]
+  const float* rgb_in;   // [B,3,HW] or null
+  float* rgb_out;        // [B,3,HW]
+  int B, HW, Hg, Wg, Rh, Rw;
+};
+
+struct SynSmem {
+  uint8_t* a_hi;
+  uint8_t* a_lo;
+  uint8_t* b_st;
+  float* tab_g1;   // [C]  (const: g1 | pixel: bn scale)
+  float* tab_g0;   // [C]  (const: g0 | pixel: bn shift)
+  float* tab_bias; // [C]
+  float* tab_rgbw; // [3*C]
+  float* tab_bgb;  // [512]
+  float* st_sum;   // [C]
+  float* st_sq;    // [C]
+  float* rgb_part; // [2][128][3]
+  uint64_t* bars;
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ SynSmem carve(uint8_t* raw) {
+  uint8_t* s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  SynSmem m;
+  m.a_hi = s;
+  m.a_lo = s + 4 * kAChunk;
+  m.b_st = s + 8 * kAChunk;
+  float* f = reinterpret_cast<float*>(m.b_st + kSynStages * kBStage);
+  m.tab_g1 = f; f += kC;
+  m.tab_g0 = f; f += kC;
+  m.tab_bias = f; f += kC;
+  m.tab_rgbw = f; f += 3 * kC;
+  m.tab_bgb = f; f += 512;
+  m.st_sum = f; f += kC;
+  m.st_sq = f; f += kC;
+  m.rgb_part = f; f += 2 * 128 * 3;
+  m.bars = reinterpret_cast<uint64_t*>(f);
+  m.tmem_slot = reinterpret_cast<uint32_t*>(m.bars + 32);
+  return m;
+}
+constexpr uint32_t kSynSmemBytes = 8 * kAChunk + kSynStages * kBStage + (kC * 8 + 512 + 768) * 4 + 32 * 8 + 16 + 1024;
+
+// barrier slots
+enum { A_FULL = 0 /*4*/, A_EMPTY = 4 /*4*/, B_FULL = 8 /*2*/, B_EMPTY = 10 /*2*/, ACC_FULL = 12 /*2*/,
+       ACC_EMPTY = 14 /*2*/, G1_FULL = 16, A1_FULL = 17, Y_FULL = 18 };
+
+__device__ __forceinline__ void rows_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+
+// 32 lanes x 32 values: after the call lane j holds sum over lanes of v[j].
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool upper = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = upper ? v[i] : v[i + w];
+      const float keep = upper ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// shared pieces
+// ------------------------------------------------------------------------------------------
+template <int kPasses>
+__device__ __forceinline__ void producer_loop(const SynSmem& m, const uint8_t* const* imgs, const int* nstages,
+                                              int nimgs, int num_my_tiles) {
+  // Every tile consumes the same sequence of weight stages: for each image, `nstages` tiles of
+  // [256 x 64] in storage order (kc-major, hi then lo); the lo tiles are skipped in 1-pass mode.
+  uint32_t st = 0, ph = 0;
+  for (int t = 0; t < num_my_tiles; ++t)
+    for (int g = 0; g < nimgs; ++g)
+      for (int s = 0; s < nstages[g]; ++s) {
+        if (kPasses == 1 && (s & 1)) continue;
+        mbar_wait(m.bars + B_EMPTY + st, ph ^ 1);
+        mbar_arrive_expect_tx(m.bars + B_FULL + st, kBStage);
+        bulk_g2s(m.b_st + st * kBStage, imgs[g] + static_cast<size_t>(s) * kBStage, kBStage, m.bars + B_FULL + st);
+        if (++st == kSynStages) { st = 0; ph ^= 1; }
+      }
+}
+
+struct MmaPipe {
+  uint32_t st = 0, ph = 0;
+};
+
+// One K=64 chunk of a 3-pass (or 1-pass) product against the next weight stage(s).
+template <int kPasses>
+__device__ __forceinline__ void mma_chunk(const SynSmem& m, MmaPipe& p, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
+                                          uint32_t idesc, bool accumulate) {
+  mbar_wait(m.bars + B_FULL + p.st, p.ph);
+  tc_fence_after();
+  umma_k64(tmem_d, a_hi, smem_u32(m.b_st + p.st * kBStage), idesc, accumulate);
+  if (kPasses == 3) umma_k64(tmem_d, a_lo, smem_u32(m.b_st + p.st * kBStage), idesc, true);
+  umma_commit(m.bars + B_EMPTY + p.st);
+  if (++p.st == kSynStages) { p.st = 0; p.ph ^= 1; }
+  if (kPasses == 3) {
+    mbar_wait(m.bars + B_FULL + p.st, p.ph);
+    tc_fence_after();
+    umma_k64(tmem_d, a_hi, smem_u32(m.b_st + p.st * kBStage), idesc, true);
+    umma_commit(m.bars + B_EMPTY + p.st);
+    if (++p.st == kSynStages) { p.st = 0; p.ph ^= 1; }
+  }
+}
+
+// Drain one accumulator: bias, residual, stats, ToRGB, plane stores.
+__device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem& m, uint32_t tmem_acc, int b, int p0,
+                                              int warp, int lane) {
+  const int q = warp & 3, h = warp >> 2;
+  const int row = q * 32 + lane;
+  const int pix = p0 + row;
+  const bool valid = pix < a.HW;
+  const long plane = static_cast<long>(b) * kC * a.HW + pix;
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll 1
+  for (int kc = 0; kc < 4; ++kc) {
+    const int c0 = kc * 64 + h * 32;
+    uint32_t raw[32];
+    tmem_ld32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
+    tmem_ld_wait();
+    float v[32], s2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float o = __uint_as_float(raw[j]) + m.tab_bias[c0 + j];
+      if (a.skip && valid) o += a.skip[plane + static_cast<long>(c0 + j) * a.HW];
+      if (valid) a.out[plane + static_cast<long>(c0 + j) * a.HW] = o;
+      o = valid ? o : 0.f;
+      v[j] = o;
+      s2[j] = o * o;
+      if (a.rgb_w) {
+        r0 = fmaf(o, m.tab_rgbw[c0 + j], r0);
+        r1 = fmaf(o, m.tab_rgbw[kC + c0 + j], r1);
+        r2 = fmaf(o, m.tab_rgbw[2 * kC + c0 + j], r2);
+      }
+    }
+    if (a.stats) {
+      const float t1 = transpose_reduce32(v, lane);
+      const float t2 = transpose_reduce32(s2, lane);
+      atomicAdd(m.st_sum + c0 + lane, t1);
+      atomicAdd(m.st_sq + c0 + lane, t2);
+    }
+  }
+  if (a.rgb_w) {
+    float* part = m.rgb_part + (h * 128 + row) * 3;
+    part[0] = r0; part[1] = r1; part[2] = r2;
+  }
+}
+
+__device__ __forceinline__ void rgb_finish(const SpadeArgs& a, const SynSmem& m, int b, int p0, int warp, int lane) {
+  // called by all row warps after rows_barrier(); warps with h == 0 combine the two channel halves
+  if ((warp >> 2) != 0) return;
+  const int row = (warp & 3) * 32 + lane;
+  const int pix = p0 + row;
+  if (pix >= a.HW) return;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float o = m.rgb_part[row * 3 + j] + m.rgb_part[(128 + row) * 3 + j] + a.rgb_b[j];
+    const long idx = (static_cast<long>(b) * 3 + j) * a.HW + pix;
+    if (a.rgb_in) o += a.rgb_in[idx];
+    a.rgb_out[idx] = o;
+  }
+}
+
+__device__ __forceinline__ void init_common(const SpadeArgs& a, const SynSmem& m, int warp) {
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) {
+    m.tab_bias[i] = a.bias[i];
+    m.st_sum[i] = 0.f;
+    m.st_sq[i] = 0.f;
+  }
+  if (a.rgb_w)
+    for (int i = threadIdx.x; i < 3 * kC; i += blockDim.x) m.tab_rgbw[i] = a.rgb_w[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(m.bars + A_FULL + i, 8);
+      mbar_init(m.bars + A_EMPTY + i, 1);
+    }
+    for (int i = 0; i < kSynStages; ++i) {
+      mbar_init(m.bars + B_FULL + i, 1);
+      mbar_init(m.bars + B_EMPTY + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(m.bars + ACC_FULL + i, 1);
+      mbar_init(m.bars + ACC_EMPTY + i, 8);
+    }
+    mbar_init(m.bars + G1_FULL, 1);
+    mbar_init(m.bars + A1_FULL, 8);
+    mbar_init(m.bars + Y_FULL, 8);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<512>(m.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+__device__ __forceinline__ void flush_stats(const SpadeArgs& a, const SynSmem& m) {
+  // row warps only (256 threads), after a rows_barrier()
+  if (!a.stats) return;
+  const int c = threadIdx.x;
+  if (c < kC) {
+    atomicAdd(a.stats + c, static_cast<double>(m.st_sum[c]));
+    atomicAdd(a.stats + kC + c, static_cast<double>(m.st_sq[c]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// const-style variant (pipelined)
+// ------------------------------------------------------------------------------------------
+template <int kPasses>
+__global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const SynSmem m = carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  init_common(a, m, warp);
+  const uint32_t tmem = *m.tmem_slot;
+  const int tiles_per_img = (a.HW + 127) / 128;
+  const int num_tiles = a.B * tiles_per_img;
+  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (warp < 8) {
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    int cur_b = -1;
+    auto prologue = [&](int it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / tiles_per_img, p0 = (tile % tiles_per_img) * 128;
+      if (b != cur_b) {  // refresh the per-sample modulation table
+        rows_barrier();  // everyone finished reading the previous table
+        for (int i = threadIdx.x; i < kC; i += 256) {
+          m.tab_g1[i] = a.mod[(static_cast<long>(b) * 2 + 0) * kC + i];
+          m.tab_g0[i] = a.mod[(static_cast<long>(b) * 2 + 1) * kC + i];
+        }
+        rows_barrier();
+        cur_b = b;
+      }
+      const int pix = p0 + row;
+      const bool valid = pix < a.HW;
+      const float* xp = a.x + static_cast<long>(b) * a.x_bstride + pix;
+#pragma unroll 1
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(m.bars + A_EMPTY + kc, (it & 1) ^ 1);
+        const int c0 = kc * 64 + h * 32;
+        float xv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xv[j] = valid ? __ldg(xp + static_cast<long>(c0 + j) * a.HW) : 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c0 + g * 8 + j;
+            y[j] = lrelu02(fmaf(xv[g * 8 + j], m.tab_g1[c], m.tab_g0[c]));
+          }
+          store_a8<kPasses == 3>(m.a_hi + kc * kAChunk, m.a_lo + kc * kAChunk, row, h * 32 + g * 8, y);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(m.bars + A_FULL + kc);
+      }
+    };
+    auto epilogue = [&](int it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / tiles_per_img, p0 = (tile % tiles_per_img) * 128;
+      const uint32_t buf = it & 1;
+      mbar_wait(m.bars + ACC_FULL + buf, (it >> 1) & 1);
+      tc_fence_after();
+      conv_epilogue(a, m, tmem + buf * 256, b, p0, warp, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(m.bars + ACC_EMPTY + buf);
+      if (a.rgb_w) {
+        rows_barrier();
+        rgb_finish(a, m, b, p0, warp, lane);
+        rows_barrier();
+      }
+    };
+    if (my_tiles > 0) prologue(0);
+    for (int it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles) prologue(it + 1);
+      epilogue(it);
+    }
+    rows_barrier();
+    flush_stats(a, m);
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 256);
+      MmaPipe p;
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(m.bars + ACC_EMPTY + buf, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(m.bars + A_FULL + kc, it & 1);
+          tc_fence_after();
+          mma_chunk<kPasses>(m, p, tmem + buf * 256, smem_u32(m.a_hi + kc * kAChunk), smem_u32(m.a_lo + kc * kAChunk),
+                             idesc, kc > 0);
+          umma_commit(m.bars + A_EMPTY + kc);
+        }
+        umma_commit(m.bars + ACC_FULL + buf);
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const uint8_t* imgs[1] = {a.wimg};
+      const int ns[1] = {8};
+      producer_loop<kPasses>(m, imgs, ns, 1, my_tiles);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// pixel-style variant (sequential phases per tile)
+// ------------------------------------------------------------------------------------------
+// PyTorch's bilinear source index (align_corners=False): src = max(scale*(dst+0.5)-0.5, 0)
+__device__ __forceinline__ void bilin(int dst, int in_size, float scale, int& i0, int& i1, float& l0, float& l1) {
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+  l0 = 1.f - l1;
+}
+
+template <int kPasses>
+__global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const SynSmem m = carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) {
+    m.tab_g1[i] = a.scsh[i];
+    m.tab_g0[i] = a.scsh[kC + i];
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) m.tab_bgb[i] = a.bgb[i];
+  init_common(a, m, warp);
+  const uint32_t tmem = *m.tmem_slot;
+  const int tiles_per_img = (a.HW + 127) / 128;
+  const int num_tiles = a.B * tiles_per_img;
+  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const float sy = static_cast<float>(a.Rh) / static_cast<float>(a.Hg);
+  const float sx = static_cast<float>(a.Rw) / static_cast<float>(a.Wg);
+
+  if (warp < 8) {
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / tiles_per_img, p0 = (tile % tiles_per_img) * 128;
+      const int pix = p0 + row;
+      const bool valid = pix < a.HW;
+      // ---- phase 0: A1 = relu(bilinear(P_lr)) for this warp's half of the 128 shared channels
+      {
+        const int py = valid ? pix / a.Wg : 0, px = valid ? pix % a.Wg : 0;
+        int y0, y1, x0, x1;
+        float ly0, ly1, lx0, lx1;
+        bilin(py, a.Rh, sy, y0, y1, ly0, ly1);
+        bilin(px, a.Rw, sx, x0, x1, lx0, lx1);
+        const float* base = a.p_lr + static_cast<long>(b) * a.Rh * a.Rw * a.p_stride;
+        const float4* n00 = reinterpret_cast<const float4*>(base + (static_cast<long>(y0) * a.Rw + x0) * a.p_stride);
+        const float4* n01 = reinterpret_cast<const float4*>(base + (static_cast<long>(y0) * a.Rw + x1) * a.p_stride);
+        const float4* n10 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * a.Rw + x0) * a.p_stride);
+        const float4* n11 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * a.Rw + x1) * a.p_stride);
+        const float4* pb = a.p_bias ? reinterpret_cast<const float4*>(a.p_bias + static_cast<long>(b) * 128) : nullptr;
+        // this warp covers shared channels [h*64, h*64+64) == K chunk h of A1
+#pragma unroll 2
+        for (int g = 0; g < 8; ++g) {
+          float y[8];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int f4 = h * 16 + g * 2 + u;
+            const float4 v00 = __ldg(n00 + f4), v01 = __ldg(n01 + f4), v10 = __ldg(n10 + f4), v11 = __ldg(n11 + f4);
+            // same association as upsample_bilinear2d: ly0*(lx0*a + lx1*b) + ly1*(lx0*c + lx1*d)
+            y[u * 4 + 0] = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+            y[u * 4 + 1] = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+            y[u * 4 + 2] = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+            y[u * 4 + 3] = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+            if (pb) {
+              const float4 c4 = __ldg(pb + f4);
+              y[u * 4 + 0] += c4.x; y[u * 4 + 1] += c4.y; y[u * 4 + 2] += c4.z; y[u * 4 + 3] += c4.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = valid ? fmaxf(y[j], 0.f) : 0.f;
+          store_a8<kPasses == 3>(m.a_hi + h * kAChunk, m.a_lo + h * kAChunk, row, g * 8, y);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(m.bars + A1_FULL);
+      }
+      // ---- phase 1: gamma/beta accumulators -> y = lrelu(BN(x)*(1+gamma)+beta) -> A (4 chunks)
+      mbar_wait(m.bars + G1_FULL, it & 1);
+      tc_fence_after();
+      const float* xp = a.x + static_cast<long>(b) * a.x_bstride + pix;
+#pragma unroll 1
+      for (int kc = 0; kc < 4; ++kc) {
+        const int c0 = kc * 64 + h * 32;
+        const uint32_t col = (kc >> 1) * 256 + (kc & 1) * 128 + h * 32;
+        uint32_t gr[32], br[32];
+        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + col, gr);
+        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + col + 64, br);
+        float xv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xv[j] = valid ? __ldg(xp + static_cast<long>(c0 + j) * a.HW) : 0.f;
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int jj = g * 8 + j;
+            const int c = c0 + jj;
+            const float gam = __uint_as_float(gr[jj]) + m.tab_bgb[col + jj];        // 1 + gamma
+            const float bet = __uint_as_float(br[jj]) + m.tab_bgb[col + 64 + jj];   // beta
+            const float xn = fmaf(xv[jj], m.tab_g1[c], m.tab_g0[c]);
+            y[j] = lrelu02(fmaf(xn, gam, bet));
+          }
+          store_a8<kPasses == 3>(m.a_hi + kc * kAChunk, m.a_lo + kc * kAChunk, row, h * 32 + g * 8, y);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(m.bars + Y_FULL);
+      // ---- phase 2: conv accumulator
+      mbar_wait(m.bars + ACC_FULL, it & 1);
+      tc_fence_after();
+      conv_epilogue(a, m, tmem, b, p0, warp, lane);
+      tc_fence_before();
+      rows_barrier();
+      if (a.rgb_w) {
+        rgb_finish(a, m, b, p0, warp, lane);
+        rows_barrier();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(m.bars + ACC_EMPTY);
+    }
+    rows_barrier();
+    flush_stats(a, m);
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 256);
+      MmaPipe p;
+      for (int it = 0; it < my_tiles; ++it) {
+        // TMEM (both halves) is free once the previous tile's conv epilogue has drained
+        mbar_wait(m.bars + ACC_EMPTY, (it & 1) ^ 1);
+        mbar_wait(m.bars + A1_FULL, it & 1);
+        tc_fence_after();
+        for (int nb = 0; nb < 2; ++nb)
+          for (int kc = 0; kc < 2; ++kc)
+            mma_chunk<kPasses>(m, p, tmem + nb * 256, smem_u32(m.a_hi + kc * kAChunk), smem_u32(m.a_lo + kc * kAChunk),
+                               idesc, kc > 0);
+        umma_commit(m.bars + G1_FULL);
+        mbar_wait(m.bars + Y_FULL, it & 1);
+        tc_fence_after();
+        for (int kc = 0; kc < 4; ++kc)
+          mma_chunk<kPasses>(m, p, tmem, smem_u32(m.a_hi + kc * kAChunk), smem_u32(m.a_lo + kc * kAChunk), idesc, kc > 0);
+        umma_commit(m.bars + ACC_FULL);
+      }
+    }
+  } else {
+    if (lane == 0) {
+      // gamma/beta image: [2 nblocks][2 kchunks][hi,lo] = 8 stages, then the conv image: 8 stages
+      const uint8_t* imgs[2] = {a.wgb, a.wimg};
+      const int ns[2] = {8, 8};
+      producer_loop<kPasses>(m, imgs, ns, 2, my_tiles);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm finalisation: batch (or running) statistics -> scale/shift (+ fused per-sample modulation)
+// ------------------------------------------------------------------------------------------
+// nn.SyncBatchNorm semantics (map3d_layers.py:162): biased variance for normalisation, unbiased for
+// the running estimate, momentum 0.1, eps 1e-5.
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count_in, const double* __restrict__ count_ptr,
+                                   const float* __restrict__ weight,
+                                   const float* __restrict__ bias, float* running_mean, float* running_var,
+                                   int training, float eps, float momentum, const float* __restrict__ gb, int B,
+                                   float* __restrict__ scsh, float* __restrict__ mod) {
+  const int c = threadIdx.x;
+  float mean, var;
+  const double count = count_ptr ? count_ptr[0] : count_in;
+  if (training) {
+    const double mu = stats[c] / count;
+    double v = stats[kC + c] / count - mu * mu;
+    v = v < 0 ? 0 : v;
+    mean = static_cast<float>(mu);
+    var = static_cast<float>(v);
+    if (running_mean) {
+      const double unb = count > 1 ? v * count / (count - 1) : v;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unb);
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float sc = weight[c] * rsqrtf(var + eps);
+  const float sh = bias[c] - mean * sc;
+  if (scsh) {
+    scsh[c] = sc;
+    scsh[kC + c] = sh;
+  }
+  if (mod && gb) {
+    for (int b = 0; b < B; ++b) {
+      const float G = gb[(static_cast<long>(b) * 2 + 0) * kC + c];   // 1 + gamma
+      const float Bt = gb[(static_cast<long>(b) * 2 + 1) * kC + c];  // beta
+      mod[(static_cast<long>(b) * 2 + 0) * kC + c] = sc * G;
+      mod[(static_cast<long>(b) * 2 + 1) * kC + c] = fmaf(sh, G, Bt);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// synthesis input x0 = sin(W [i, j]^T + b)  (map3d_layers.py:260-275), shared by the whole batch,
+// with its BatchNorm statistics.
+// ------------------------------------------------------------------------------------------
+__global__ void synth_input_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                   const float* __restrict__ ic, const float* __restrict__ jc, int Hg, int Wg,
+                                   float* __restrict__ x0, double* __restrict__ stats, double batch_mult) {
+  // grid: (ceil(HW/256), C); one channel per blockIdx.y
+  const int c = blockIdx.y;
+  const int HW = Hg * Wg;
+  const float w0 = w[c * 2 + 0], w1 = w[c * 2 + 1], bb = bias[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const float v = sinf(fmaf(w1, jc[p % Wg], fmaf(w0, ic[p / Wg], bb)));
+    x0[static_cast<long>(c) * HW + p] = v;
+    s1 += v;
+    s2 += v * v;
+  }
+  __shared__ float r1[8], r2[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0 && stats) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) { t1 += r1[i]; t2 += r2[i]; }
+    atomicAdd(stats + c, static_cast<double>(t1) * batch_mult);
+    atomicAdd(stats + kC + c, static_cast<double>(t2) * batch_mult);
+  }
+}
+
+}  // namespace hg
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float* scsh, const float* p_lr,
+                  long p_stride, const float* p_bias, const void* wgb, const float* bgb, const void* wimg, const float* bias, const float* skip,
+                  float* out, double* stats, const float* rgb_w, const float* rgb_b, const float* rgb_in,
+                  float* rgb_out, int B, int C, int Hg, int Wg, int Rh, int Rw, int passes, void* stream) {
+  HG_REQUIRE(C == hg::kC, "hg_spade_conv: only %d channels are supported (got %d)", hg::kC, C);
+  HG_REQUIRE(x && wimg && bias && out, "hg_spade_conv: null pointer");
+  HG_REQUIRE((mod != nullptr) != (p_lr != nullptr), "hg_spade_conv: give exactly one of mod (const style) / p_lr (pixel style)");
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_spade_conv: passes must be 1 or 3");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_spade_conv: bad shape");
+  HG_REQUIRE(!rgb_w || (rgb_b && rgb_out), "hg_spade_conv: rgb_b / rgb_out missing");
+  if (p_lr) {
+    HG_REQUIRE(scsh && wgb && bgb && Rh > 0 && Rw > 0, "hg_spade_conv: pixel-style arguments missing");
+    HG_REQUIRE((reinterpret_cast<uintptr_t>(p_lr) & 15) == 0 && p_stride >= 128 && (p_stride & 3) == 0,
+               "hg_spade_conv: p_lr must be 16-byte aligned with a row stride >= 128 that is a multiple of 4");
+    HG_REQUIRE(!p_bias || (reinterpret_cast<uintptr_t>(p_bias) & 15) == 0, "hg_spade_conv: p_bias must be 16-byte aligned");
+  }
+  hg::SpadeArgs a{x, x_bstride, mod, scsh, p_lr, p_stride, p_bias, static_cast<const uint8_t*>(wgb), bgb,
+                  static_cast<const uint8_t*>(wimg), bias, skip, out, stats, rgb_w, rgb_b, rgb_in, rgb_out,
+                  B, Hg * Wg, Hg, Wg, Rh, Rw};
+  const int tiles = B * ((Hg * Wg + 127) / 128);
+  const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
+  auto st = static_cast<cudaStream_t>(stream);
+#define HG_LAUNCH(KERNEL)                                                                                         \
+  do {                                                                                                            \
+    cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kSynSmemBytes); \
+    if (e != cudaSuccess) { hg::set_error("hg_spade_conv: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; } \
+    KERNEL<<<grid, hg::kSynThreads, hg::kSynSmemBytes, st>>>(a);                                                  \
+  } while (0)
+  if (mod) {
+    if (passes == 3) HG_LAUNCH(hg::spade_const_kernel<3>); else HG_LAUNCH(hg::spade_const_kernel<1>);
+  } else {
+    if (passes == 3) HG_LAUNCH(hg::spade_pixel_kernel<3>); else HG_LAUNCH(hg::spade_pixel_kernel<1>);
+  }
+#undef HG_LAUNCH
+  return hg::check_launch("hg_spade_conv");
+}
+
+int hg_bn_finalize(const double* stats, double count, const double* count_dev, const float* weight, const float* bias, float* running_mean,
+                   float* running_var, int training, float eps, float momentum, const float* gb, int B, int C,
+                   float* scsh, float* mod, void* stream) {
+  HG_REQUIRE(C == hg::kC, "hg_bn_finalize: only %d channels are supported (got %d)", hg::kC, C);
+  HG_REQUIRE(weight && bias && (scsh || mod), "hg_bn_finalize: null pointer");
+  HG_REQUIRE(training ? (stats != nullptr && (count > 0 || count_dev)) : (running_mean && running_var),
+             "hg_bn_finalize: statistics missing");
+  hg::bn_finalize_kernel<<<1, hg::kC, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, count, count_dev, weight, bias, running_mean, running_var, training, eps, momentum, gb, B, scsh, mod);
+  return hg::check_launch("hg_bn_finalize");
+}
+
+int hg_synth_input(const float* w, const float* bias, const float* ic, const float* jc, int C, int Hg, int Wg,
+                   float* x0, double* stats, int batch, void* stream) {
+  HG_REQUIRE(C == hg::kC, "hg_synth_input: only %d channels are supported (got %d)", hg::kC, C);
+  HG_REQUIRE(w && bias && ic && jc && x0, "hg_synth_input: null pointer");
+  const int HW = Hg * Wg;
+  int bx = (HW + 255) / 256;
+  if (bx > 32) bx = 32;
+  dim3 grid(bx, C);
+  hg::synth_input_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, bias, ic, jc, Hg, Wg, x0, stats,
+                                                                              static_cast<double>(batch));
+  return hg::check_launch("hg_synth_input");
+}
+
+}  // extern "C"
