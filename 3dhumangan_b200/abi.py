@@ -31,6 +31,8 @@ SIGNATURES = {
     "hg_bn_finalize": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hg_synth_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "hg_render_weight_blob_bytes": (c_size_t, []),
+    "hg_render_mlp": (c_int, [c_void_p] * 12 + [c_int] * 4 + [c_float] + [c_int] * 4 + [c_void_p]),
     "hg_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
@@ -179,3 +181,20 @@ def synth_input(w, bias, ic, jc, x0, stats, batch):
         check(lib().hg_synth_input(ptr(w), ptr(bias), ptr(ic), ptr(jc), C, ic.numel(), jc.numel(), ptr(x0), ptr(stats),
                                    batch, stream()), "hg_synth_input")
     return x0
+
+
+def render_mlp(rec, z_vals, film, wblob, w_sigma, w_rgb, b_feat, heads_b, *, B, R, S, noise=None, noise_std=0.0,
+               white_back=False, last_back=False, clamp_mode="relu", passes=3, want_weights=False, raw=False):
+    """Fused FiLM-SIREN + ray integration (csrc/render.cu) -> ray_out [B,R,260] (256 feat, 3 rgb, depth)."""
+    dev = rec.device
+    ray_out = None if raw else torch.empty(B, R, 260, dtype=torch.float32, device=dev)
+    raw_out = torch.empty(B, R * S, 260, dtype=torch.float32, device=dev) if raw else None
+    weights = torch.empty(B, R * S, dtype=torch.float32, device=dev) if want_weights else None
+    if clamp_mode not in ("relu", "softplus"):
+        raise RuntimeError("Need to choose clamp mode")          # volume_rendering.py:31
+    with torch.cuda.device_of(rec):
+        check(lib().hg_render_mlp(ptr(rec), ptr(z_vals), ptr(noise), ptr(film), ptr(wblob), ptr(w_sigma), ptr(w_rgb),
+                                  ptr(b_feat), ptr(heads_b), ptr(ray_out), ptr(weights), ptr(raw_out), B, R, S, 256, float(noise_std),
+                                  int(bool(white_back)), int(bool(last_back)), int(clamp_mode == "softplus"), passes,
+                                  stream()), "hg_render_mlp")
+    return (raw_out if raw else ray_out), weights

@@ -51,6 +51,7 @@ struct RenderArgs {
   const float* heads_b;  // [4]: b_sigma, b_rgb[3]
   float* ray_out;        // [B,R,260]
   float* weights_out;    // [B,N] or null
+  float* raw_out;        // [B,N,260] per-point (rgb 3, feat 256, sigma) instead of compositing, or null
   int B, R, S;           // rays per image, samples per ray (power of two <= 128)
   float noise_std;
   int white_back, last_back, clamp_softplus;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
           }
           store_a8<kPasses == 3>(m.a_hi, m.a_lo, row, k0, x);
         }
-        if (h == 0) m.zs[row] = valid ? a.z_vals[gp] : 0.f;
+        if (h == 0) m.zs[row] = (valid && a.z_vals) ? a.z_vals[gp] : 0.f;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(m.bars + RA_FULL + 0);
@@ -285,6 +286,31 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
       mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
       film_epilogue<kPasses, 2>(m, accA, 6, warp, lane, false);
 
+      if (a.raw_out) {
+        // ---- per-point outputs of COORDCONCATSIREN.forward (modulated.py:70-73): [rgb, feat, sigma]
+        ren_rows_barrier();
+        float* po = a.raw_out + gp * kRayOut;
+        if (h == 0 && valid) {
+          po[259] = m.part[row * 4] + m.part[(128 + row) * 4] + a.heads_b[0];
+          for (int j = 0; j < 3; ++j) {
+            const float dot = m.part[row * 4 + 1 + j] + m.part[(128 + row) * 4 + 1 + j] + a.heads_b[1 + j];
+            po[j] = 1.f / (1.f + expf(-dot));
+          }
+        }
+        mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+#pragma unroll 1
+        for (int kc = 0; kc < 4; ++kc) {
+          const int c0 = kc * 64 + h * 32;
+          uint32_t raw[32];
+          tmem_ld32(accB + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
+          tmem_ld_wait();
+          if (valid)
+            for (int j = 0; j < 32; ++j) po[3 + c0 + j] = __uint_as_float(raw[j]) + m.b_feat[c0 + j];
+        }
+        tc_fence_before();
+        ren_rows_barrier();
+        continue;
+      }
       // ---- compositing weights (volume_rendering.py:12-38); overlaps the feature GEMM
       ren_rows_barrier();
       float alpha = 0.f;
@@ -462,17 +488,18 @@ size_t hg_render_weight_blob_bytes(void) { return static_cast<size_t>(hg::kWeigh
 
 int hg_render_mlp(const float* rec, const float* z_vals, const float* noise, const float* film, const void* wblob,
                   const float* w_sigma, const float* w_rgb, const float* b_feat, const float* heads_b, float* ray_out,
-                  float* weights_out, int B, int R, int S, int hidden, float noise_std, int white_back, int last_back,
+                  float* weights_out, float* raw_out, int B, int R, int S, int hidden, float noise_std, int white_back, int last_back,
                   int clamp_softplus, int passes, void* stream) {
   HG_REQUIRE(hidden == hg::kRH, "hg_render_mlp: only hidden_dim == %d is supported (got %d)", hg::kRH, hidden);
-  HG_REQUIRE(rec && z_vals && film && wblob && w_sigma && w_rgb && b_feat && heads_b && ray_out, "hg_render_mlp: null pointer");
+  HG_REQUIRE(rec && film && wblob && w_sigma && w_rgb && b_feat && heads_b, "hg_render_mlp: null pointer");
+  HG_REQUIRE(raw_out || (ray_out && z_vals), "hg_render_mlp: need ray_out + z_vals (compositing) or raw_out (per-point)");
   HG_REQUIRE(B > 0 && R > 0, "hg_render_mlp: bad shape");
   HG_REQUIRE(S >= 2 && S <= 128 && (S & (S - 1)) == 0, "hg_render_mlp: samples per ray must be a power of two in [2,128] (got %d)", S);
   HG_REQUIRE(passes == 1 || passes == 3, "hg_render_mlp: passes must be 1 or 3");
   HG_REQUIRE((reinterpret_cast<uintptr_t>(rec) & 15) == 0 && (reinterpret_cast<uintptr_t>(wblob) & 15) == 0,
              "hg_render_mlp: rec / wblob must be 16-byte aligned");
   hg::RenderArgs a{rec, z_vals, noise, film, static_cast<const uint8_t*>(wblob), w_sigma, w_rgb, b_feat, heads_b,
-                   ray_out, weights_out, B, R, S, noise_std, white_back, last_back, clamp_softplus};
+                   ray_out, weights_out, raw_out, B, R, S, noise_std, white_back, last_back, clamp_softplus};
   const int rpt = 128 / S;
   const int tiles = B * ((R + rpt - 1) / rpt);
   const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
