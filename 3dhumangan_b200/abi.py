@@ -33,6 +33,8 @@ SIGNATURES = {
     "hg_synth_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "hg_render_weight_blob_bytes": (c_size_t, []),
     "hg_render_mlp": (c_int, [c_void_p] * 12 + [c_int] * 4 + [c_float] + [c_int] * 4 + [c_void_p]),
+    "hg_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    "hg_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 14 + [c_float, c_void_p]),
     "hg_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
@@ -58,6 +60,26 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = lib().hg_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+LAUNCHES = 0        # kernels launched through this binding (bench.py reports it as gpu_launches)
+TIMING = None       # when a list: (name, start_event, end_event) per launch, recorded on the current stream
+
+
+def call(name, *args):
+    """Invoke one launching entry point: count it, optionally bracket it with CUDA events, raise on error."""
+    global LAUNCHES
+    fn = getattr(lib(), name)
+    if TIMING is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        TIMING.append((name, s, e))
+    else:
+        rc = fn(*args)
+    LAUNCHES += 1
+    check(rc, name)
 
 
 def ptr(t):
@@ -98,8 +120,8 @@ def pack_weight(W, Nb=None, scale=1.0, scale_dev=None, out=None):
     if out is None:
         out = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
     with torch.cuda.device_of(W):
-        check(lib().hg_pack_weight(c_void_p(W.data_ptr()), N, K, W.stride(0), ptr(scale_dev), float(scale), Nb,
-                                   ptr(out), out.numel(), stream()), "hg_pack_weight")
+        call("hg_pack_weight", c_void_p(W.data_ptr()), N, K, W.stride(0), ptr(scale_dev), float(scale), Nb,
+                                   ptr(out), out.numel(), stream())
     return out, Nb
 
 
@@ -110,8 +132,8 @@ def linear(X, Wimg, Nb, N, bias=None, passes=3, out=None):
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=X.device)
     with torch.cuda.device_of(X):
-        check(lib().hg_linear(c_void_p(X.data_ptr()), X.stride(0), M, K, ptr(Wimg), Nb, N, ptr(bias),
-                              ptr(out), out.stride(0), passes, stream()), "hg_linear")
+        call("hg_linear", c_void_p(X.data_ptr()), X.stride(0), M, K, ptr(Wimg), Nb, N, ptr(bias),
+                              ptr(out), out.stride(0), passes, stream())
     return out
 
 
@@ -122,7 +144,7 @@ def vertex_ik(fk, lbs):
     lbs = lbs.float().contiguous()
     out = torch.empty(B, V, 16, dtype=torch.float32, device=fk.device)
     with torch.cuda.device_of(fk):
-        check(lib().hg_vertex_ik(ptr(fk), ptr(lbs), B, V, ptr(out), stream()), "hg_vertex_ik")
+        call("hg_vertex_ik", ptr(fk), ptr(lbs), B, V, ptr(out), stream())
     return out
 
 
@@ -148,9 +170,9 @@ def geo_features(cond_vertices, tpose, skeletons, vik, *, input_scaler, legacy_m
     d2 = torch.empty(B, N, dtype=torch.float32, device=dev) if want_nearest else None
     keep = [f(t) for t in (xs, ys, zs, focals, scales, cam2world, jitter, points_in, skeletons, cond_vertices, tpose, vik)]
     with torch.cuda.device_of(rec):
-        check(lib().hg_geo_features(*[ptr(t) for t in keep], B, Rw, Rh, S, V, N, float(input_scaler),
+        call("hg_geo_features", *[ptr(t) for t in keep], B, Rw, Rh, S, V, N, float(input_scaler),
                                     int(bool(legacy_mode)), ptr(rec), ptr(z_vals), ptr(pts), ptr(near), ptr(d2),
-                                    stream()), "hg_geo_features")
+                                    stream())
     return {"rec": rec, "z_vals": z_vals, "points": pts, "nearest": near, "nearest_d2": d2}
 
 
@@ -159,27 +181,27 @@ def spade_conv(x, x_bstride, wimg, bias, out, *, B, Hg, Wg, mod=None, scsh=None,
                Rh=0, Rw=0, passes=3):
     """One SPADE half-block (see csrc/synth.cu).  All tensors fp32 CUDA; `stats` is a float64 view [>=512]."""
     with torch.cuda.device_of(out):
-        check(lib().hg_spade_conv(ptr(x), int(x_bstride), ptr(mod), ptr(scsh), ptr(p_lr), int(p_stride), ptr(p_bias),
+        call("hg_spade_conv", ptr(x), int(x_bstride), ptr(mod), ptr(scsh), ptr(p_lr), int(p_stride), ptr(p_bias),
                                   ptr(wgb), ptr(bgb), ptr(wimg), ptr(bias), ptr(skip), ptr(out), ptr(stats),
                                   ptr(rgb_w), ptr(rgb_b), ptr(rgb_in), ptr(rgb_out), B, 256, Hg, Wg, Rh, Rw, passes,
-                                  stream()), "hg_spade_conv")
+                                  stream())
     return out
 
 
 def bn_finalize(stats, weight, bias, running_mean, running_var, training, *, count=0.0, count_dev=None, gb=None, B=0,
                 scsh=None, mod=None, eps=1e-5, momentum=0.1):
     with torch.cuda.device_of(weight):
-        check(lib().hg_bn_finalize(ptr(stats), float(count), ptr(count_dev), ptr(weight), ptr(bias), ptr(running_mean),
+        call("hg_bn_finalize", ptr(stats), float(count), ptr(count_dev), ptr(weight), ptr(bias), ptr(running_mean),
                                    ptr(running_var), int(bool(training)), float(eps), float(momentum), ptr(gb), B, 256,
-                                   ptr(scsh), ptr(mod), stream()), "hg_bn_finalize")
+                                   ptr(scsh), ptr(mod), stream())
 
 
 def synth_input(w, bias, ic, jc, x0, stats, batch):
     """x0[C,HW] = sin(w[:,0]*i + w[:,1]*j + b) and batch-multiplied BN statistics (map3d_layers.py:260-275)."""
     C = w.shape[0]
     with torch.cuda.device_of(x0):
-        check(lib().hg_synth_input(ptr(w), ptr(bias), ptr(ic), ptr(jc), C, ic.numel(), jc.numel(), ptr(x0), ptr(stats),
-                                   batch, stream()), "hg_synth_input")
+        call("hg_synth_input", ptr(w), ptr(bias), ptr(ic), ptr(jc), C, ic.numel(), jc.numel(), ptr(x0), ptr(stats),
+                                   batch, stream())
     return x0
 
 
@@ -193,8 +215,8 @@ def render_mlp(rec, z_vals, film, wblob, w_sigma, w_rgb, b_feat, heads_b, *, B, 
     if clamp_mode not in ("relu", "softplus"):
         raise RuntimeError("Need to choose clamp mode")          # volume_rendering.py:31
     with torch.cuda.device_of(rec):
-        check(lib().hg_render_mlp(ptr(rec), ptr(z_vals), ptr(noise), ptr(film), ptr(wblob), ptr(w_sigma), ptr(w_rgb),
+        call("hg_render_mlp", ptr(rec), ptr(z_vals), ptr(noise), ptr(film), ptr(wblob), ptr(w_sigma), ptr(w_rgb),
                                   ptr(b_feat), ptr(heads_b), ptr(ray_out), ptr(weights), ptr(raw_out), B, R, S, 256, float(noise_std),
                                   int(bool(white_back)), int(bool(last_back)), int(clamp_mode == "softplus"), passes,
-                                  stream()), "hg_render_mlp")
+                                  stream())
     return (raw_out if raw else ray_out), weights

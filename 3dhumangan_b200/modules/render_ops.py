@@ -89,3 +89,37 @@ def render_forward(P, freq, phase, cond, cfg, u, noise, *, passes=3, wblob=None,
         noise_std=cfg["nerf_noise"], white_back=cfg.get("white_back", False), last_back=cfg.get("last_back", False),
         clamp_mode=cfg["clamp_mode"], passes=passes, want_weights=want_weights)
     return {"ray_out": ray_out, "z_vals": geo["z_vals"], "weights": weights, "nearest": geo["nearest"]}
+
+
+@torch.no_grad()
+def siren_points(module, pts, freq, phase, geo, dirs, input_scaler=1.0, geo_scaler=1.0, passes=3):
+    """Stand-alone COORDCONCATSIREN.forward: [B,N,3], [B,4H], [B,4H], [B,N,G], [B,N,3] -> [B,N,3+F+1].
+    The view direction must be constant over all points (it is folded into the colour layer's offset)."""
+    abi.require_device()
+    squeeze = pts.dim() < 3
+    if squeeze:
+        pts, geo, dirs = pts.unsqueeze(1), geo.unsqueeze(1), dirs.unsqueeze(1)
+    B, N, _ = pts.shape
+    G = geo.shape[-1]
+    d0 = dirs.reshape(-1, 3)[0]
+    if not bool((dirs.reshape(-1, 3) == d0).all()):
+        raise RuntimeError("hg3d: COORDCONCATSIREN.forward needs one view direction for all points "
+                           "(lock_view_dependence=True in every shipped curriculum)")
+    P = {"neural_field." + k: v for k, v in list(module.named_parameters()) + list(module.named_buffers())}
+    rec = torch.zeros(B, N, 36, dtype=torch.float32, device=pts.device)
+    rec[..., :3] = pts.float() * input_scaler
+    rec[..., 3:3 + G] = geo.float() * geo_scaler
+    wblob = pack_render_weights(P, geo_dim=G)
+    film = film_table(P, freq, phase, locked_dir=tuple(float(v) for v in d0))
+    g = lambda n: P["neural_field." + n]
+    heads_b = torch.cat([g("sigma_layer.bias").reshape(1), g("color_layer_linear.bias").reshape(3)]).float().contiguous()
+    S = 32
+    Np = (N + S - 1) // S * S
+    if Np != N:
+        rec = torch.cat([rec, torch.zeros(B, Np - N, 36, dtype=torch.float32, device=pts.device)], 1)
+    raw, _ = abi.render_mlp(rec.contiguous(), None, film, wblob, g("sigma_layer.weight").reshape(-1).float().contiguous(),
+                            g("color_layer_linear.weight").float().contiguous(),
+                            g("feature_layer_linear.bias").float().contiguous(), heads_b, B=B, R=Np // S, S=S,
+                            passes=passes, raw=True)
+    out = raw[:, :N]
+    return out.squeeze(1) if squeeze else out

@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the 3DHumanGAN generator hot path on B200 (and its CPU reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C2native|C5|tiny]
+
+One "step" = one `Map3DGenerator.forward` over one batch of synthetic latents + random SMPL-like poses
+(train-mode BatchNorm, as the reference's trainer runs the generator) at BASELINE.json configs[1]:
+batch 8 per GPU, 512x512, render 96x96, 32 samples per ray.  Prints ONE JSON line (rank 0):
+
+  value        images/s, whole job, inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e          images/s through the public module API with pinned HOST inputs (latents + pose conditions
+               copied H2D every step) and the generated images read back D2H every step
+  roofline     dominant kernel: algorithmic bytes (or FLOPs) per launch / mean CUDA-event duration vs the
+               measured peak in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (port of the reference's PyTorch path) on the host cores, bounded sample
+  --impl reference   times that CPU arm on its own (rank 0 only)
+
+Multi-GPU (`torchrun ... bench.py --gpus N`): weak scaling, 8 images per rank, SyncBatchNorm statistics
+all-reduced over NCCL inside the forward (18 small all-reduces), no other data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images_per_sec_G_fwd_512x512"
+UNIT = "images/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    return dict(FALLBACK_PEAKS, _source="fallback")
+
+
+def workload_cfg(pkg, name):
+    cfg = pkg.configs.baseline_config(name)
+    cfg["nerf_noise"] = 0.0
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (bounded sample)
+# --------------------------------------------------------------------------------------------------
+def cpu_sample(pkg, name, steps, warmup, sample_div=4):
+    """Times `oracle.port.generator_forward` for ONE image on a 1/sample_div^2 sub-grid of the workload
+    (gen and render resolutions divided by sample_div, same 32 samples per ray, same dims) and scales
+    by the pixel ratio.  Returns (images_per_sec, cores, description)."""
+    from oracle import port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = workload_cfg(pkg, name)
+    full_px = cfg["gen_height"] * cfg["gen_width"]
+    cfg.update(gen_height=cfg["gen_height"] // sample_div, gen_width=cfg["gen_width"] // sample_div,
+               render_height=cfg["render_height"] // sample_div, render_width=cfg["render_width"] // sample_div)
+    frac = cfg["gen_height"] * cfg["gen_width"] / full_px
+    params = port.init_generator_params(cfg, seed=0)
+    cond = pkg.synthetic.make_conditions(1, seed=1)
+    z = torch.randn(1, cfg["latent_dim"], generator=torch.Generator().manual_seed(2))
+    R, S = cfg["render_height"] * cfg["render_width"], cfg["num_steps"]
+    torch.manual_seed(3)
+    u, noise = pkg.rng.draw_render_noise(1, R, S, "cpu", cfg["sample_dist"])
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            port.generator_forward(params, z, cond, cfg, u, noise, training=True)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    desc = (f"oracle.port.generator_forward, 1 image on a {cfg['gen_height']}x{cfg['gen_width']} / render "
+            f"{cfg['render_height']}x{cfg['render_width']}x{S} sub-grid ({frac:.4f} of the workload's pixels), "
+            f"{t:.2f} s per pass, scaled by pixel count; fp32, torch {torch.__version__}, {cores} threads")
+    return frac / t, cores, desc, t
+
+
+def run_reference(args, pkg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    ips, cores, desc, t = cpu_sample(pkg, args.workload, steps, warm)
+    cfg = workload_cfg(pkg, args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": describe(cfg, args.workload, 8), "timing": "host wall clock, bounded sample"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def describe(cfg, name, batch):
+    return (f"{name}: Map3DGenerator.forward, batch {batch}/GPU, gen {cfg['gen_height']}x{cfg['gen_width']}, render "
+            f"{cfg['render_height']}x{cfg['render_width']}, {cfg['num_steps']} samples/ray, hidden {cfg['hidden_dim']}, "
+            f"train-mode BatchNorm, random init, synthetic SMPL-like poses")
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r.split(", ") for r in open(self.path).read().strip().splitlines() if r.count(",") >= 6]
+        os.unlink(self.path)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].strip().lower() == "active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+def kernel_costs(cfg, B):
+    """Algorithmic work per launch of each kernel (DESIGN.md 'Kernels'): FLOPs of the fp32-equivalent
+    contraction and compulsory HBM bytes."""
+    HW = cfg["gen_height"] * cfg["gen_width"]
+    R, S = cfg["render_height"] * cfg["render_width"], cfg["num_steps"]
+    C = 256
+    act = B * HW * C * 4
+    return {
+        "hg_spade_conv": {"flops": 2.0 * B * HW * C * C, "bytes": 2.0 * act},           # read x + write out (skip/rgb extra)
+        "hg_render_mlp": {"flops": 938496.0 * B * R * S, "bytes": B * R * S * (36 + 1) * 4.0 + B * R * 260 * 4.0},
+        "hg_geo_features": {"flops": 8.0 * B * R * S * 6890, "bytes": B * R * S * (36 + 1 + 1) * 4.0},
+    }
+
+
+def run_gpu(args, pkg):
+    import torch.distributed as dist
+    abi = importlib.import_module("3dhumangan_b200.abi")
+    gen = importlib.import_module("3dhumangan_b200.modules.generator")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    abi.require_device()
+
+    cfg = workload_cfg(pkg, args.workload)
+    B = args.batch
+    torch.manual_seed(0)
+    G = gen.Map3DGenerator(**cfg).to(dev)
+    G.set_device(dev)
+    G.train()
+    passes_mode = args.precision
+    kw = dict(cfg, hg_precision=passes_mode)
+
+    # host (pinned) inputs: per-rank latents and poses
+    cond_h = {k: v.pin_memory() for k, v in pkg.synthetic.make_conditions(B, seed=1 + rank).items()}
+    z_h = torch.randn(B, cfg["latent_dim"], generator=torch.Generator().manual_seed(2 + rank)).pin_memory()
+    out_h = torch.empty(B, 3, cfg["gen_height"], cfg["gen_width"]).pin_memory()
+    h2d = z_h.numel() * 4 + sum(v.numel() * v.element_size() for v in cond_h.values())
+    d2h = out_h.numel() * 4
+    cond_d = {k: v.to(dev) for k, v in cond_h.items()}
+    z_d = z_h.to(dev)
+
+    def step_resident():
+        with torch.no_grad():
+            return G(z_d, cond_d, **kw)["rgbs"]
+
+    def step_e2e():
+        with torch.no_grad():
+            c = {k: v.to(dev, non_blocking=True) for k, v in cond_h.items()}
+            z = z_h.to(dev, non_blocking=True)
+            out_h.copy_(G(z, c, **kw)["rgbs"], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    abi.TIMING = []
+    launches0 = abi.LAUNCHES
+    ms_total = timed(step_resident, args.steps)
+    launches = abi.LAUNCHES - launches0
+    timing, abi.TIMING = abi.TIMING, None
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    imgs = B * world * args.steps
+    value = imgs / (ms_total / 1000.0)
+    e2e = imgs / (ms_e2e / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # per-kernel device time from the events recorded inside the timed region
+    per = {}
+    for name, s, e in timing:
+        d = per.setdefault(name, [0.0, 0])
+        d[0] += s.elapsed_time(e)
+        d[1] += 1
+    breakdown = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps, "ms_per_launch": v[0] / v[1]}
+                 for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])}
+    pk = peaks()
+    costs = kernel_costs(cfg, B)
+    dom = next(iter(breakdown))
+    roof = None
+    if dom in costs:
+        sec = breakdown[dom]["ms_per_launch"] / 1000.0
+        fl, by = costs[dom]["flops"], costs[dom]["bytes"]
+        mult = 3.0 if passes_mode == "fp32x3" else 1.0
+        t_tensor = fl * mult / (pk["bf16_tflops"] * 1e12)
+        t_hbm = by / (pk["hbm_gbs"] * 1e9)
+        if t_hbm >= t_tensor:
+            roof = {"bound": "hbm", "achieved": by / sec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
+        else:
+            roof = {"bound": "tensor", "achieved": fl / sec / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof.update(kernel=dom, traffic=None, peak_source=pk["_source"], algorithmic_flops_per_launch=fl,
+                    algorithmic_bytes_per_launch=by, mma_passes=int(mult),
+                    tensor_frac_issued=fl * mult / sec / (pk["bf16_tflops"] * 1e12),
+                    hbm_frac=by / sec / (pk["hbm_gbs"] * 1e9))
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        ips, cores, desc, _ = cpu_sample(pkg, args.workload, 1, 0)
+        cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)" if passes_mode == "fp32x3" else "bf16",
+        "data": "synthetic",
+        "config": {"workload": describe(cfg, args.workload, B), "global_batch": B * world,
+                   "parallelism": f"dp{world} (SyncBatchNorm statistics all-reduced over NCCL)" if world > 1 else "single GPU",
+                   "l2": "activations are 2.1 GB per tensor (>> 126 MB L2): inputs larger than L2, no flush needed",
+                   "precision": passes_mode},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "kernels": breakdown,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C2", "C2native", "C5", "tiny"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--precision", default=os.environ.get("HG3D_PRECISION", "fp32x3"), choices=["fp32x3", "bf16"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    pkg = importlib.import_module("3dhumangan_b200")
+    if args.impl == "reference":
+        run_reference(args, pkg)
+    else:
+        run_gpu(args, pkg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+/* hg3d.h -- C ABI of lib3dhg_sm100a.so: the B200-native (sm_100a) kernels behind the 3DHumanGAN
+ * generator / discriminator hot path.
+ *
+ * Boundary contract (the reference's own native boundary is the pybind11
+ * plugin loader lib/components/custom_ops.py:46-110 with bias_act.cpp:32, upfirdn2d.cpp:16):
+ *   - plain C: raw DEVICE pointers, sizes, enums; no C++ or torch types cross the boundary;
+ *   - ownership: the caller allocates every input, output and workspace tensor and keeps it alive;
+ *     the library never allocates device memory and never synchronises the device;
+ *   - stream: every launch takes the CUDA stream explicitly (`void* stream` = cudaStream_t);
+ *     the default stream is never touched implicitly;
+ *   - errors: return 0 on success, non-zero otherwise; `hg_last_error()` returns a thread-local
+ *     message (the Python shim raises RuntimeError, mirroring TORCH_CHECK in bias_act.cpp:34-51);
+ *   - threading: re-entrant; call from the rank's Python thread and from autograd's backward thread;
+ *   - all floating-point tensors are fp32 and densely packed unless a stride argument says otherwise.
+ *
+ * "passes" selects the tensor-core precision mode of every GEMM-shaped kernel:
+ *     3 = bf16x3 split (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, fp32 accumulate): meets the 1e-3-of-fp32 contract
+ *     1 = plain bf16 operands (the analogue of the reference's autocast training mode)
+ */
+#ifndef HG3D_H_
+#define HG3D_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library state -------------------------------------------------------------------------- */
+const char* hg_last_error(void);
+int hg_abi_version(void);
+int hg_check_device(void); /* 0 iff the current device is an sm_100 part */
+
+/* ---- packed tensor-core weights --------------------------------------------------------------
+ * W [N,K] fp32 (row stride ldw) * scale (* *scale_dev when non-null, a DEVICE scalar such as the
+ * 1/sigma of spectral normalisation, map3d_layers.py:205-206) -> bf16 hi/lo operand image:
+ * [N/Nb blocks][ceil(K/64) chunks][hi, lo][Nb x 64, K-major, 128B-swizzled].  Nb multiple of 16, <= 256. */
+size_t hg_packed_weight_bytes(int N, int K, int Nb);
+int hg_pack_weight(const float* W, int N, int K, int ldw, const float* scale_dev, float scale, int Nb,
+                   void* out_img, size_t out_bytes, void* stream);
+
+/* Y[M,N] = X[M,K] . W^T + bias   (K <= 256).  Used for mlp_shared at render resolution
+ * (SPADE2d.forward, map3d_layers.py:178) and as the primitive self-test. */
+int hg_linear(const float* X, int ldx, int M, int K, const void* Wimg, int Nb, int N, const float* bias, float* Y,
+              int ldy, int passes, void* stream);
+
+/* ---- renderer -------------------------------------------------------------------------------- */
+/* vertex_ik[b,v,:] = sum_j lbs[b,v,j] * inverse(fk[b,j])      replaces smpl.py:217-218.
+ * fk [B,24,4,4], lbs [B,V,24] -> vertex_ik [B,V,16] (16-byte aligned). */
+int hg_vertex_ik(const float* fk, const float* lbs, int B, int V, float* vertex_ik, void* stream);
+
+/* Ray sampling + jitter + camera transform + K=1 nearest posed vertex + 31-d geometry feature.
+ * Replaces vr.get_initial_rays_weak_perspective (volume_rendering.py:86-110), vr.perturb_points /
+ * transform_sampled_points (:124-170) and get_geo_features (smpl.py:210-249, incl. pytorch3d knn_points).
+ *   xs [Rw], ys [Rh], zs [S]: the three torch.linspace tables of the ray grid;
+ *   focals, scales [B]; cam2world [B,4,4]; jitter [B,Rw*Rh*S] uniform draws or NULL;
+ *   points_in [B,n_points,3] or NULL: when given, the ray stage is skipped (staged / test use);
+ *   skeletons [B,24,3], vertices [B,V,3], tpose [B,V,3], vertex_ik [B,V,16];
+ *   rec [B,n_points,36] out: xyz*input_scaler (3), features (31, order per legacy_mode), 2 zeros;
+ *   z_vals [B,n_points], points [B,n_points,3], nearest [B,n_points] (int32), nearest_d2: optional outs.
+ * Nearest index is bit-exact w.r.t. d2 = (dx*dx + dy*dy) + dz*dz in fp32, lowest index on ties. */
+int hg_geo_features(const float* xs, const float* ys, const float* zs, const float* focals, const float* scales,
+                    const float* cam2world, const float* jitter, const float* points_in, const float* skeletons,
+                    const float* vertices, const float* tpose, const float* vertex_ik, int B, int Rw, int Rh, int S,
+                    int V, int n_points, float input_scaler, int legacy_mode, float* rec, float* z_vals,
+                    float* points, int* nearest, float* nearest_d2, void* stream);
+
+/* Fused FiLM-SIREN MLP + volume integration.  Replaces COORDCONCATSIREN.forward (modulated.py:41-75)
+ * and vr.ray_integration (volume_rendering.py:12-56).
+ *   rec [B,R*S,36]; z_vals [B,R*S]; noise [B,R*S] N(0,1) draws or NULL;
+ *   film [B,7,2,256]: per layer (F, P) with layer output sin(F*acc + P) (host folds bias, x30, 15*freq+30);
+ *   wblob: hg_render_weight_blob_bytes() bytes, the 7 packed matrices in kernel schedule order;
+ *   w_sigma [256], w_rgb [3,256], b_feat [256], heads_b [4] = {b_sigma, b_rgb[3]};
+ *   ray_out [B,R,260] out: 256 composited features, 3 composited rgb (before *2-1), depth;
+ *   weights_out [B,R*S] optional; raw_out [B,R*S,260] optional: per-point (rgb, feat, sigma) INSTEAD of compositing.
+ *   S: samples per ray, power of two in [2,128]; hidden must be 256. */
+size_t hg_render_weight_blob_bytes(void);
+int hg_render_mlp(const float* rec, const float* z_vals, const float* noise, const float* film, const void* wblob,
+                  const float* w_sigma, const float* w_rgb, const float* b_feat, const float* heads_b, float* ray_out,
+                  float* weights_out, float* raw_out, int B, int R, int S, int hidden, float noise_std, int white_back,
+                  int last_back, int clamp_softplus, int passes, void* stream);
+
+/* ---- synthesis backbone ---------------------------------------------------------------------- */
+/* x0[C,Hg*Wg] = sin(w[:,0]*ic[i] + w[:,1]*jc[j] + b) (SynthesisInput, map3d_layers.py:260-275); when stats
+ * is non-null adds batch * (sum, sumsq) per channel to stats[0:C], stats[C:2C] (double). */
+int hg_synth_input(const float* w, const float* bias, const float* ic, const float* jc, int C, int Hg, int Wg,
+                   float* x0, double* stats, int batch, void* stream);
+
+/* BatchNorm statistics -> scale/shift (+ running-stat update, + fused per-sample SPADE modulation).
+ * nn.SyncBatchNorm semantics (map3d_layers.py:162).  stats [2,C] double (already all-reduced across ranks),
+ * count from `count_dev` (device double) when non-null else `count`.  training=0 uses the running stats.
+ * gb [B,2,C] = (1+gamma, beta) per sample -> mod [B,2,C] = (sc*G, sh*G+beta); scsh [2,C] = (sc, sh). */
+int hg_bn_finalize(const double* stats, double count, const double* count_dev, const float* weight, const float* bias,
+                   float* running_mean, float* running_var, int training, float eps, float momentum, const float* gb,
+                   int B, int C, float* scsh, float* mod, void* stream);
+
+/* One SPADE half-block: out = Conv1x1_SN(lrelu(BN(x)*(1+gamma)+beta)) + bias [+ skip], optional ToRGB
+ * accumulation and the (sum, sumsq) statistics of `out` for the next BatchNorm.
+ * Replaces SPADE2d.forward + SPADEBlock.forward + ToRGB.forward (map3d_layers.py:176-190, 218-238, 346-352)
+ * and, in pixel-style mode, the F.interpolate of map3d_generator.py:244-245.
+ *   x [B or 1,C,HW] with batch stride x_bstride (0 = shared);  exactly one of
+ *   mod  [B,2,C]                      const-style (per-sample gamma/beta), or
+ *   p_lr [B,Rh*Rw,p_stride] (+ p_bias [B,128], scsh [2,C], wgb packed [512x128], bgb [512])  pixel-style;
+ *   wimg packed [C x C] conv weight; bias [C]; skip [B,C,HW] or NULL; out [B,C,HW];
+ *   stats [2,C] double or NULL; rgb_w [3,C], rgb_b [3], rgb_in [B,3,HW] or NULL, rgb_out [B,3,HW] (all NULL = no ToRGB).
+ *   C must be 256. */
+int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float* scsh, const float* p_lr,
+                  long p_stride, const float* p_bias, const void* wgb, const float* bgb, const void* wimg,
+                  const float* bias, const float* skip, float* out, double* stats, const float* rgb_w,
+                  const float* rgb_b, const float* rgb_in, float* rgb_out, int B, int C, int Hg, int Wg, int Rh, int Rw,
+                  int passes, void* stream);
+
+/* ---- StyleGAN3 native ops named by the reference ---------------------------------------------- */
+/* y = clamp(act(x + b[(i / stepB) % sizeB]) * gain)   replaces bias_act.cpp:32 / bias_act.cu:24 (forward).
+ * act: 1 linear 2 relu 3 lrelu 4 tanh 5 sigmoid 6 elu 7 selu 8 softplus 9 swish; clamp < 0 disables. */
+int hg_bias_act(const float* x, const float* b, float* y, long n, int stepB, int sizeB, int act, float alpha,
+                float gain, float clamp, void* stream);
+
+/* Zero-insert up-sample, pad/crop, 2-D FIR, decimate   replaces upfirdn2d.cpp:16 / upfirdn2d.cu:29-375.
+ * x [NC,inH,inW] -> y [NC,outH,outW]; f [fH,fW]; the filter is flipped unless flip_filter (conv2d is a correlation). */
+int hg_upfirdn2d(const float* x, const float* f, float* y, int NC, int inH, int inW, int outH, int outW, int fH,
+                 int fW, int upx, int upy, int downx, int downy, int padx0, int pady0, int flip_filter, float gain,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HG3D_H_ */

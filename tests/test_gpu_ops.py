@@ -1,0 +1,62 @@
+"""bias_act / upfirdn2d (sm_100a) against the restated reference implementations."""
+import importlib
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("act", ["linear", "relu", "lrelu", "tanh", "sigmoid", "elu", "selu", "softplus", "swish"])
+@pytest.mark.parametrize("shape,dim", [((7, 256), 1), ((3, 5, 11, 13), 1), ((4, 9, 6), 2)])
+def test_bias_act(port, act, shape, dim):
+    ba = importlib.import_module("3dhumangan_b200.ops.bias_act")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(*shape, generator=g) * 3
+    b = torch.randn(shape[dim], generator=g)
+    for clamp in (None, 0.7):
+        ref = port.bias_act_ref(x, b, dim=dim, act=act, clamp=clamp)
+        with torch.no_grad():
+            got = ba.bias_act(x.cuda(), b.cuda(), dim=dim, act=act, clamp=clamp).cpu()
+        assert torch.allclose(got, ref, rtol=2e-6, atol=2e-6), (act, clamp, (got - ref).abs().max())
+    with torch.no_grad():
+        got = ba.bias_act(x.cuda(), None, act=act, gain=0.5, alpha=0.1).cpu()
+    assert torch.allclose(got, port.bias_act_ref(x, None, act=act, gain=0.5, alpha=0.1), rtol=2e-6, atol=2e-6)
+
+
+def test_upfirdn2d_matches_reference_semantics(port):
+    uf = importlib.import_module("3dhumangan_b200.ops.upfirdn2d")
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 17, 13, generator=g)
+    f2 = uf.setup_filter([1, 3, 3, 1])
+    f1 = uf.setup_filter([0.1, 0.2, 0.3, 0.25, 0.1, 0.05, 0.0, 0.0, 0.1, 0.2, 0.05, 0.02])   # 12 taps -> separable
+    assert f2.ndim == 2 and f1.ndim == 1
+    cases = [dict(f=f2), dict(f=f2, up=2, padding=[2, 1, 2, 1], gain=4), dict(f=f2, down=2, padding=1),
+             dict(f=f2, up=(2, 1), down=(1, 2), padding=[1, 2, 0, 3], flip_filter=True),
+             dict(f=f1, up=2, padding=[6, 5, 6, 5], gain=4), dict(f=f1, down=2, padding=[1, 2, 5, 5], flip_filter=True), dict(f=f2, down=2, padding=[-1, -2, 0, -3]),
+             dict(f=None, up=1)]
+    for kw in cases:
+        ref = port.upfirdn2d_ref(x, **kw)
+        with torch.no_grad():
+            got = uf.upfirdn2d(x.cuda(), **{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}).cpu()
+        assert got.shape == ref.shape, (kw, got.shape, ref.shape)
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5), kw
+
+
+def test_upsample_downsample_wrappers(port):
+    """The only call shapes of the reference: augment.py:314,325 (sym6 filter, up=2 / down=2 with negative padding)."""
+    uf = importlib.import_module("3dhumangan_b200.ops.upfirdn2d")
+    sym6 = [0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.048311742585633, 0.4910559419267466,
+            0.787641141030194]
+    f = uf.setup_filter(sym6 + sym6[::-1])
+    x = torch.randn(2, 3, 40, 24, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        up = uf.upsample2d(x.cuda(), f.cuda(), up=2)
+        dn = uf.downsample2d(up, f.cuda(), down=2, padding=-6, flip_filter=True)
+    fw = f.numel()
+    p_up = [(fw + 1) // 2, (fw - 2) // 2] * 2
+    ref_up = port.upfirdn2d_ref(x, f, up=2, padding=p_up, gain=4)
+    assert torch.allclose(up.cpu(), ref_up, rtol=1e-5, atol=1e-5)
+    p_dn = [-6 + (fw - 1) // 2, -6 + (fw - 2) // 2] * 2
+    ref_dn = port.upfirdn2d_ref(ref_up, f, down=2, padding=p_dn, flip_filter=True)
+    assert torch.allclose(dn.cpu(), ref_dn, rtol=1e-5, atol=1e-5)
