@@ -26,7 +26,9 @@ SIGNATURES = {
     "hg_packed_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "hg_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "hg_vertex_ik": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "hg_geo_features": (c_int, [c_void_p] * 12 + [c_int] * 6 + [c_float, c_int] + [c_void_p] * 6),
+    "hg_knn_padded": (c_int, [c_int]),
+    "hg_knn_prep": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "hg_geo_features": (c_int, [c_void_p] * 14 + [c_int] * 6 + [c_float, c_int] + [c_void_p] * 6),
     "hg_spade_conv": (c_int, [c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_long] + [c_void_p] * 12 + [c_int] * 7 + [c_void_p]),
     "hg_bn_finalize": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -150,7 +152,7 @@ def vertex_ik(fk, lbs):
 
 def geo_features(cond_vertices, tpose, skeletons, vik, *, input_scaler, legacy_mode=False, points_in=None,
                  xs=None, ys=None, zs=None, focals=None, scales=None, cam2world=None, jitter=None,
-                 want_points=False, want_nearest=False):
+                 want_points=False, want_nearest=False, brute_force=False):
     """Ray sampling (or given points) + K=1 nearest vertex + 31-d features -> point records [B,N,36].
 
     Returns dict(rec, z_vals, points, nearest, nearest_d2) (optional outputs None unless requested)."""
@@ -168,7 +170,16 @@ def geo_features(cond_vertices, tpose, skeletons, vik, *, input_scaler, legacy_m
     pts = torch.empty(B, N, 3, dtype=torch.float32, device=dev) if want_points else None
     near = torch.empty(B, N, dtype=torch.int32, device=dev) if want_nearest else None
     d2 = torch.empty(B, N, dtype=torch.float32, device=dev) if want_nearest else None
-    keep = [f(t) for t in (xs, ys, zs, focals, scales, cam2world, jitter, points_in, skeletons, cond_vertices, tpose, vik)]
+    verts = f(cond_vertices)
+    ksort = kbox = None
+    if not brute_force and V <= 8192:
+        Vp = int(lib().hg_knn_padded(V))
+        ksort = torch.empty(B, Vp, 4, dtype=torch.float32, device=dev)
+        kbox = torch.empty(B, Vp // 32, 2, 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device_of(rec):
+            call("hg_knn_prep", ptr(verts), B, V, ptr(ksort), ptr(kbox), stream())
+    keep = [f(t) for t in (xs, ys, zs, focals, scales, cam2world, jitter, points_in, skeletons, verts, tpose, vik)]
+    keep += [ksort, kbox]
     with torch.cuda.device_of(rec):
         call("hg_geo_features", *[ptr(t) for t in keep], B, Rw, Rh, S, V, N, float(input_scaler),
                                     int(bool(legacy_mode)), ptr(rec), ptr(z_vals), ptr(pts), ptr(near), ptr(d2),

@@ -8,10 +8,16 @@
 //      [pytorch3d.ops.knn_points], canonicalisation, nearest distance)
 //
 // One thread = one sample point.  The 6890 posed vertices of the point's body are staged in
-// shared memory as float4 (110 KB) and scanned by every thread with broadcast LDS.128 reads; the
-// distance is evaluated exactly as the oracle defines it -- (dx*dx + dy*dy) + dz*dz with one fp32
-// rounding per operation (no FMA contraction), strict '<' so the lowest index wins ties -- which
-// makes the nearest index bit-exact for identical input points.
+// shared memory as float4 (110 KB); the distance is evaluated exactly as the oracle defines it --
+// (dx*dx + dy*dy) + dz*dz with one fp32 rounding per operation (no FMA contraction), lowest index
+// on ties -- which makes the nearest index bit-exact for identical input points.
+//
+// Exact pruning (hg_knn_prep): vertices are Morton-sorted per body and cut into clusters of 32 with
+// an axis-aligned box each.  A point first measures the first vertex of every cluster (a real
+// candidate), then scans only clusters whose box distance -- computed with the SAME rounded
+// operations, hence a true lower bound of every member's computed distance -- does not exceed the
+// running best.  The result is identical to the brute-force scan (ties: explicit lowest original
+// index) at ~1/8 of the instructions.
 //
 // Output record per point (kPointStride floats, 16-byte aligned rows):
 //   [0..2]  xyz * input_scaler        (input of first_layer_coord, modulated.py:44,56)
@@ -76,6 +82,100 @@ __global__ void vertex_ik_kernel(const float* __restrict__ fk, const float* __re
   for (int i = 0; i < 4; ++i) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
 }
 
+
+// -------------------------------------------------------------------------------------------
+// KNN preparation: Morton sort + cluster boxes (one CTA per body)
+// -------------------------------------------------------------------------------------------
+constexpr int kSortN = 8192;      // >= V, power of two
+constexpr int kCluster = 32;
+
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v &= 1023u;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void __launch_bounds__(1024, 1) knn_prep_kernel(const float* __restrict__ vertices, int V, int Vp,
+                                                           float4* __restrict__ sorted, float4* __restrict__ boxes) {
+  extern __shared__ unsigned long long keys[];   // [kSortN]
+  __shared__ float red[6][32];
+  __shared__ float bb[6];
+  const int b = blockIdx.x;
+  const float* vp = vertices + static_cast<long>(b) * V * 3;
+  float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+  for (int v = threadIdx.x; v < V; v += blockDim.x)
+    for (int d = 0; d < 3; ++d) {
+      const float c = vp[v * 3 + d];
+      lo[d] = fminf(lo[d], c);
+      hi[d] = fmaxf(hi[d], c);
+    }
+  for (int d = 0; d < 3; ++d) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    if ((threadIdx.x & 31) == 0) { red[d][threadIdx.x >> 5] = lo[d]; red[3 + d][threadIdx.x >> 5] = hi[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float r = red[threadIdx.x][0];
+    for (int i = 1; i < 32; ++i) r = threadIdx.x < 3 ? fminf(r, red[threadIdx.x][i]) : fmaxf(r, red[threadIdx.x][i]);
+    bb[threadIdx.x] = r;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < kSortN; v += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (v < V) {
+      uint32_t code = 0;
+      for (int d = 0; d < 3; ++d) {
+        const float ext = fmaxf(bb[3 + d] - bb[d], 1e-20f);
+        int qd = static_cast<int>((vp[v * 3 + d] - bb[d]) / ext * 1023.f);
+        qd = qd < 0 ? 0 : (qd > 1023 ? 1023 : qd);
+        code |= spread10(static_cast<uint32_t>(qd)) << d;
+      }
+      key = (static_cast<unsigned long long>(code) << 13) | static_cast<unsigned long long>(v);
+    }
+    keys[v] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= kSortN; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < kSortN; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], c = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > c) == up) { keys[i] = c; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  float4* out = sorted + static_cast<long>(b) * Vp;
+  for (int i = threadIdx.x; i < Vp; i += blockDim.x) {
+    const int src = i < V ? i : V - 1;   // pad with copies of the last vertex (same index: harmless)
+    const int v = static_cast<int>(keys[src] & 8191ull);
+    out[i] = make_float4(vp[v * 3], vp[v * 3 + 1], vp[v * 3 + 2], __int_as_float(v));
+  }
+  __syncthreads();
+  const int M = Vp / kCluster;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    float l[3] = {3e38f, 3e38f, 3e38f}, h[3] = {-3e38f, -3e38f, -3e38f};
+    for (int i = 0; i < kCluster; ++i) {
+      const int src = (m * kCluster + i) < V ? (m * kCluster + i) : V - 1;
+      const int v = static_cast<int>(keys[src] & 8191ull);
+      for (int d = 0; d < 3; ++d) {
+        l[d] = fminf(l[d], vp[v * 3 + d]);
+        h[d] = fmaxf(h[d], vp[v * 3 + d]);
+      }
+    }
+    boxes[(static_cast<long>(b) * M + m) * 2 + 0] = make_float4(l[0], l[1], l[2], 0.f);
+    boxes[(static_cast<long>(b) * M + m) * 2 + 1] = make_float4(h[0], h[1], h[2], 0.f);
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // rays + KNN + features
 // -------------------------------------------------------------------------------------------
@@ -93,6 +193,9 @@ struct GeoArgs {
   const float* vertices;   // [B,V,3]
   const float* tpose;      // [B,V,3]
   const float* vertex_ik;  // [B,V,16]
+  const float4* sorted;    // [B,Vp] Morton-sorted (x,y,z,index) or null -> brute force over `vertices`
+  const float4* boxes;     // [B,Vp/32,2] cluster boxes (lo, hi)
+  int Vp;
   int B, Rw, Rh, S, V;
   int n_points;  // per body: Rw*Rh*S, or N when points_in is given
   float input_scaler;
@@ -108,13 +211,21 @@ struct GeoArgs {
 constexpr int kGeoThreads = 512;
 
 __global__ void __launch_bounds__(kGeoThreads, 1) geo_kernel(GeoArgs a) {
-  extern __shared__ float4 sv[];  // [V] posed vertices
+  extern __shared__ float4 sv[];  // [Vn] posed vertices (x,y,z,index), then [M][2] cluster boxes
   __shared__ float sk[kJoints * 3];
   __shared__ float c2w[16];
   const int b = blockIdx.y;
-  for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
-    const float* p = a.vertices + (static_cast<long>(b) * a.V + v) * 3;
-    sv[v] = make_float4(p[0], p[1], p[2], 0.f);
+  const int Vn = a.sorted ? a.Vp : a.V;
+  const int M = a.sorted ? a.Vp / kCluster : 0;
+  float4* sbox = sv + Vn;
+  if (a.sorted) {
+    for (int v = threadIdx.x; v < Vn; v += blockDim.x) sv[v] = a.sorted[static_cast<long>(b) * Vn + v];
+    for (int v = threadIdx.x; v < 2 * M; v += blockDim.x) sbox[v] = a.boxes[static_cast<long>(b) * 2 * M + v];
+  } else {
+    for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
+      const float* p = a.vertices + (static_cast<long>(b) * a.V + v) * 3;
+      sv[v] = make_float4(p[0], p[1], p[2], __int_as_float(v));
+    }
   }
   if (threadIdx.x < kJoints * 3) sk[threadIdx.x] = a.skeletons[static_cast<long>(b) * kJoints * 3 + threadIdx.x];
   if (threadIdx.x < 16 && a.cam2world) c2w[threadIdx.x] = a.cam2world[b * 16 + threadIdx.x];
@@ -161,13 +272,33 @@ __global__ void __launch_bounds__(kGeoThreads, 1) geo_kernel(GeoArgs a) {
 
     // K=1 nearest posed vertex (smpl.py:220), exact oracle arithmetic
     float best = 3.4e38f;
-    int bi = 0;
-#pragma unroll 4
-    for (int v = 0; v < a.V; ++v) {
-      const float4 q = sv[v];
+    int bi = 0x7fffffff;
+    auto consider = [&](const float4 q) {
       const float ex = __fsub_rn(px, q.x), ey = __fsub_rn(py, q.y), ez = __fsub_rn(pz, q.z);
       const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-      if (d2 < best) { best = d2; bi = v; }
+      const int vi = __float_as_int(q.w);
+      if (d2 < best || (d2 == best && vi < bi)) { best = d2; bi = vi; }
+    };
+    if (M == 0) {
+#pragma unroll 4
+      for (int v = 0; v < Vn; ++v) consider(sv[v]);
+    } else {
+      // pass 1: one real candidate per cluster tightens the bound
+#pragma unroll 4
+      for (int m = 0; m < M; ++m) consider(sv[m * kCluster]);
+      // pass 2: scan the clusters whose box can still contain a vertex at distance <= best.  The box
+      // distance uses the same rounded operations as `consider`, so it never exceeds a member's d2.
+      for (int m = 0; m < M; ++m) {
+        const float4 lo = sbox[2 * m], hi = sbox[2 * m + 1];
+        const float bx = fmaxf(fmaxf(__fsub_rn(lo.x, px), __fsub_rn(px, hi.x)), 0.f);
+        const float by = fmaxf(fmaxf(__fsub_rn(lo.y, py), __fsub_rn(py, hi.y)), 0.f);
+        const float bz = fmaxf(fmaxf(__fsub_rn(lo.z, pz), __fsub_rn(pz, hi.z)), 0.f);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), __fmul_rn(bz, bz));
+        if (lb <= best) {
+#pragma unroll 8
+          for (int i = 0; i < kCluster; ++i) consider(sv[m * kCluster + i]);
+        }
+      }
     }
     if (a.nearest) a.nearest[gp] = bi;
     if (a.nearest_d2) a.nearest_d2[gp] = best;
@@ -218,23 +349,45 @@ int hg_vertex_ik(const float* fk, const float* lbs, int B, int V, float* vertex_
   return hg::check_launch("hg_vertex_ik");
 }
 
+// Morton-sort the posed vertices of every body and box them in clusters of 32 (exact KNN pruning).
+// sorted: [B, Vp] float4, boxes: [B, Vp/32, 2] float4 with Vp = hg_knn_padded(V).
+int hg_knn_padded(int V) { return (V + hg::kCluster - 1) / hg::kCluster * hg::kCluster; }
+
+int hg_knn_prep(const float* vertices, int B, int V, void* sorted, void* boxes, void* stream) {
+  HG_REQUIRE(vertices && sorted && boxes, "hg_knn_prep: null pointer");
+  HG_REQUIRE(B > 0 && V > 0 && V <= hg::kSortN, "hg_knn_prep: need 0 < V <= %d (got %d)", hg::kSortN, V);
+  HG_REQUIRE((reinterpret_cast<uintptr_t>(sorted) & 15) == 0 && (reinterpret_cast<uintptr_t>(boxes) & 15) == 0,
+             "hg_knn_prep: outputs must be 16-byte aligned");
+  const int smem = hg::kSortN * 8;
+  cudaError_t e = cudaFuncSetAttribute(hg::knn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { hg::set_error("hg_knn_prep: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; }
+  hg::knn_prep_kernel<<<B, 1024, smem, static_cast<cudaStream_t>(stream)>>>(
+      vertices, V, hg_knn_padded(V), static_cast<float4*>(sorted), static_cast<float4*>(boxes));
+  return hg::check_launch("hg_knn_prep");
+}
+
 // See include/hg3d.h for the argument contract.
 int hg_geo_features(const float* xs, const float* ys, const float* zs, const float* focals, const float* scales,
                     const float* cam2world, const float* jitter, const float* points_in, const float* skeletons,
-                    const float* vertices, const float* tpose, const float* vertex_ik, int B, int Rw, int Rh, int S,
+                    const float* vertices, const float* tpose, const float* vertex_ik, const void* knn_sorted,
+                    const void* knn_boxes, int B, int Rw, int Rh, int S,
                     int V, int n_points, float input_scaler, int legacy_mode, float* rec, float* z_vals,
                     float* points, int* nearest, float* nearest_d2, void* stream) {
   HG_REQUIRE(skeletons && vertices && tpose && vertex_ik && rec, "hg_geo_features: null pointer");
   HG_REQUIRE(B > 0 && V > 0 && n_points > 0, "hg_geo_features: bad shape B=%d V=%d N=%d", B, V, n_points);
-  HG_REQUIRE(static_cast<size_t>(V) * 16 <= 200 * 1024, "hg_geo_features: V=%d does not fit in shared memory", V);
+  HG_REQUIRE(static_cast<size_t>(V) * 17 <= 200 * 1024, "hg_geo_features: V=%d does not fit in shared memory", V);
   if (!points_in) {
     HG_REQUIRE(xs && ys && zs && focals && scales && cam2world, "hg_geo_features: ray tables missing");
     HG_REQUIRE(Rw > 0 && Rh > 0 && S > 1 && n_points == Rw * Rh * S, "hg_geo_features: n_points != Rw*Rh*S");
   }
   HG_REQUIRE((reinterpret_cast<uintptr_t>(vertex_ik) & 15) == 0, "hg_geo_features: vertex_ik must be 16-byte aligned");
+  HG_REQUIRE((knn_sorted == nullptr) == (knn_boxes == nullptr), "hg_geo_features: knn_sorted and knn_boxes go together");
+  const int Vp = hg_knn_padded(V);
   hg::GeoArgs a{xs, ys, zs, focals, scales, cam2world, jitter, points_in, skeletons, vertices, tpose, vertex_ik,
+                static_cast<const float4*>(knn_sorted), static_cast<const float4*>(knn_boxes), Vp,
                 B, Rw, Rh, S, V, n_points, input_scaler, legacy_mode, rec, z_vals, points, nearest, nearest_d2};
-  const size_t smem = static_cast<size_t>(V) * sizeof(float4);
+  const size_t smem = knn_sorted ? (static_cast<size_t>(Vp) + 2 * (Vp / hg::kCluster)) * sizeof(float4)
+                                 : static_cast<size_t>(V) * sizeof(float4);
   cudaError_t e = cudaFuncSetAttribute(hg::geo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) { hg::set_error("hg_geo_features: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; }
   int bx = (n_points + hg::kGeoThreads - 1) / hg::kGeoThreads;

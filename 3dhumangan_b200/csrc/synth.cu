@@ -3,7 +3,11 @@
 // (SPADE2d.forward lib/components/map3d_layers.py:176-190, SPADEBlock.forward :218-238,
 //  ToRGB :346-352, SynthesisNetwork.forward lib/generators/map3d_generator.py:58-97.)
 //
-// Activations live in HBM as fp32 planes [B, C=256, HW] (the reference's NCHW).  A CTA owns tiles
+// Activations live in HBM as fp32 in a tile-blocked planar layout [B, T, C=256, 128] (T = ceil(HW/128)
+// tiles of 128 consecutive pixels): the 128 KB a CTA reads / writes per tile are CONTIGUOUS (one DRAM
+// page stream, one TLB entry) while a warp still touches 32 consecutive pixels of one channel (128 B).
+// (The plain NCHW planes of the first version made every tile touch 256 planes 1 MB apart: 13% of the
+// HBM roofline, see profiles/r1_bench_v1_planar_layout.json.)  A CTA owns tiles
 // of 128 consecutive pixels of one image: 8 "row" warps build the bf16(x3) A operand in shared
 // memory (BN scale/shift, SPADE modulation, LeakyReLU fused into the operand producer), one
 // thread issues tcgen05.mma against weight tiles streamed from L2 by the bulk-copy engine, and
@@ -31,8 +35,8 @@ constexpr uint32_t kAChunk = 128 * 128;   // [128 x 64] bf16
 constexpr uint32_t kBStage = 256 * 128;   // [256 x 64] bf16
 
 struct SpadeArgs {
-  const float* x;        // [B or 1, C, HW]
-  long x_bstride;        // C*HW, or 0 when x is shared by the whole batch (synthesis input)
+  const float* x;        // [B or 1, T, C, 128] tile-blocked
+  long x_bstride;        // T*C*128, or 0 when x is shared by the whole batch (synthesis input)
   const float* mod;      // const-style: [B,2,C] (g1, g0): y = lrelu(x*g1 + g0)
   const float* scsh;     // pixel-style: [2,C] BN scale, shift
   const float* p_lr;     // pixel-style: [B, Rh*Rw, p_stride>=128] pre-activation of mlp_shared at render res
@@ -42,8 +46,8 @@ struct SpadeArgs {
   const float* bgb;      // pixel-style: [512] bias in the same interleaved order (gamma part includes +1)
   const uint8_t* wimg;   // packed conv weight [256 x 256] (already divided by sigma)
   const float* bias;     // [C]
-  const float* skip;     // [B,C,HW] residual or null
-  float* out;            // [B,C,HW]
+  const float* skip;     // [B,T,C,128] residual or null
+  float* out;            // [B,T,C,128]
   double* stats;         // [2,C] accumulated sum / sumsq of out, or null
   const float* rgb_w;    // [3,C] or null
   const float* rgb_b;    // [3]
@@ -162,20 +166,30 @@ __device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem&
   const int row = q * 32 + lane;
   const int pix = p0 + row;
   const bool valid = pix < a.HW;
-  const long plane = static_cast<long>(b) * kC * a.HW + pix;
+  const int T = (a.HW + 127) / 128;
+  const long plane = (static_cast<long>(b) * T + (p0 >> 7)) * kC * 128 + row;   // + c * 128
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 1
   for (int kc = 0; kc < 4; ++kc) {
     const int c0 = kc * 64 + h * 32;
     uint32_t raw[32];
     tmem_ld32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
+    // residual input: issue all 32 loads before anything depends on them (read-only path; a load placed
+    // next to its store is serialised behind the store by the aliasing rules: 128 exposed latencies per tile)
+    float sk[32];
+    if (a.skip) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sk[j] = valid ? __ldg(a.skip + plane + (c0 + j) * 128) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sk[j] = 0.f;
+    }
     tmem_ld_wait();
     float v[32], s2[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float o = __uint_as_float(raw[j]) + m.tab_bias[c0 + j];
-      if (a.skip && valid) o += a.skip[plane + static_cast<long>(c0 + j) * a.HW];
-      if (valid) a.out[plane + static_cast<long>(c0 + j) * a.HW] = o;
+      float o = __uint_as_float(raw[j]) + m.tab_bias[c0 + j] + sk[j];
+      if (valid) a.out[plane + (c0 + j) * 128] = o;
       o = valid ? o : 0.f;
       v[j] = o;
       s2[j] = o * o;
@@ -287,21 +301,30 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
       }
       const int pix = p0 + row;
       const bool valid = pix < a.HW;
-      const float* xp = a.x + static_cast<long>(b) * a.x_bstride + pix;
-#pragma unroll 1
+      // Out-of-range rows read the tile's first pixel (always valid) and are zeroed afterwards.
+      const float* xp = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(p0 >> 7) * kC * 128 + (valid ? row : 0);
+      // All 32 loads of a chunk are issued back to back (volatile asm keeps ptxas from re-batching them in
+      // groups of 8) and the NEXT chunk's loads are in flight while this chunk is converted and stored.
+      float xv[2][32];
+      auto issue = [&](float (&dst)[32], int kc) {
+        const float* src = xp + (kc * 64 + h * 32) * 128;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dst[j]) : "l"(src + j * 128));
+      };
+      issue(xv[0], 0);
+#pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
+        if (kc < 3) issue(xv[(kc + 1) & 1], kc + 1);
         mbar_wait(m.bars + A_EMPTY + kc, (it & 1) ^ 1);
         const int c0 = kc * 64 + h * 32;
-        float xv[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) xv[j] = valid ? __ldg(xp + static_cast<long>(c0 + j) * a.HW) : 0.f;
+        float (&cur)[32] = xv[kc & 1];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float y[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int c = c0 + g * 8 + j;
-            y[j] = lrelu02(fmaf(xv[g * 8 + j], m.tab_g1[c], m.tab_g0[c]));
+            y[j] = valid ? lrelu02(fmaf(cur[g * 8 + j], m.tab_g1[c], m.tab_g0[c])) : 0.f;
           }
           store_a8<kPasses == 3>(m.a_hi + kc * kAChunk, m.a_lo + kc * kAChunk, row, h * 32 + g * 8, y);
         }
@@ -442,20 +465,26 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
         if (lane == 0) mbar_arrive(m.bars + A1_FULL);
       }
       // ---- phase 1: gamma/beta accumulators -> y = lrelu(BN(x)*(1+gamma)+beta) -> A (4 chunks)
+      const float* xp = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(p0 >> 7) * kC * 128 + (valid ? row : 0);
+      float xv[2][32];
+      auto issue = [&](float (&dst)[32], int kc) {
+        const float* src = xp + (kc * 64 + h * 32) * 128;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dst[j]) : "l"(src + j * 128));
+      };
+      issue(xv[0], 0);   // in flight while the gamma/beta GEMM finishes
       mbar_wait(m.bars + G1_FULL, it & 1);
       tc_fence_after();
-      const float* xp = a.x + static_cast<long>(b) * a.x_bstride + pix;
-#pragma unroll 1
+#pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
+        if (kc < 3) issue(xv[(kc + 1) & 1], kc + 1);
         const int c0 = kc * 64 + h * 32;
         const uint32_t col = (kc >> 1) * 256 + (kc & 1) * 128 + h * 32;
         uint32_t gr[32], br[32];
         tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + col, gr);
         tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + col + 64, br);
-        float xv[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) xv[j] = valid ? __ldg(xp + static_cast<long>(c0 + j) * a.HW) : 0.f;
         tmem_ld_wait();
+        float (&cur)[32] = xv[kc & 1];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float y[8];
@@ -465,8 +494,8 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
             const int c = c0 + jj;
             const float gam = __uint_as_float(gr[jj]) + m.tab_bgb[col + jj];        // 1 + gamma
             const float bet = __uint_as_float(br[jj]) + m.tab_bgb[col + 64 + jj];   // beta
-            const float xn = fmaf(xv[jj], m.tab_g1[c], m.tab_g0[c]);
-            y[j] = lrelu02(fmaf(xn, gam, bet));
+            const float xn = fmaf(cur[jj], m.tab_g1[c], m.tab_g0[c]);
+            y[j] = valid ? lrelu02(fmaf(xn, gam, bet)) : 0.f;
           }
           store_a8<kPasses == 3>(m.a_hi + kc * kAChunk, m.a_lo + kc * kAChunk, row, h * 32 + g * 8, y);
         }
@@ -570,7 +599,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
 
 // ------------------------------------------------------------------------------------------
 // synthesis input x0 = sin(W [i, j]^T + b)  (map3d_layers.py:260-275), shared by the whole batch,
-// with its BatchNorm statistics.
+// written in the tile-blocked layout [T, C, 128], with its BatchNorm statistics.
 // ------------------------------------------------------------------------------------------
 __global__ void synth_input_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                    const float* __restrict__ ic, const float* __restrict__ jc, int Hg, int Wg,
@@ -582,7 +611,7 @@ __global__ void synth_input_kernel(const float* __restrict__ w, const float* __r
   float s1 = 0.f, s2 = 0.f;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
     const float v = sinf(fmaf(w1, jc[p % Wg], fmaf(w0, ic[p / Wg], bb)));
-    x0[static_cast<long>(c) * HW + p] = v;
+    x0[(static_cast<long>(p >> 7) * kC + c) * 128 + (p & 127)] = v;
     s1 += v;
     s2 += v * v;
   }

@@ -137,11 +137,12 @@ def synthesis_forward(params, feat_lr, fixed_style, cfg, *, training=True, passe
     stats[:, 512] = float(B * HW)
     ic = torch.linspace(-1, 1, Hg, **f32)
     jc = torch.linspace(-1, 1, Wg, **f32)
-    x0 = torch.empty(C, HW, **f32)
+    T = (HW + 127) // 128                      # activations are tile-blocked: [B, T, C, 128] (csrc/synth.cu)
+    x0 = torch.empty(T, C, 128, **f32)
     abi.synth_input(P[input_prefix + "network.0.weight"].reshape(C, 2).contiguous(), P[input_prefix + "network.0.bias"],
                     ic, jc, x0, stats[0] if training else None, B)
 
-    bufs = [torch.empty(B, C, HW, **f32) for _ in range(3)]
+    bufs = [torch.empty(B, T, C, 128, **f32) for _ in range(3)]
     rgb = [torch.empty(B, 3, HW, **f32) for _ in range(2)]
     rgb_cur = None
     scsh = torch.empty(2, C, **f32)
@@ -184,9 +185,9 @@ def synthesis_forward(params, feat_lr, fixed_style, cfg, *, training=True, passe
                skip=block_in[0] if use_skip else None, stats=stats[idx + 1] if training else None, **kw)
         if use_rgb:
             rgb_cur = rgb_next
-        cur, cur_bstride = out, C * HW
+        cur, cur_bstride = out, T * C * 128
         if return_internal and last_half:
-            internal[f"m3d_{k}"] = cur.reshape(B, C, Hg, Wg).clone()
+            internal[f"m3d_{k}"] = cur.permute(0, 2, 1, 3).reshape(B, C, T * 128)[:, :, :HW].reshape(B, C, Hg, Wg).clone()
     out_rgb = rgb_cur.reshape(B, 3, Hg, Wg)
     return (out_rgb, internal) if return_internal else out_rgb
 

@@ -49,6 +49,11 @@ int hg_linear(const float* X, int ldx, int M, int K, const void* Wimg, int Nb, i
  * fk [B,24,4,4], lbs [B,V,24] -> vertex_ik [B,V,16] (16-byte aligned). */
 int hg_vertex_ik(const float* fk, const float* lbs, int B, int V, float* vertex_ik, void* stream);
 
+/* Exact-KNN acceleration structure: Morton-sorted vertices (x,y,z,index) + one box per cluster of 32.
+ * vertices [B,V,3] (V <= 8192) -> sorted [B,Vp] float4, boxes [B,Vp/32,2] float4, Vp = hg_knn_padded(V). */
+int hg_knn_padded(int V);
+int hg_knn_prep(const float* vertices, int B, int V, void* sorted, void* boxes, void* stream);
+
 /* Ray sampling + jitter + camera transform + K=1 nearest posed vertex + 31-d geometry feature.
  * Replaces vr.get_initial_rays_weak_perspective (volume_rendering.py:86-110), vr.perturb_points /
  * transform_sampled_points (:124-170) and get_geo_features (smpl.py:210-249, incl. pytorch3d knn_points).
@@ -56,14 +61,16 @@ int hg_vertex_ik(const float* fk, const float* lbs, int B, int V, float* vertex_
  *   focals, scales [B]; cam2world [B,4,4]; jitter [B,Rw*Rh*S] uniform draws or NULL;
  *   points_in [B,n_points,3] or NULL: when given, the ray stage is skipped (staged / test use);
  *   skeletons [B,24,3], vertices [B,V,3], tpose [B,V,3], vertex_ik [B,V,16];
+ *   knn_sorted / knn_boxes: outputs of hg_knn_prep, or both NULL for the brute-force scan (same result);
  *   rec [B,n_points,36] out: xyz*input_scaler (3), features (31, order per legacy_mode), 2 zeros;
  *   z_vals [B,n_points], points [B,n_points,3], nearest [B,n_points] (int32), nearest_d2: optional outs.
  * Nearest index is bit-exact w.r.t. d2 = (dx*dx + dy*dy) + dz*dz in fp32, lowest index on ties. */
 int hg_geo_features(const float* xs, const float* ys, const float* zs, const float* focals, const float* scales,
                     const float* cam2world, const float* jitter, const float* points_in, const float* skeletons,
-                    const float* vertices, const float* tpose, const float* vertex_ik, int B, int Rw, int Rh, int S,
-                    int V, int n_points, float input_scaler, int legacy_mode, float* rec, float* z_vals,
-                    float* points, int* nearest, float* nearest_d2, void* stream);
+                    const float* vertices, const float* tpose, const float* vertex_ik, const void* knn_sorted,
+                    const void* knn_boxes, int B, int Rw, int Rh, int S, int V, int n_points, float input_scaler,
+                    int legacy_mode, float* rec, float* z_vals, float* points, int* nearest, float* nearest_d2,
+                    void* stream);
 
 /* Fused FiLM-SIREN MLP + volume integration.  Replaces COORDCONCATSIREN.forward (modulated.py:41-75)
  * and vr.ray_integration (volume_rendering.py:12-56).
@@ -81,7 +88,10 @@ int hg_render_mlp(const float* rec, const float* z_vals, const float* noise, con
                   int last_back, int clamp_softplus, int passes, void* stream);
 
 /* ---- synthesis backbone ---------------------------------------------------------------------- */
-/* x0[C,Hg*Wg] = sin(w[:,0]*ic[i] + w[:,1]*jc[j] + b) (SynthesisInput, map3d_layers.py:260-275); when stats
+/* Synthesis activations use a tile-blocked planar layout [B, T, C, 128] with T = ceil(Hg*Wg/128): element
+ * (b, c, pixel p) lives at ((b*T + p/128)*C + c)*128 + p%128, so the 128 KB a CTA touches per tile are contiguous.
+ *
+ * x0[T,C,128] = sin(w[:,0]*ic[i] + w[:,1]*jc[j] + b) (SynthesisInput, map3d_layers.py:260-275); when stats
  * is non-null adds batch * (sum, sumsq) per channel to stats[0:C], stats[C:2C] (double). */
 int hg_synth_input(const float* w, const float* bias, const float* ic, const float* jc, int C, int Hg, int Wg,
                    float* x0, double* stats, int batch, void* stream);
@@ -98,10 +108,10 @@ int hg_bn_finalize(const double* stats, double count, const double* count_dev, c
  * accumulation and the (sum, sumsq) statistics of `out` for the next BatchNorm.
  * Replaces SPADE2d.forward + SPADEBlock.forward + ToRGB.forward (map3d_layers.py:176-190, 218-238, 346-352)
  * and, in pixel-style mode, the F.interpolate of map3d_generator.py:244-245.
- *   x [B or 1,C,HW] with batch stride x_bstride (0 = shared);  exactly one of
+ *   x [B or 1,T,C,128] with batch stride x_bstride (T*C*128, or 0 = shared by the batch);  exactly one of
  *   mod  [B,2,C]                      const-style (per-sample gamma/beta), or
  *   p_lr [B,Rh*Rw,p_stride] (+ p_bias [B,128], scsh [2,C], wgb packed [512x128], bgb [512])  pixel-style;
- *   wimg packed [C x C] conv weight; bias [C]; skip [B,C,HW] or NULL; out [B,C,HW];
+ *   wimg packed [C x C] conv weight; bias [C]; skip [B,T,C,128] or NULL; out [B,T,C,128];
  *   stats [2,C] double or NULL; rgb_w [3,C], rgb_b [3], rgb_in [B,3,HW] or NULL, rgb_out [B,3,HW] (all NULL = no ToRGB).
  *   C must be 256. */
 int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float* scsh, const float* p_lr,

@@ -12,8 +12,9 @@ def _setup(pkg, B, seed=5):
     return cond, {k: v.cuda() for k, v in cond.items()}
 
 
+@pytest.mark.parametrize("brute", [False, True])
 @pytest.mark.parametrize("legacy", [False, True])
-def test_knn_bit_exact_and_features(pkg, port, legacy):
+def test_knn_bit_exact_and_features(pkg, port, legacy, brute):
     """Same input points on both sides: nearest index and squared distance must be bit-exact."""
     abi = import_module("3dhumangan_b200.abi")
     abi.require_device()
@@ -29,7 +30,7 @@ def test_knn_bit_exact_and_features(pkg, port, legacy):
     d2_ref, _ = port.knn1(pts, cond["vertices"])
     vik = abi.vertex_ik(cg["fk_matrices"], cg["lbs_weights"])
     out = abi.geo_features(cg["vertices"], cg["tpose_vertices"], cg["skeletons_xyz"], vik, input_scaler=2 / 2.85,
-                           legacy_mode=legacy, points_in=pts.cuda(), want_nearest=True)
+                           legacy_mode=legacy, points_in=pts.cuda(), want_nearest=True, brute_force=brute)
     torch.cuda.synchronize()
     assert torch.equal(out["nearest"].cpu().long(), idx_ref), "nearest-vertex indices differ"
     assert torch.equal(out["nearest_d2"].cpu(), d2_ref), "squared distances not bit-exact"
@@ -75,3 +76,22 @@ def test_ray_sampling_matches_oracle(pkg, port):
     d2, idx = port.knn1(flat, cond["vertices"])
     mism = out["nearest"].cpu().long() != idx
     assert mism.float().mean() < 1e-3
+
+
+def test_pruned_knn_equals_brute_force_on_ray_samples(pkg):
+    """Exact pruning (Morton clusters + box lower bounds) must return the brute-force answer bit for bit,
+    including points far outside the body (most ray samples) and exact duplicates of vertices."""
+    abi = import_module("3dhumangan_b200.abi")
+    B = 2
+    cond, cg = _setup(pkg, B, seed=8)
+    g = torch.Generator().manual_seed(1)
+    pts = (torch.rand(B, 40000, 3, generator=g) - 0.5) * torch.tensor([3.0, 3.0, 1.5])
+    pts[0, :3000] = cond["vertices"][0, :3000]
+    pts[1, :3000] = cond["vertices"][1, 3000:6000] + 1e-4
+    vik = abi.vertex_ik(cg["fk_matrices"], cg["lbs_weights"])
+    kw = dict(input_scaler=1.0, points_in=pts.cuda(), want_nearest=True)
+    a = abi.geo_features(cg["vertices"], cg["tpose_vertices"], cg["skeletons_xyz"], vik, brute_force=False, **kw)
+    b = abi.geo_features(cg["vertices"], cg["tpose_vertices"], cg["skeletons_xyz"], vik, brute_force=True, **kw)
+    assert torch.equal(a["nearest"], b["nearest"])
+    assert torch.equal(a["nearest_d2"], b["nearest_d2"])
+    assert torch.equal(a["rec"], b["rec"])
