@@ -37,6 +37,10 @@ SIGNATURES = {
     "hg_render_mlp": (c_int, [c_void_p] * 12 + [c_int] * 4 + [c_float] + [c_int] * 4 + [c_void_p]),
     "hg_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 14 + [c_float, c_void_p]),
+    "hg_conv2d": (c_int, [c_void_p, c_int, c_void_p, c_int] + [c_int] * 6 + [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                              c_void_p, c_int, c_void_p]),
+    "hg_pool_add": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_void_p]),
+    "hg_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hg_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
@@ -231,3 +235,35 @@ def render_mlp(rec, z_vals, film, wblob, w_sigma, w_rgb, b_feat, heads_b, *, B, 
                                   int(bool(white_back)), int(bool(last_back)), int(clamp_mode == "softplus"), passes,
                                   stream())
     return (raw_out if raw else ray_out), weights
+
+
+def conv2d(x1, wimg, Cout, Nb, *, ksize, H, W, x2=None, up2=False, pre_lrelu=False, bias=None, residual=None,
+           res_up2=False, passes=3, out=None):
+    """Implicit-GEMM 3x3 / 1x1 convolution (csrc/dconv.cu).  x1 [B,C1,Hs,Ws] (+x2 concat) -> [B,Cout,H,W]."""
+    B, C1 = x1.shape[0], x1.shape[1]
+    C2 = 0 if x2 is None else x2.shape[1]
+    if out is None:
+        out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x1.device)
+    with torch.cuda.device_of(x1):
+        call("hg_conv2d", ptr(x1), C1, ptr(x2), C2, B, H, W, int(bool(up2)), int(bool(pre_lrelu)), ksize, ptr(wimg), Cout, Nb,
+             ptr(bias), ptr(residual), int(bool(res_up2)), ptr(out), passes, stream())
+    return out
+
+
+def pool_add(a, pool_a, b=None, pool_b=False):
+    """P_a(a) + P_b(b), P = 2x2 average pooling when flagged."""
+    Bn, C, Ha, Wa = a.shape
+    H, W = (Ha // 2, Wa // 2) if pool_a else (Ha, Wa)
+    out = torch.empty(Bn, C, H, W, dtype=torch.float32, device=a.device)
+    with torch.cuda.device_of(a):
+        call("hg_pool_add", ptr(a), int(bool(pool_a)), ptr(b), int(bool(pool_b)), ptr(out), Bn * C, H, W, stream())
+    return out
+
+
+def dense(x, w, bias):
+    B, K = x.shape
+    O = w.shape[0]
+    out = torch.empty(B, O, dtype=torch.float32, device=x.device)
+    with torch.cuda.device_of(x):
+        call("hg_dense", ptr(x), ptr(w), ptr(bias), ptr(out), B, K, O, stream())
+    return out

@@ -73,6 +73,10 @@ class UNetDiscriminator(nn.Module):
         self._cfg = {k: v for k, v in kwargs.items() if isinstance(k, str)}
 
     def forward(self, images, conditions, alpha, **kwargs):
-        """-> {"prediction": [B,1,H,W], "latents": [B,L], "segments": [B,label_dim,H,W]} (:125-160)."""
+        """-> {"prediction": [B,1,H,W], "latents": [B,L], "segments": [B,label_dim,H,W]} (:125-160).
+        `conditions`, `alpha` and other kwargs are accepted and ignored, as in the reference."""
         from . import discriminator_ops
+        if torch.is_grad_enabled() and (images.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("hg3d: the backward kernels of the sm_100a path are not built yet; call the "
+                               "discriminator under torch.no_grad()")
         return discriminator_ops.discriminator_forward(self, images)

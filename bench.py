@@ -239,6 +239,26 @@ def run_gpu(args, pkg):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    if os.environ.get("HG3D_BENCH_DEBUG") and rank == 0:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ev[0].record()
+            c = {k: v.to(dev, non_blocking=True) for k, v in cond_h.items()}
+            z = z_h.to(dev, non_blocking=True)
+            ev[1].record()
+            t1 = time.perf_counter()
+            r = G(z, c, **kw)["rgbs"]
+            ev[2].record()
+            t2 = time.perf_counter()
+            out_h.copy_(r, non_blocking=True)
+            ev[3].record()
+        t3 = time.perf_counter()
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        sys.stderr.write("e2e breakdown (device ms): h2d %.2f forward %.2f d2h %.2f | host ms: h2d-issue %.2f forward-issue %.2f "
+                         "d2h-issue %.2f drain %.2f\n" % (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]),
+                                                        (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3))
 
     imgs = B * world * args.steps
     value = imgs / (ms_total / 1000.0)

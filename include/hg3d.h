@@ -120,6 +120,22 @@ int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float*
                   const float* rgb_b, const float* rgb_in, float* rgb_out, int B, int C, int Hg, int Wg, int Rh, int Rw,
                   int passes, void* stream);
 
+/* ---- discriminator --------------------------------------------------------------------------- */
+/* 3x3 (pad 1) / 1x1 convolution over NCHW fp32 planes as an implicit GEMM; replaces the conv2d calls of
+ * ResBlock / UNetDiscriminator (unet_discriminators.py:7-72, 114-160) with the surrounding ops folded in:
+ *   x1 [B,C1,Hs,Ws] (+ x2 [B,C2,Hs,Ws]: channel concat, :147); up2: nearest x2 up-sample in front (Hs=H/2);
+ *   pre_lrelu: LeakyReLU(0.2) in front; wimg: hg_pack_weight of W permuted to [Cout, tap, Cin] (K = taps*Cin,
+ *   or 64 when taps*Cin <= 64); bias [Cout] or NULL; residual [B,Cout,H,W] (or [B,Cout,H/2,W/2] with res_up2)
+ *   added in the epilogue; out [B,Cout,H,W].  C1, C2 multiples of 64 (or taps*Cin <= 64); Cout <= 2*Nb. */
+int hg_conv2d(const float* x1, int C1, const float* x2, int C2, int B, int H, int W, int up2, int pre_lrelu, int ksize,
+              const void* wimg, int Cout, int Nb, const float* bias, const float* residual, int res_up2, float* out,
+              int passes, void* stream);
+/* out[planes,H,W] = P_a(a) + P_b(b); P = AvgPool2d(2) of a [planes,2H,2W] source when the flag is set (:42-44,52-54). */
+int hg_pool_add(const float* a, int pool_a, const float* b, int pool_b, float* out, long planes, int H, int W,
+                void* stream);
+/* out[B,O] = x[B,K] . w[O,K]^T + bias: the full-extent `latent_layer` convolution (:117-118,135). */
+int hg_dense(const float* x, const float* w, const float* bias, float* out, int B, int K, int O, void* stream);
+
 /* ---- StyleGAN3 native ops named by the reference ---------------------------------------------- */
 /* y = clamp(act(x + b[(i / stepB) % sizeB]) * gain)   replaces bias_act.cpp:32 / bias_act.cu:24 (forward).
  * act: 1 linear 2 relu 3 lrelu 4 tanh 5 sigmoid 6 elu 7 selu 8 softplus 9 swish; clamp < 0 disables. */
