@@ -103,10 +103,16 @@ def stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_DEVICE_OK = set()
+
+
 def require_device(t=None):
     if not torch.cuda.is_available():
         raise RuntimeError("hg3d: no CUDA device visible; the sm_100a kernels cannot run (no fallback)")
-    check(lib().hg_check_device(), "hg_check_device")
+    dev = torch.cuda.current_device()
+    if dev not in _DEVICE_OK:          # cudaGetDeviceProperties is slow: check each device once
+        check(lib().hg_check_device(), "hg_check_device")
+        _DEVICE_OK.add(dev)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kDcThreads, 1) conv_kernel(ConvArgs a) {
         for (int ck = 0; ck < nchunks; ++ck)
           for (int nb = 0; nb < a.nblocks; ++nb)
             for (int part = 0; part < (kPasses == 3 ? 2 : 1); ++part) {
-              mbar_wait(bars + DB_EMPTY + st, ph ^ 1);
+              mbar_wait_backoff(bars + DB_EMPTY + st, ph ^ 1);
               mbar_arrive_expect_tx(bars + DB_FULL + st, stage_bytes);
               bulk_g2s(b_st + st * kDcB,
                        a.wimg + (static_cast<size_t>(nb * nchunks + ck) * 2 + part) * stage_bytes, stage_bytes,

@@ -36,7 +36,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int K, in
   const size_t tile_bytes = static_cast<size_t>(Nb) * 128;
   uint8_t* hi = out + (static_cast<size_t>(nb * kchunks + kc) * 2 + 0) * tile_bytes;
   uint8_t* lo = hi + tile_bytes;
-  store_a8<true>(hi, lo, r, c * 8, x);
+  uint32_t h4[4], l4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_bf16x2(x[2 * i], x[2 * i + 1], h4[i], l4[i]);
+  const uint32_t off = sw128_offset(r, c * 8);
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+  *reinterpret_cast<uint4*>(lo + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -186,7 +191,7 @@ linear_kernel(const float* __restrict__ X, int ldx, int M, int K, const uint8_t*
         for (int nb = 0; nb < nblocks; ++nb)
           for (int kc = 0; kc < kchunks; ++kc)
             for (int part = 0; part < (kPasses == 3 ? 2 : 1); ++part) {
-              mbar_wait(b_empty + st, ph ^ 1);
+              mbar_wait_backoff(b_empty + st, ph ^ 1);
               mbar_arrive_expect_tx(b_full + st, tile_bytes);
               bulk_g2s(b_st + st * kStageBytesB,
                        Wimg + (static_cast<size_t>(nb * kchunks + kc) * 2 + part) * tile_bytes, tile_bytes,

@@ -160,16 +160,27 @@ __device__ __forceinline__ void film_epilogue(const RenSmem& m, uint32_t tmem_ac
     tmem_ld_wait();
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      float x[8];
+      float x[8], f8[8], p8[8];
+      lds8(F + c0 + g * 8, f8);
+      lds8(P + c0 + g * 8, p8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c0 + g * 8 + j;
-        x[j] = sin_reduced(fmaf(F[c], __uint_as_float(raw[g * 8 + j]), P[c]));
-        if (kHead == 1) d0 = fmaf(x[j], m.w_sigma[c], d0);
-        if (kHead == 2) {
-          d0 = fmaf(x[j], m.w_rgb[c], d0);
-          d1 = fmaf(x[j], m.w_rgb[kRH + c], d1);
-          d2 = fmaf(x[j], m.w_rgb[2 * kRH + c], d2);
+      for (int j = 0; j < 8; ++j) x[j] = sin_reduced(fmaf(f8[j], __uint_as_float(raw[g * 8 + j]), p8[j]));
+      if (kHead == 1) {
+        float w8[8];
+        lds8(m.w_sigma + c0 + g * 8, w8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d0 = fmaf(x[j], w8[j], d0);
+      }
+      if (kHead == 2) {
+        float w0[8], w1[8], w2[8];
+        lds8(m.w_rgb + c0 + g * 8, w0);
+        lds8(m.w_rgb + kRH + c0 + g * 8, w1);
+        lds8(m.w_rgb + 2 * kRH + c0 + g * 8, w2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          d0 = fmaf(x[j], w0[j], d0);
+          d1 = fmaf(x[j], w1[j], d1);
+          d2 = fmaf(x[j], w2[j], d2);
         }
       }
       store_a8<kPasses == 3>(m.a_hi + kc * kRA, m.a_lo + kc * kRA, row, h * 32 + g * 8, x);
@@ -356,7 +367,12 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
           tmem_ld_wait();
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = w * (__uint_as_float(raw[j]) + m.b_feat[c0 + j]);
+          for (int g = 0; g < 4; ++g) {
+            float b8[8];
+            lds8(m.b_feat + c0 + g * 8, b8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] = w * (__uint_as_float(raw[g * 8 + j]) + b8[j]);
+          }
           const float tot = transpose_reduce32r(v, lane);
           if (valid) ro[c0 + lane] = tot + back;   // `ro`/`valid` are warp-uniform here (S == 32)
         }
@@ -468,7 +484,7 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
       for (int it = 0; it < my_tiles; ++it)
         for (int sidx = 0; sidx < kWeightStages; ++sidx) {
           if (kPasses == 1 && (sidx & 1)) continue;
-          mbar_wait(m.bars + RB_EMPTY + st, ph ^ 1);
+          mbar_wait_backoff(m.bars + RB_EMPTY + st, ph ^ 1);
           mbar_arrive_expect_tx(m.bars + RB_FULL + st, kRB);
           bulk_g2s(m.b_st + st * kRB, a.wblob + static_cast<size_t>(sidx) * kRB, kRB, m.bars + RB_FULL + st);
           if (++st == kRenStages) { st = 0; ph ^= 1; }

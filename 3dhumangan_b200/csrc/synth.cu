@@ -4,21 +4,27 @@
 //  ToRGB :346-352, SynthesisNetwork.forward lib/generators/map3d_generator.py:58-97.)
 //
 // Activations live in HBM as fp32 in a tile-blocked planar layout [B, T, C=256, 128] (T = ceil(HW/128)
-// tiles of 128 consecutive pixels): the 128 KB a CTA reads / writes per tile are CONTIGUOUS (one DRAM
-// page stream, one TLB entry) while a warp still touches 32 consecutive pixels of one channel (128 B).
-// (The plain NCHW planes of the first version made every tile touch 256 planes 1 MB apart: 13% of the
-// HBM roofline, see profiles/r1_bench_v1_planar_layout.json.)  A CTA owns tiles
-// of 128 consecutive pixels of one image: 8 "row" warps build the bf16(x3) A operand in shared
-// memory (BN scale/shift, SPADE modulation, LeakyReLU fused into the operand producer), one
-// thread issues tcgen05.mma against weight tiles streamed from L2 by the bulk-copy engine, and
-// the row warps drain the fp32 accumulator from TMEM: bias, residual, ToRGB, per-channel
-// sum / sum-of-squares for the NEXT BatchNorm (so the SyncBN statistics never need a separate pass
-// over the activation), coalesced plane stores.
+// tiles of 128 consecutive pixels): the 128 KB a CTA reads / writes per tile are CONTIGUOUS, and every
+// 32-channel slice of a tile is one contiguous 16 KB block.
+//
+// Per CTA (352 threads), persistent over tiles of 128 pixels of one image:
+//   warps 0-7  "row" warps: read the activation slices from the shared-memory staging ring, apply
+//              BN scale/shift + SPADE modulation + LeakyReLU, split to bf16 hi/lo and write the A
+//              operand (2-slot ring of [128 x 64] K-major SW128 tiles); later drain the fp32
+//              accumulator from TMEM: bias, residual, ToRGB, per-channel sum / sum-of-squares for
+//              the NEXT BatchNorm (the SyncBN statistics never need their own pass), plane stores.
+//   warp 8     one thread issues tcgen05.mma (M=128, N=256, K=16; bf16x3 split or plain bf16).
+//   warp 9     one thread streams the packed weight tiles from L2 (cp.async.bulk, 2 x 32 KB stages).
+//   warp 10    one thread streams the activation (and residual) slices from HBM into a 5 x 16 KB
+//              staging ring with cp.async.bulk, several slices ahead of the row warps and across
+//              tile boundaries: ~80 KB in flight per SM without spending registers, which is what
+//              an HBM-bound kernel needs (v1 kept <= 32 KB in flight through registers and reached
+//              26 % of the HBM roofline, profiles/r1_*).
 //
 // Two variants:
 //   const-style : gamma/beta are per-sample vectors (blocks whose style map is spatially
-//                 constant, 12 of 18 half-blocks in 'mixed'/'isolated' mode).  Pipelined:
-//                 operand production of tile t+1 overlaps the MMAs of tile t (2 TMEM accumulators).
+//                 constant, 12 of 18 half-blocks in 'mixed'/'isolated' mode).  Operand production of
+//                 tile t+1 overlaps the MMAs of tile t (2 TMEM accumulators).
 //   pixel-style : gamma/beta come from a second GEMM on relu(bilinear_up(P_lr)) where
 //                 P_lr = W_shared . feature_maps + b at RENDER resolution (W_shared commutes with
 //                 the bilinear up-sample), so the 28x larger up-sampled style map of
@@ -29,10 +35,13 @@
 namespace hg {
 
 constexpr int kC = 256;             // channels (hidden_dim == feature_dim == 256)
-constexpr int kSynThreads = 320;    // warps 0-7 rows, 8 MMA, 9 weight producer
-constexpr int kSynStages = 2;
+constexpr int kSynThreads = 352;    // warps 0-7 rows, 8 MMA, 9 weight producer, 10 activation producer
+constexpr int kSynStages = 2;       // weight stages
+constexpr int kASlots = 2;          // operand ring
+constexpr int kXSlots = 5;          // activation staging ring
 constexpr uint32_t kAChunk = 128 * 128;   // [128 x 64] bf16
 constexpr uint32_t kBStage = 256 * 128;   // [256 x 64] bf16
+constexpr uint32_t kXSlice = 32 * 128 * 4;  // 32 channels x 128 pixels fp32
 
 struct SpadeArgs {
   const float* x;        // [B or 1, T, C, 128] tile-blocked
@@ -57,9 +66,10 @@ struct SpadeArgs {
 };
 
 struct SynSmem {
-  uint8_t* a_hi;
+  uint8_t* a_hi;   // [kASlots] chunks
   uint8_t* a_lo;
   uint8_t* b_st;
+  float* x_st;     // [kXSlots][32][128]
   float* tab_g1;   // [C]  (const: g1 | pixel: bn scale)
   float* tab_g0;   // [C]  (const: g0 | pixel: bn shift)
   float* tab_bias; // [C]
@@ -76,9 +86,10 @@ __device__ __forceinline__ SynSmem carve(uint8_t* raw) {
   uint8_t* s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   SynSmem m;
   m.a_hi = s;
-  m.a_lo = s + 4 * kAChunk;
-  m.b_st = s + 8 * kAChunk;
-  float* f = reinterpret_cast<float*>(m.b_st + kSynStages * kBStage);
+  m.a_lo = s + kASlots * kAChunk;
+  m.b_st = s + 2 * kASlots * kAChunk;
+  m.x_st = reinterpret_cast<float*>(m.b_st + kSynStages * kBStage);
+  float* f = m.x_st + kXSlots * (kXSlice / 4);
   m.tab_g1 = f; f += kC;
   m.tab_g0 = f; f += kC;
   m.tab_bias = f; f += kC;
@@ -88,18 +99,21 @@ __device__ __forceinline__ SynSmem carve(uint8_t* raw) {
   m.st_sq = f; f += kC;
   m.rgb_part = f; f += 2 * 128 * 3;
   m.bars = reinterpret_cast<uint64_t*>(f);
-  m.tmem_slot = reinterpret_cast<uint32_t*>(m.bars + 32);
+  m.tmem_slot = reinterpret_cast<uint32_t*>(m.bars + 40);
   return m;
 }
-constexpr uint32_t kSynSmemBytes = 8 * kAChunk + kSynStages * kBStage + (kC * 8 + 512 + 768) * 4 + 32 * 8 + 16 + 1024;
+constexpr uint32_t kSynSmemBytes = 2 * kASlots * kAChunk + kSynStages * kBStage + kXSlots * kXSlice +
+                                   (kC * 8 + 512 + 768) * 4 + 40 * 8 + 16 + 1024;
+static_assert(kSynSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots
-enum { A_FULL = 0 /*4*/, A_EMPTY = 4 /*4*/, B_FULL = 8 /*2*/, B_EMPTY = 10 /*2*/, ACC_FULL = 12 /*2*/,
-       ACC_EMPTY = 14 /*2*/, G1_FULL = 16, A1_FULL = 17, Y_FULL = 18 };
+enum { A_FULL = 0 /*2*/, A_EMPTY = 2 /*2*/, B_FULL = 4 /*2*/, B_EMPTY = 6 /*2*/, ACC_FULL = 8 /*2*/,
+       ACC_EMPTY = 10 /*2*/, G1_FULL = 12, A1_FULL = 13, X_FULL = 16 /*5*/, X_EMPTY = 24 /*5*/ };
 
 __device__ __forceinline__ void rows_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+
 
 // 32 lanes x 32 values: after the call lane j holds sum over lanes of v[j].
 __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
@@ -120,8 +134,8 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 // shared pieces
 // ------------------------------------------------------------------------------------------
 template <int kPasses>
-__device__ __forceinline__ void producer_loop(const SynSmem& m, const uint8_t* const* imgs, const int* nstages,
-                                              int nimgs, int num_my_tiles) {
+__device__ __forceinline__ void weight_producer_loop(const SynSmem& m, const uint8_t* const* imgs, const int* nstages,
+                                                     int nimgs, int num_my_tiles) {
   // Every tile consumes the same sequence of weight stages: for each image, `nstages` tiles of
   // [256 x 64] in storage order (kc-major, hi then lo); the lo tiles are skipped in 1-pass mode.
   uint32_t st = 0, ph = 0;
@@ -129,12 +143,54 @@ __device__ __forceinline__ void producer_loop(const SynSmem& m, const uint8_t* c
     for (int g = 0; g < nimgs; ++g)
       for (int s = 0; s < nstages[g]; ++s) {
         if (kPasses == 1 && (s & 1)) continue;
-        mbar_wait(m.bars + B_EMPTY + st, ph ^ 1);
+        mbar_wait_backoff(m.bars + B_EMPTY + st, ph ^ 1);
         mbar_arrive_expect_tx(m.bars + B_FULL + st, kBStage);
         bulk_g2s(m.b_st + st * kBStage, imgs[g] + static_cast<size_t>(s) * kBStage, kBStage, m.bars + B_FULL + st);
         if (++st == kSynStages) { st = 0; ph ^= 1; }
       }
 }
+
+// Activation staging ring, producer side: one 16 KB slice (32 channels x 128 pixels) per call.
+struct XProducer {
+  uint32_t g = 0;
+  __device__ __forceinline__ void emit(const SynSmem& m, const float* src) {
+    const uint32_t slot = g % kXSlots, ph = (g / kXSlots) & 1;
+    mbar_wait_backoff(m.bars + X_EMPTY + slot, ph ^ 1);
+    mbar_arrive_expect_tx(m.bars + X_FULL + slot, kXSlice);
+    bulk_g2s(m.x_st + slot * (kXSlice / 4), src, kXSlice, m.bars + X_FULL + slot);
+    ++g;
+  }
+};
+// Consumer side.  EVERY consuming warp waits for and releases EVERY slice, in order; only the owning
+// column half (slice index parity == h) actually reads it.  (With per-half arrivals a slot of an odd-sized
+// ring alternates between the halves and a fast half can get two phases ahead of the slot -- the parity wait
+// then succeeds on a stale phase.  That race produced launch failures; see DESIGN.md "Pitfalls".)
+struct XConsumer {
+  uint32_t g = 0;
+  uint32_t slot = 0;
+  __device__ __forceinline__ const float* begin(const SynSmem& m) {
+    slot = g % kXSlots;
+    mbar_wait(m.bars + X_FULL + slot, (g / kXSlots) & 1);
+    return m.x_st + slot * (kXSlice / 4);
+  }
+  __device__ __forceinline__ void end(const SynSmem& m, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(m.bars + X_EMPTY + slot);
+    ++g;
+  }
+  // read this warp's 32 values of the slice pair (2*kc, 2*kc+1): half h owns slice 2*kc + h
+  __device__ __forceinline__ void take_pair(const SynSmem& m, int h, int row, int lane, float (&dst)[32]) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const uint32_t xs = smem_u32(begin(m)) + row * 4;
+      if (hh == h) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = lds_f32(xs + j * 512);
+      }
+      end(m, lane);
+    }
+  }
+};
 
 struct MmaPipe {
   uint32_t st = 0, ph = 0;
@@ -159,9 +215,9 @@ __device__ __forceinline__ void mma_chunk(const SynSmem& m, MmaPipe& p, uint32_t
   }
 }
 
-// Drain one accumulator: bias, residual, stats, ToRGB, plane stores.
-__device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem& m, uint32_t tmem_acc, int b, int p0,
-                                              int warp, int lane) {
+// Drain one accumulator: bias, residual (from the staging ring), stats, ToRGB, plane stores.
+__device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem& m, XConsumer& xc, uint32_t tmem_acc,
+                                              int b, int p0, int warp, int lane) {
   const int q = warp & 3, h = warp >> 2;
   const int row = q * 32 + lane;
   const int pix = p0 + row;
@@ -174,12 +230,9 @@ __device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem&
     const int c0 = kc * 64 + h * 32;
     uint32_t raw[32];
     tmem_ld32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
-    // residual input: issue all 32 loads before anything depends on them (read-only path; a load placed
-    // next to its store is serialised behind the store by the aliasing rules: 128 exposed latencies per tile)
     float sk[32];
     if (a.skip) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sk[j] = valid ? __ldg(a.skip + plane + (c0 + j) * 128) : 0.f;
+      xc.take_pair(m, h, row, lane, sk);
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) sk[j] = 0.f;
@@ -187,16 +240,29 @@ __device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem&
     tmem_ld_wait();
     float v[32], s2[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float o = __uint_as_float(raw[j]) + m.tab_bias[c0 + j] + sk[j];
-      if (valid) a.out[plane + (c0 + j) * 128] = o;
-      o = valid ? o : 0.f;
-      v[j] = o;
-      s2[j] = o * o;
+    for (int g = 0; g < 4; ++g) {
+      float bs[8];
+      lds8(m.tab_bias + c0 + g * 8, bs);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = g * 8 + jj;
+        float o = __uint_as_float(raw[j]) + bs[jj] + sk[j];
+        if (valid) a.out[plane + (c0 + j) * 128] = o;
+        o = valid ? o : 0.f;
+        v[j] = o;
+        s2[j] = o * o;
+      }
       if (a.rgb_w) {
-        r0 = fmaf(o, m.tab_rgbw[c0 + j], r0);
-        r1 = fmaf(o, m.tab_rgbw[kC + c0 + j], r1);
-        r2 = fmaf(o, m.tab_rgbw[2 * kC + c0 + j], r2);
+        float w0[8], w1[8], w2[8];
+        lds8(m.tab_rgbw + c0 + g * 8, w0);
+        lds8(m.tab_rgbw + kC + c0 + g * 8, w1);
+        lds8(m.tab_rgbw + 2 * kC + c0 + g * 8, w2);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          r0 = fmaf(v[g * 8 + jj], w0[jj], r0);
+          r1 = fmaf(v[g * 8 + jj], w1[jj], r1);
+          r2 = fmaf(v[g * 8 + jj], w2[jj], r2);
+        }
       }
     }
     if (a.stats) {
@@ -227,7 +293,8 @@ __device__ __forceinline__ void rgb_finish(const SpadeArgs& a, const SynSmem& m,
   }
 }
 
-__device__ __forceinline__ void init_common(const SpadeArgs& a, const SynSmem& m, int warp) {
+__device__ __forceinline__ void init_common(const SpadeArgs& a, const SynSmem& m, int tmem_warp, int warp, int acc_empty_count,
+                                            int x_slots, int x_count, int s_count) {
   for (int i = threadIdx.x; i < kC; i += blockDim.x) {
     m.tab_bias[i] = a.bias[i];
     m.st_sum[i] = 0.f;
@@ -236,7 +303,7 @@ __device__ __forceinline__ void init_common(const SpadeArgs& a, const SynSmem& m
   if (a.rgb_w)
     for (int i = threadIdx.x; i < 3 * kC; i += blockDim.x) m.tab_rgbw[i] = a.rgb_w[i];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kASlots; ++i) {
       mbar_init(m.bars + A_FULL + i, 8);
       mbar_init(m.bars + A_EMPTY + i, 1);
     }
@@ -246,14 +313,17 @@ __device__ __forceinline__ void init_common(const SpadeArgs& a, const SynSmem& m
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(m.bars + ACC_FULL + i, 1);
-      mbar_init(m.bars + ACC_EMPTY + i, 8);
+      mbar_init(m.bars + ACC_EMPTY + i, acc_empty_count);
     }
     mbar_init(m.bars + G1_FULL, 1);
     mbar_init(m.bars + A1_FULL, 8);
-    mbar_init(m.bars + Y_FULL, 8);
+    for (int i = 0; i < kXSlots; ++i) {   // slots [0, x_slots): activation ring; the rest: residual ring (const kernel)
+      mbar_init(m.bars + X_FULL + i, 1);
+      mbar_init(m.bars + X_EMPTY + i, i < x_slots ? x_count : s_count);
+    }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<512>(m.tmem_slot);
+  if (warp == tmem_warp) tmem_alloc<512>(m.tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -269,29 +339,53 @@ __device__ __forceinline__ void flush_stats(const SpadeArgs& a, const SynSmem& m
   }
 }
 
+// slices of one tile in consumption order: 8 x 16 KB (channels 32j .. 32j+31)
+__device__ __forceinline__ void emit_tile(const SynSmem& m, XProducer& xp, const float* tile_base) {
+  for (int j = 0; j < 8; ++j) xp.emit(m, tile_base + j * 32 * 128);
+}
+
 // ------------------------------------------------------------------------------------------
-// const-style variant (pipelined)
+// const-style variant: operand-producer team and epilogue team run CONCURRENTLY on different tiles
 // ------------------------------------------------------------------------------------------
+//   warps 0-7   P team: staging ring -> BN/modulation/lrelu -> bf16 hi/lo operand (tile t+1)
+//   warps 8-11  E team: TMEM accumulator of tile t -> bias/residual/ToRGB/statistics -> HBM; warp 8+q
+//               owns TMEM lanes 32q..32q+31 and all 256 columns
+//   warp 12 MMA issuer, warp 13 weight producer, warp 14 activation / residual producer
+// v2 ran prologue(t+1) and epilogue(t) back to back on the same 8 warps (2 per scheduler, latency-bound:
+// 26.6 % tensor, 45 % of DRAM peak).  Here a scheduler holds 2 P warps + 1 E warp and the tile period is
+// max(T_P, T_E, T_MMA) instead of T_P + T_E.
+constexpr int kConstThreads = 480;
+constexpr int kXs = 3;   // staging slots 0..2: activation slices (P team)
+constexpr int kSs = 2;   // staging slots 3..4: residual slices (E team)
+
 template <int kPasses>
-__global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a) {
+__global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const SynSmem m = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  init_common(a, m, warp);
+  init_common(a, m, /*tmem_warp=*/12, warp, /*acc_empty_count=*/4, kXs, /*x_count=*/8, /*s_count=*/4);
   const uint32_t tmem = *m.tmem_slot;
-  const int tiles_per_img = (a.HW + 127) / 128;
-  const int num_tiles = a.B * tiles_per_img;
+  const int T = (a.HW + 127) / 128;
+  const int num_tiles = a.B * T;
   const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  auto tile_of = [&](int it, int& b, int& ti) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    b = tile / T;
+    ti = tile - b * T;
+  };
 
   if (warp < 8) {
+    // ------------------------------------------------------------------ P team
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     int cur_b = -1;
-    auto prologue = [&](int it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int b = tile / tiles_per_img, p0 = (tile % tiles_per_img) * 128;
+    uint32_t acnt = 0;   // operand chunks produced (2-slot ring)
+    uint32_t xg = 0;     // activation slices: every P warp walks every slice, half h reads the ones with parity h
+    for (int it = 0; it < my_tiles; ++it) {
+      int b, ti;
+      tile_of(it, b, ti);
       if (b != cur_b) {  // refresh the per-sample modulation table
-        rows_barrier();  // everyone finished reading the previous table
+        rows_barrier();
         for (int i = threadIdx.x; i < kC; i += 256) {
           m.tab_g1[i] = a.mod[(static_cast<long>(b) * 2 + 0) * kC + i];
           m.tab_g0[i] = a.mod[(static_cast<long>(b) * 2 + 1) * kC + i];
@@ -299,95 +393,192 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
         rows_barrier();
         cur_b = b;
       }
-      const int pix = p0 + row;
-      const bool valid = pix < a.HW;
-      // Out-of-range rows read the tile's first pixel (always valid) and are zeroed afterwards.
-      const float* xp = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(p0 >> 7) * kC * 128 + (valid ? row : 0);
-      // All 32 loads of a chunk are issued back to back (volatile asm keeps ptxas from re-batching them in
-      // groups of 8) and the NEXT chunk's loads are in flight while this chunk is converted and stored.
-      float xv[2][32];
-      auto issue = [&](float (&dst)[32], int kc) {
-        const float* src = xp + (kc * 64 + h * 32) * 128;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dst[j]) : "l"(src + j * 128));
-      };
-      issue(xv[0], 0);
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        if (kc < 3) issue(xv[(kc + 1) & 1], kc + 1);
-        mbar_wait(m.bars + A_EMPTY + kc, (it & 1) ^ 1);
+      const bool valid = ti * 128 + row < a.HW;
+#pragma unroll 1
+      for (int kc = 0; kc < 4; ++kc, ++acnt) {
         const int c0 = kc * 64 + h * 32;
-        float (&cur)[32] = xv[kc & 1];
+        float cur[32];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh, ++xg) {
+          const uint32_t xslot = xg % kXs;
+          mbar_wait(m.bars + X_FULL + xslot, (xg / kXs) & 1);
+          if (hh == h) {
+            const uint32_t xs = smem_u32(m.x_st + xslot * (kXSlice / 4)) + row * 4;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cur[j] = lds_f32(xs + j * 512);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(m.bars + X_EMPTY + xslot);
+        }
+        const uint32_t slot = acnt & 1;
+        mbar_wait(m.bars + A_EMPTY + slot, ((acnt >> 1) & 1) ^ 1);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float y[8];
+          float y[8], t1[8], t0[8];
+          lds8(m.tab_g1 + c0 + g * 8, t1);
+          lds8(m.tab_g0 + c0 + g * 8, t0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = c0 + g * 8 + j;
-            y[j] = valid ? lrelu02(fmaf(cur[g * 8 + j], m.tab_g1[c], m.tab_g0[c])) : 0.f;
-          }
-          store_a8<kPasses == 3>(m.a_hi + kc * kAChunk, m.a_lo + kc * kAChunk, row, h * 32 + g * 8, y);
+          for (int j = 0; j < 8; ++j) y[j] = valid ? lrelu02(fmaf(cur[g * 8 + j], t1[j], t0[j])) : 0.f;
+          store_a8<kPasses == 3>(m.a_hi + slot * kAChunk, m.a_lo + slot * kAChunk, row, h * 32 + g * 8, y);
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(m.bars + A_FULL + kc);
+        if (lane == 0) mbar_arrive(m.bars + A_FULL + slot);
       }
-    };
-    auto epilogue = [&](int it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int b = tile / tiles_per_img, p0 = (tile % tiles_per_img) * 128;
+    }
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ E team
+    const int q = warp - 8;
+    const int row = q * 32 + lane;
+    uint32_t sg = 0;   // residual slices consumed
+    for (int it = 0; it < my_tiles; ++it) {
+      int b, ti;
+      tile_of(it, b, ti);
       const uint32_t buf = it & 1;
+      const int pix = ti * 128 + row;
+      const bool valid = pix < a.HW;
+      const long plane = (static_cast<long>(b) * T + ti) * kC * 128 + row;
       mbar_wait(m.bars + ACC_FULL + buf, (it >> 1) & 1);
       tc_fence_after();
-      conv_epilogue(a, m, tmem + buf * 256, b, p0, warp, lane);
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll 1
+      for (int cg = 0; cg < 8; ++cg) {
+        const int c0 = cg * 32;
+        uint32_t raw[32];
+        tmem_ld32(tmem + buf * 256 + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
+        float sk[32];
+        if (a.skip) {
+          const uint32_t sslot = kXs + sg % kSs;
+          mbar_wait(m.bars + X_FULL + sslot, (sg / kSs) & 1);
+          const uint32_t xs = smem_u32(m.x_st + sslot * (kXSlice / 4)) + row * 4;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sk[j] = lds_f32(xs + j * 512);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(m.bars + X_EMPTY + sslot);
+          ++sg;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sk[j] = 0.f;
+        }
+        tmem_ld_wait();
+        float v[32], s2[32];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float bs[8];
+          lds8(m.tab_bias + c0 + g * 8, bs);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int j = g * 8 + jj;
+            float o = __uint_as_float(raw[j]) + bs[jj] + sk[j];
+            if (valid) a.out[plane + (c0 + j) * 128] = o;
+            o = valid ? o : 0.f;
+            v[j] = o;
+            s2[j] = o * o;
+          }
+          if (a.rgb_w) {
+            float w0[8], w1[8], w2[8];
+            lds8(m.tab_rgbw + c0 + g * 8, w0);
+            lds8(m.tab_rgbw + kC + c0 + g * 8, w1);
+            lds8(m.tab_rgbw + 2 * kC + c0 + g * 8, w2);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              r0 = fmaf(v[g * 8 + jj], w0[jj], r0);
+              r1 = fmaf(v[g * 8 + jj], w1[jj], r1);
+              r2 = fmaf(v[g * 8 + jj], w2[jj], r2);
+            }
+          }
+        }
+        if (a.stats) {
+          const float t1 = transpose_reduce32(v, lane);
+          const float t2 = transpose_reduce32(s2, lane);
+          atomicAdd(m.st_sum + c0 + lane, t1);
+          atomicAdd(m.st_sq + c0 + lane, t2);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(m.bars + ACC_EMPTY + buf);
-      if (a.rgb_w) {
-        rows_barrier();
-        rgb_finish(a, m, b, p0, warp, lane);
-        rows_barrier();
+      if (a.rgb_w && valid) {   // this thread saw all 256 channels of its pixel
+        const float r[3] = {r0, r1, r2};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const long idx = (static_cast<long>(b) * 3 + j) * a.HW + pix;
+          float o = r[j] + a.rgb_b[j];
+          if (a.rgb_in) o += a.rgb_in[idx];
+          a.rgb_out[idx] = o;
+        }
       }
-    };
-    if (my_tiles > 0) prologue(0);
-    for (int it = 0; it < my_tiles; ++it) {
-      if (it + 1 < my_tiles) prologue(it + 1);
-      epilogue(it);
     }
-    rows_barrier();
-    flush_stats(a, m);
-  } else if (warp == 8) {
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (a.stats) {
+      for (int c = threadIdx.x - 256; c < kC; c += 128) {
+        atomicAdd(a.stats + c, static_cast<double>(m.st_sum[c]));
+        atomicAdd(a.stats + kC + c, static_cast<double>(m.st_sq[c]));
+      }
+    }
+  } else if (warp == 12) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 256);
       MmaPipe p;
+      uint32_t acnt = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(m.bars + ACC_EMPTY + buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int kc = 0; kc < 4; ++kc) {
-          mbar_wait(m.bars + A_FULL + kc, it & 1);
+        for (int kc = 0; kc < 4; ++kc, ++acnt) {
+          const uint32_t slot = acnt & 1;
+          mbar_wait(m.bars + A_FULL + slot, (acnt >> 1) & 1);
           tc_fence_after();
-          mma_chunk<kPasses>(m, p, tmem + buf * 256, smem_u32(m.a_hi + kc * kAChunk), smem_u32(m.a_lo + kc * kAChunk),
+          mma_chunk<kPasses>(m, p, tmem + buf * 256, smem_u32(m.a_hi + slot * kAChunk), smem_u32(m.a_lo + slot * kAChunk),
                              idesc, kc > 0);
-          umma_commit(m.bars + A_EMPTY + kc);
+          umma_commit(m.bars + A_EMPTY + slot);
         }
         umma_commit(m.bars + ACC_FULL + buf);
       }
     }
-  } else {
+  } else if (warp == 13) {
     if (lane == 0) {
       const uint8_t* imgs[1] = {a.wimg};
       const int ns[1] = {8};
-      producer_loop<kPasses>(m, imgs, ns, 1, my_tiles);
+      weight_producer_loop<kPasses>(m, imgs, ns, 1, my_tiles);
+    }
+  } else {
+    if (lane == 0) {
+      // two independent rings: activation slices for the P team (slots 0..2), residual slices for the E team
+      // (slots 3..4).  The P team runs one tile ahead of the E team, so interleave x(it+1) with skip(it).
+      uint32_t xg = 0, sg = 0;
+      auto emit_x = [&](const float* src) {
+        const uint32_t slot = xg % kXs;
+        mbar_wait_backoff(m.bars + X_EMPTY + slot, ((xg / kXs) & 1) ^ 1);
+        mbar_arrive_expect_tx(m.bars + X_FULL + slot, kXSlice);
+        bulk_g2s(m.x_st + slot * (kXSlice / 4), src, kXSlice, m.bars + X_FULL + slot);
+        ++xg;
+      };
+      auto emit_s = [&](const float* src) {
+        const uint32_t slot = kXs + sg % kSs;
+        mbar_wait_backoff(m.bars + X_EMPTY + slot, ((sg / kSs) & 1) ^ 1);
+        mbar_arrive_expect_tx(m.bars + X_FULL + slot, kXSlice);
+        bulk_g2s(m.x_st + slot * (kXSlice / 4), src, kXSlice, m.bars + X_FULL + slot);
+        ++sg;
+      };
+      auto xbase = [&](int it) { int b, ti; tile_of(it, b, ti); return a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * kC * 128; };
+      auto sbase = [&](int it) { int b, ti; tile_of(it, b, ti); return a.skip + (static_cast<long>(b) * T + ti) * kC * 128; };
+      if (my_tiles > 0)
+        for (int j = 0; j < 8; ++j) emit_x(xbase(0) + j * 32 * 128);
+      for (int it = 0; it < my_tiles; ++it)
+        for (int j = 0; j < 8; ++j) {
+          if (it + 1 < my_tiles) emit_x(xbase(it + 1) + j * 32 * 128);
+          if (a.skip) emit_s(sbase(it) + j * 32 * 128);
+        }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tmem);
+  if (warp == 12) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
-// pixel-style variant (sequential phases per tile)
+// pixel-style variant
 // ------------------------------------------------------------------------------------------
 // PyTorch's bilinear source index (align_corners=False): src = max(scale*(dst+0.5)-0.5, 0)
 __device__ __forceinline__ void bilin(int dst, int in_size, float scale, int& i0, int& i1, float& l0, float& l1) {
@@ -399,6 +590,9 @@ __device__ __forceinline__ void bilin(int dst, int in_size, float scale, int& i0
   l0 = 1.f - l1;
 }
 
+// Per tile: A1 = relu(bilinear(P_lr)+c) [2 chunks] -> GEMM1 (gamma|beta, 4 x N=256 accumulations into both
+// TMEM halves) -> y = lrelu(BN(x)*(1+gamma)+beta) [4 chunks through the 2-slot ring, chunk-pipelined with
+// GEMM2 from chunk 2 on] -> GEMM2 (conv) into TMEM half A (free once chunks 0,1 of y are built) -> epilogue.
 template <int kPasses>
 __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -409,23 +603,32 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
     m.tab_g0[i] = a.scsh[kC + i];
   }
   for (int i = threadIdx.x; i < 512; i += blockDim.x) m.tab_bgb[i] = a.bgb[i];
-  init_common(a, m, warp);
+  init_common(a, m, /*tmem_warp=*/8, warp, /*acc_empty_count=*/8, kXSlots, /*x_count=*/8, /*s_count=*/8);
   const uint32_t tmem = *m.tmem_slot;
-  const int tiles_per_img = (a.HW + 127) / 128;
-  const int num_tiles = a.B * tiles_per_img;
+  const int T = (a.HW + 127) / 128;
+  const int num_tiles = a.B * T;
   const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const float sy = static_cast<float>(a.Rh) / static_cast<float>(a.Hg);
   const float sx = static_cast<float>(a.Rw) / static_cast<float>(a.Wg);
+  auto tile_of = [&](int it, int& b, int& ti) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    b = tile / T;
+    ti = tile - b * T;
+  };
 
   if (warp < 8) {
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
+    uint32_t acnt = 0;
+    XConsumer xc;
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int b = tile / tiles_per_img, p0 = (tile % tiles_per_img) * 128;
+      int b, ti;
+      tile_of(it, b, ti);
+      const int p0 = ti * 128;
       const int pix = p0 + row;
       const bool valid = pix < a.HW;
-      // ---- phase 0: A1 = relu(bilinear(P_lr)) for this warp's half of the 128 shared channels
+      // ---- phase 0: A1 = relu(bilinear(P_lr) + c): column half h builds K chunk h (slot h of the ring).
+      // The ring is empty here: the previous tile's GEMM2 finished before its epilogue (ACC_FULL).
       {
         const int py = valid ? pix / a.Wg : 0, px = valid ? pix % a.Wg : 0;
         int y0, y1, x0, x1;
@@ -438,7 +641,6 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
         const float4* n10 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * a.Rw + x0) * a.p_stride);
         const float4* n11 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * a.Rw + x1) * a.p_stride);
         const float4* pb = a.p_bias ? reinterpret_cast<const float4*>(a.p_bias + static_cast<long>(b) * 128) : nullptr;
-        // this warp covers shared channels [h*64, h*64+64) == K chunk h of A1
 #pragma unroll 2
         for (int g = 0; g < 8; ++g) {
           float y[8];
@@ -464,50 +666,48 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
         __syncwarp();
         if (lane == 0) mbar_arrive(m.bars + A1_FULL);
       }
-      // ---- phase 1: gamma/beta accumulators -> y = lrelu(BN(x)*(1+gamma)+beta) -> A (4 chunks)
-      const float* xp = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(p0 >> 7) * kC * 128 + (valid ? row : 0);
-      float xv[2][32];
-      auto issue = [&](float (&dst)[32], int kc) {
-        const float* src = xp + (kc * 64 + h * 32) * 128;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dst[j]) : "l"(src + j * 128));
-      };
-      issue(xv[0], 0);   // in flight while the gamma/beta GEMM finishes
+      // ---- phase 1: gamma/beta accumulators -> y = lrelu(BN(x)*(1+gamma)+beta) -> operand ring
       mbar_wait(m.bars + G1_FULL, it & 1);
       tc_fence_after();
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        if (kc < 3) issue(xv[(kc + 1) & 1], kc + 1);
+#pragma unroll 1
+      for (int kc = 0; kc < 4; ++kc, ++acnt) {
         const int c0 = kc * 64 + h * 32;
         const uint32_t col = (kc >> 1) * 256 + (kc & 1) * 128 + h * 32;
         uint32_t gr[32], br[32];
         tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + col, gr);
         tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + col + 64, br);
+        float cur[32];
+        xc.take_pair(m, h, row, lane, cur);
         tmem_ld_wait();
-        float (&cur)[32] = xv[kc & 1];
+        const uint32_t slot = acnt & 1;
+        // chunks 0,1 overwrite A1 (free: G1_FULL); chunks 2,3 wait for GEMM2 to have consumed chunks 0,1
+        mbar_wait(m.bars + A_EMPTY + slot, ((acnt >> 1) & 1) ^ 1);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float y[8];
+          float y[8], bg[8], bb[8], t1[8], t0[8];
+          lds8(m.tab_bgb + col + g * 8, bg);
+          lds8(m.tab_bgb + col + 64 + g * 8, bb);
+          lds8(m.tab_g1 + c0 + g * 8, t1);
+          lds8(m.tab_g0 + c0 + g * 8, t0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int jj = g * 8 + j;
-            const int c = c0 + jj;
-            const float gam = __uint_as_float(gr[jj]) + m.tab_bgb[col + jj];        // 1 + gamma
-            const float bet = __uint_as_float(br[jj]) + m.tab_bgb[col + 64 + jj];   // beta
-            const float xn = fmaf(cur[jj], m.tab_g1[c], m.tab_g0[c]);
+            const float gam = __uint_as_float(gr[jj]) + bg[j];        // 1 + gamma
+            const float bet = __uint_as_float(br[jj]) + bb[j];        // beta
+            const float xn = fmaf(cur[jj], t1[j], t0[j]);
             y[j] = valid ? lrelu02(fmaf(xn, gam, bet)) : 0.f;
           }
-          store_a8<kPasses == 3>(m.a_hi + kc * kAChunk, m.a_lo + kc * kAChunk, row, h * 32 + g * 8, y);
+          store_a8<kPasses == 3>(m.a_hi + slot * kAChunk, m.a_lo + slot * kAChunk, row, h * 32 + g * 8, y);
         }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(m.bars + A_FULL + slot);
       }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(m.bars + Y_FULL);
       // ---- phase 2: conv accumulator
       mbar_wait(m.bars + ACC_FULL, it & 1);
       tc_fence_after();
-      conv_epilogue(a, m, tmem, b, p0, warp, lane);
+      conv_epilogue(a, m, xc, tmem, b, p0, warp, lane);
       tc_fence_before();
       rows_barrier();
       if (a.rgb_w) {
@@ -523,6 +723,7 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 256);
       MmaPipe p;
+      uint32_t acnt = 0;
       for (int it = 0; it < my_tiles; ++it) {
         // TMEM (both halves) is free once the previous tile's conv epilogue has drained
         mbar_wait(m.bars + ACC_EMPTY, (it & 1) ^ 1);
@@ -533,19 +734,39 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
             mma_chunk<kPasses>(m, p, tmem + nb * 256, smem_u32(m.a_hi + kc * kAChunk), smem_u32(m.a_lo + kc * kAChunk),
                                idesc, kc > 0);
         umma_commit(m.bars + G1_FULL);
-        mbar_wait(m.bars + Y_FULL, it & 1);
+        // y chunks 0 and 1 must BOTH exist before GEMM2 may overwrite TMEM half A (their gamma/beta live there)
+        const uint32_t ph0 = (acnt >> 1) & 1;
+        mbar_wait(m.bars + A_FULL + 0, ph0);
+        mbar_wait(m.bars + A_FULL + 1, ph0);
         tc_fence_after();
-        for (int kc = 0; kc < 4; ++kc)
-          mma_chunk<kPasses>(m, p, tmem, smem_u32(m.a_hi + kc * kAChunk), smem_u32(m.a_lo + kc * kAChunk), idesc, kc > 0);
+        for (int kc = 0; kc < 4; ++kc, ++acnt) {
+          const uint32_t slot = acnt & 1;
+          if (kc >= 2) {
+            mbar_wait(m.bars + A_FULL + slot, (acnt >> 1) & 1);
+            tc_fence_after();
+          }
+          mma_chunk<kPasses>(m, p, tmem, smem_u32(m.a_hi + slot * kAChunk), smem_u32(m.a_lo + slot * kAChunk), idesc, kc > 0);
+          umma_commit(m.bars + A_EMPTY + slot);
+        }
         umma_commit(m.bars + ACC_FULL);
       }
     }
-  } else {
+  } else if (warp == 9) {
     if (lane == 0) {
       // gamma/beta image: [2 nblocks][2 kchunks][hi,lo] = 8 stages, then the conv image: 8 stages
       const uint8_t* imgs[2] = {a.wgb, a.wimg};
       const int ns[2] = {8, 8};
-      producer_loop<kPasses>(m, imgs, ns, 2, my_tiles);
+      weight_producer_loop<kPasses>(m, imgs, ns, 2, my_tiles);
+    }
+  } else {
+    if (lane == 0) {
+      XProducer xp;
+      for (int it = 0; it < my_tiles; ++it) {
+        int b, ti;
+        tile_of(it, b, ti);
+        emit_tile(m, xp, a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * kC * 128);
+        if (a.skip) emit_tile(m, xp, a.skip + (static_cast<long>(b) * T + ti) * kC * 128);
+      }
     }
   }
   tc_fence_before();
@@ -659,16 +880,16 @@ int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float*
   const int tiles = B * ((Hg * Wg + 127) / 128);
   const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
   auto st = static_cast<cudaStream_t>(stream);
-#define HG_LAUNCH(KERNEL)                                                                                         \
+#define HG_LAUNCH(KERNEL, THREADS)                                                                                \
   do {                                                                                                            \
     cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kSynSmemBytes); \
     if (e != cudaSuccess) { hg::set_error("hg_spade_conv: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; } \
-    KERNEL<<<grid, hg::kSynThreads, hg::kSynSmemBytes, st>>>(a);                                                  \
+    KERNEL<<<grid, THREADS, hg::kSynSmemBytes, st>>>(a);                                                          \
   } while (0)
   if (mod) {
-    if (passes == 3) HG_LAUNCH(hg::spade_const_kernel<3>); else HG_LAUNCH(hg::spade_const_kernel<1>);
+    if (passes == 3) HG_LAUNCH(hg::spade_const_kernel<3>, hg::kConstThreads); else HG_LAUNCH(hg::spade_const_kernel<1>, hg::kConstThreads);
   } else {
-    if (passes == 3) HG_LAUNCH(hg::spade_pixel_kernel<3>); else HG_LAUNCH(hg::spade_pixel_kernel<1>);
+    if (passes == 3) HG_LAUNCH(hg::spade_pixel_kernel<3>, hg::kSynThreads); else HG_LAUNCH(hg::spade_pixel_kernel<1>, hg::kSynThreads);
   }
 #undef HG_LAUNCH
   return hg::check_launch("hg_spade_conv");

@@ -43,9 +43,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// latency-critical waits (row warps, MMA issuer): plain try_wait loop
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// producer threads run far ahead of their consumers: back off between polls so that their spin loops do
+// not steal issue slots from the row warps on the same scheduler (they were ~50 % of all issued
+// warp-instructions, profiles/r1_spade_const_v3_ncu_summary.md)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+}
+
+// ---------------------------------------------------------------- explicit shared-space accesses
+// (pointers that went through integer alignment arithmetic compile to GENERIC LD/ST, which cost extra
+//  latency on the hot operand paths; these keep them LDS/STS)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_b32x4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// 8 consecutive fp32 table entries (two LDS.128; a warp-wide broadcast LDS.32 would cost one wavefront per value)
+__device__ __forceinline__ void lds8(const float* p, float (&o)[8]) {
+  const uint32_t a = smem_u32(p);
+  const float4 x = lds_f32x4(a), y = lds_f32x4(a + 16);
+  o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
+  o[4] = y.x; o[5] = y.y; o[6] = y.z; o[7] = y.w;
 }
 
 // ---------------------------------------------------------------- proxies / fences
@@ -171,8 +202,8 @@ __device__ __forceinline__ void store_a8(uint8_t* tile_hi, uint8_t* tile_lo, uin
 #pragma unroll
   for (int i = 0; i < 4; ++i) split_bf16x2(x[2 * i], x[2 * i + 1], h[i], l[i]);
   const uint32_t off = sw128_offset(row, k0);
-  *reinterpret_cast<uint4*>(tile_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-  if (kSplit) *reinterpret_cast<uint4*>(tile_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  sts_b32x4(smem_u32(tile_hi) + off, h[0], h[1], h[2], h[3]);
+  if (kSplit) sts_b32x4(smem_u32(tile_lo) + off, l[0], l[1], l[2], l[3]);
 }
 
 }  // namespace hg

@@ -339,17 +339,65 @@ class Map3DGenerator(nn.Module):
         return rgb, rgb_render, depth
 
     # -------------------------------------------------------------------------------- forward paths
+    def _forward_eager(self, latent, conditions, cfg, passes):
+        zz = latent if cfg.get("neural_field_latent_input", True) else torch.zeros_like(latent)
+        freq, phase = self.neural_field_mapping_network(zz)
+        _, styles = self.synthesis_mapping_network(latent)
+        return self._run(freq, phase, styles, conditions, cfg, passes)
+
+    def _forward_graphed(self, latent, conditions, cfg, passes):
+        """Replay the whole forward (~400 kernel launches + ~300 small torch ops) as ONE CUDA graph.
+        Captured once per (shapes, mode) key; inputs are copied into static buffers, parameters and
+        buffers are read / updated in place by the replay (running stats, spectral-norm u/v, RNG offsets)."""
+        keys = ("skeletons_xyz", "vertices", "tpose_vertices", "fk_matrices", "lbs_weights", "cam2world_matrices",
+                "intrinsics", "scales")
+        sig = (tuple(latent.shape), tuple(tuple(conditions[k].shape) for k in keys), self.training, passes,
+               cfg["render_height"], cfg["render_width"], cfg["num_steps"], cfg.get("map3d_mode"), cfg["nerf_noise"],
+               cfg.get("last_back", False), cfg.get("white_back", False), str(latent.device))
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        entry = self._graphs.get(sig)
+        if entry is None:
+            static_z = latent.clone()
+            static_c = {k: conditions[k].detach().float().contiguous().clone() for k in keys}
+            # Warm-up outside the capture (lazy inits, allocator).  It must not count as a forward: module
+            # buffers (running statistics, spectral-norm u/v, num_batches_tracked) and the RNG stream are restored.
+            saved = {k: b.detach().clone() for k, b in self.named_buffers()}
+            rng_state = torch.cuda.get_rng_state(latent.device)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._forward_eager(static_z, static_c, cfg, passes)
+            torch.cuda.current_stream().wait_stream(side)
+            for k, b in self.named_buffers():
+                b.copy_(saved[k])
+            torch.cuda.set_rng_state(rng_state, latent.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self._forward_eager(static_z, static_c, cfg, passes)
+            entry = self._graphs[sig] = (graph, static_z, static_c, outs)
+        graph, static_z, static_c, outs = entry
+        static_z.copy_(latent, non_blocking=True)
+        for k in keys:
+            static_c[k].copy_(conditions[k], non_blocking=True)
+        graph.replay()
+        return tuple(o.clone() for o in outs)
+
     def forward(self, latent, conditions, render_height, render_width, latent_indices=None, **kwargs):
-        """-> {"rgbs": [B,3,Hg,Wg], "rgbs_render": [B,3,Rh,Rw]}  (map3d_generator.py:208-280)."""
+        """-> {"rgbs": [B,3,Hg,Wg], "rgbs_render": [B,3,Rh,Rw]}  (map3d_generator.py:208-280).
+        `hg_cuda_graph=True` (or HG3D_CUDA_GRAPH=1) replays the forward as a CUDA graph."""
         self._guard(kwargs)
         with torch.no_grad():
             cfg = self._cfg_for(kwargs, render_height, render_width)
             if latent_indices is not None:
                 latent = self.latent_pool(latent_indices)
-            zz = latent if cfg.get("neural_field_latent_input", True) else torch.zeros_like(latent)
-            freq, phase = self.neural_field_mapping_network(zz)
-            _, styles = self.synthesis_mapping_network(latent)
-            rgb, rgb_render, _ = self._run(freq, phase, styles, conditions, cfg, _precision_passes(kwargs))
+            passes = _precision_passes(kwargs)
+            use_graph = kwargs.get("hg_cuda_graph", os.environ.get("HG3D_CUDA_GRAPH", "0") == "1")
+            if use_graph and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                    and torch.distributed.get_world_size() > 1 and self.training:
+                use_graph = False      # SyncBatchNorm all-reduces stay eager (NCCL inside a capture is not enabled here)
+            fn = self._forward_graphed if use_graph else self._forward_eager
+            rgb, rgb_render, _ = fn(latent, conditions, cfg, passes)
         return {"rgbs": rgb, "rgbs_render": rgb_render}
 
     def staged_forward(self, latent, conditions, render_height, render_width, truncation_psi, **kwargs):

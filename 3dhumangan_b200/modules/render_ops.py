@@ -48,8 +48,9 @@ def film_table(P, freq, phase, locked_dir=(0.0, 0.0, -1.0), prefix="neural_field
         fi, pi = f[:, i * H:(i + 1) * H], ph[:, i * H:(i + 1) * H]
         rows.append((fi, fi * g(f"network.{i}.layer.bias")[None] + pi))
     fi, pi = f[:, -H:], ph[:, -H:]
-    d = torch.tensor(locked_dir, dtype=torch.float32, device=freq.device)
-    dterm = g("color_layer_sine.layer.weight")[:, :3] @ d
+    wd = g("color_layer_sine.layer.weight")[:, :3]
+    # python-float arithmetic only: no host->device tensor creation, so the forward stays CUDA-graph capturable
+    dterm = wd[:, 0] * float(locked_dir[0]) + wd[:, 1] * float(locked_dir[1]) + wd[:, 2] * float(locked_dir[2])
     rows.append((fi, fi * (g("color_layer_sine.layer.bias") + dterm)[None] + pi))
     return torch.stack([torch.stack([F_, P_], 1) for F_, P_ in rows], 1).contiguous()
 

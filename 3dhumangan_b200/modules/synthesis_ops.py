@@ -60,6 +60,14 @@ def _gamma_beta_interleaved(wg, bg, wb, bb):
     return torch.cat(Ws).contiguous(), torch.cat(bs).contiguous()
 
 
+def all_reduce_stats(row, process_group=None):
+    """SyncBatchNorm across ranks (map3d_layers.py:162): SUM-all-reduce one statistics row
+    [sum(256) | sumsq(256) | count | pad] in fp64.  No-op without an initialised process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        dist.all_reduce(row, group=process_group)
+    return row
+
+
 def is_pixel_style(cfg, k):
     mode = cfg.get("map3d_mode", "isolated")
     return mode == "all" or k in cfg["mod_blocks"]
@@ -156,7 +164,7 @@ def synthesis_forward(params, feat_lr, fixed_style, cfg, *, training=True, passe
         bn = sp(k, j) + "first_norm."
         srow = stats[idx]
         if training and world > 1:
-            dist.all_reduce(srow, group=process_group)
+            all_reduce_stats(srow, process_group)
         pixel = (k, j) in pxi
         abi.bn_finalize(srow if training else None, P[bn + "weight"], P[bn + "bias"], P[bn + "running_mean"],
                         P[bn + "running_var"], training, count_dev=srow[512:513] if training else None,

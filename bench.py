@@ -185,7 +185,7 @@ def run_gpu(args, pkg):
     G.set_device(dev)
     G.train()
     passes_mode = args.precision
-    kw = dict(cfg, hg_precision=passes_mode)
+    kw = dict(cfg, hg_precision=passes_mode, hg_cuda_graph=not args.no_graph)
 
     # host (pinned) inputs: per-rank latents and poses
     cond_h = {k: v.pin_memory() for k, v in pkg.synthetic.make_conditions(B, seed=1 + rank).items()}
@@ -229,12 +229,24 @@ def run_gpu(args, pkg):
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    # Per-kernel device time: the same step launched eagerly with a CUDA-event pair around every launch of the
+    # C ABI (a captured graph cannot carry timing events).  Also counts this library's launches per step.
+    kw_eager = dict(kw, hg_cuda_graph=False)
+
+    def step_eager():
+        with torch.no_grad():
+            return G(z_d, cond_d, **kw_eager)["rgbs"]
+
+    step_eager()
+    torch.cuda.synchronize()
     abi.TIMING = []
     launches0 = abi.LAUNCHES
-    ms_total = timed(step_resident, args.steps)
+    ms_eager = timed(step_eager, args.steps)
     launches = abi.LAUNCHES - launches0
     timing, abi.TIMING = abi.TIMING, None
-    clocks = sampler.stop() if sampler else None
 
     for _ in range(2):
         step_e2e()
@@ -310,10 +322,12 @@ def run_gpu(args, pkg):
         "config": {"workload": describe(cfg, args.workload, B), "global_batch": B * world,
                    "parallelism": f"dp{world} (SyncBatchNorm statistics all-reduced over NCCL)" if world > 1 else "single GPU",
                    "l2": "activations are 2.1 GB per tensor (>> 126 MB L2): inputs larger than L2, no flush needed",
-                   "precision": passes_mode},
+                   "precision": passes_mode,
+                   "launch": "eager" if args.no_graph or (world > 1) else "whole forward replayed as one CUDA graph"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "eager_ms_per_step": ms_eager / args.steps,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
@@ -334,6 +348,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--precision", default=os.environ.get("HG3D_PRECISION", "fp32x3"), choices=["fp32x3", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     pkg = importlib.import_module("3dhumangan_b200")
     if args.impl == "reference":
