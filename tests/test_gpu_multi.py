@@ -1,0 +1,71 @@
+"""Data-parallel equivalence on 2 GPUs (NCCL): each rank runs the generator forward on half of the batch with
+SyncBatchNorm statistics all-reduced inside the forward; pixels and updated running statistics must equal the
+single-GPU run on the whole batch.  Skipped on a single-GPU box (the driver's default)."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port_no, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from golden_util import generator_case, rel_l2
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    gen = importlib.import_module("3dhumangan_b200.modules.generator")
+    rng = importlib.import_module("3dhumangan_b200.rng")
+    cfg, params, cond, z, (u, noise), gold = generator_case("g_tiny_dense")     # B = 2
+    dev = torch.device("cuda", rank)
+    G = gen.Map3DGenerator(**cfg).to(dev)
+    G.load_state_dict(params)
+    G.set_device(dev)
+    G.train()
+    sl = slice(rank, rank + 1)
+    rng.draw_render_noise = lambda *a, **k: (u[sl].to(dev), noise[sl].to(dev))
+    with torch.no_grad():
+        out = G(z[sl].to(dev), {k: v[sl].to(dev) for k, v in cond.items()}, **cfg)
+    torch.cuda.synchronize()
+    key = "synthesis_network.network.m3d_5.spade_0.first_norm.running_var"
+    res = {"rgbs": out["rgbs"].cpu(), "rv": G.state_dict()[key].cpu()}
+    gathered = [None, None]
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        dist.barrier()
+        dist.destroy_process_group()
+        # single-GPU reference on the full batch (no process group any more)
+        G1 = gen.Map3DGenerator(**cfg).to(dev)
+        G1.load_state_dict(params)
+        G1.set_device(dev)
+        G1.train()
+        rng.draw_render_noise = lambda *a, **k: (u.to(dev), noise.to(dev))
+        with torch.no_grad():
+            full = G1(z.to(dev), {k: v.to(dev) for k, v in cond.items()}, **cfg)
+        dp = torch.cat([gathered[0]["rgbs"], gathered[1]["rgbs"]])
+        e1 = rel_l2(dp, full["rgbs"].cpu())
+        e2 = rel_l2(gathered[0]["rv"], G1.state_dict()[key].cpu())
+        e3 = rel_l2(gathered[1]["rv"], gathered[0]["rv"])
+        e4 = rel_l2(dp, gold["rgbs"])
+        torch.save({"e_rgbs": e1, "e_running_var": e2, "e_ranks": e3, "e_gold": e4}, out_path)
+    else:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_equals_single_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, 29600 + os.getpid() % 300, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["e_rgbs"] < 1e-4, r
+    assert r["e_running_var"] < 1e-4, r
+    assert r["e_ranks"] < 1e-6, r
+    assert r["e_gold"] < 1e-3, r
