@@ -149,8 +149,13 @@ __device__ __forceinline__ void film_epilogue(const RenSmem& m, uint32_t tmem_ac
                                               bool defer_arrive) {
   const int q = warp & 3, h = warp >> 2;
   const int row = q * 32 + lane;
-  const float* F = m.film + (layer * 2 + 0) * kRH;
-  const float* P = m.film + (layer * 2 + 1) * kRH;
+  uint32_t F = smem_u32(m.film + (layer * 2 + 0) * kRH);
+  uint32_t P = smem_u32(m.film + (layer * 2 + 1) * kRH);
+  opaque(F);   // the per-sample FiLM table is refreshed between tiles: table loads stay inside this call
+  opaque(P);
+  uint32_t wsig = smem_u32(m.w_sigma), wrgb = smem_u32(m.w_rgb);
+  opaque(wsig);
+  opaque(wrgb);
   float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll 1
   for (int kc = 0; kc < 4; ++kc) {
@@ -161,21 +166,21 @@ __device__ __forceinline__ void film_epilogue(const RenSmem& m, uint32_t tmem_ac
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float x[8], f8[8], p8[8];
-      lds8(F + c0 + g * 8, f8);
-      lds8(P + c0 + g * 8, p8);
+      lds8(F + (c0 + g * 8) * 4, f8);
+      lds8(P + (c0 + g * 8) * 4, p8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = sin_reduced(fmaf(f8[j], __uint_as_float(raw[g * 8 + j]), p8[j]));
       if (kHead == 1) {
         float w8[8];
-        lds8(m.w_sigma + c0 + g * 8, w8);
+        lds8(wsig + (c0 + g * 8) * 4, w8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d0 = fmaf(x[j], w8[j], d0);
       }
       if (kHead == 2) {
         float w0[8], w1[8], w2[8];
-        lds8(m.w_rgb + c0 + g * 8, w0);
-        lds8(m.w_rgb + kRH + c0 + g * 8, w1);
-        lds8(m.w_rgb + 2 * kRH + c0 + g * 8, w2);
+        lds8(wrgb + (c0 + g * 8) * 4, w0);
+        lds8(wrgb + (kRH + c0 + g * 8) * 4, w1);
+        lds8(wrgb + (2 * kRH + c0 + g * 8) * 4, w2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           d0 = fmaf(x[j], w0[j], d0);
@@ -369,7 +374,9 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float b8[8];
-            lds8(m.b_feat + c0 + g * 8, b8);
+            uint32_t bfa = smem_u32(m.b_feat);
+            opaque(bfa);
+            lds8(bfa + (c0 + g * 8) * 4, b8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[g * 8 + j] = w * (__uint_as_float(raw[g * 8 + j]) + b8[j]);
           }

@@ -225,6 +225,9 @@ __device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem&
   const int T = (a.HW + 127) / 128;
   const long plane = (static_cast<long>(b) * T + (p0 >> 7)) * kC * 128 + row;   // + c * 128
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+  uint32_t tbias = smem_u32(m.tab_bias), trgb = smem_u32(m.tab_rgbw);   // constant tables, written before init's barrier
+  opaque(tbias);
+  opaque(trgb);
 #pragma unroll 1
   for (int kc = 0; kc < 4; ++kc) {
     const int c0 = kc * 64 + h * 32;
@@ -242,7 +245,7 @@ __device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem&
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float bs[8];
-      lds8(m.tab_bias + c0 + g * 8, bs);
+      lds8(tbias + (c0 + g * 8) * 4, bs);
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int j = g * 8 + jj;
@@ -254,9 +257,9 @@ __device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem&
       }
       if (a.rgb_w) {
         float w0[8], w1[8], w2[8];
-        lds8(m.tab_rgbw + c0 + g * 8, w0);
-        lds8(m.tab_rgbw + kC + c0 + g * 8, w1);
-        lds8(m.tab_rgbw + 2 * kC + c0 + g * 8, w2);
+        lds8(trgb + (c0 + g * 8) * 4, w0);
+        lds8(trgb + (kC + c0 + g * 8) * 4, w1);
+        lds8(trgb + (2 * kC + c0 + g * 8) * 4, w2);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           r0 = fmaf(v[g * 8 + jj], w0[jj], r0);
@@ -394,6 +397,9 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
         cur_b = b;
       }
       const bool valid = ti * 128 + row < a.HW;
+      uint32_t tg1 = smem_u32(m.tab_g1), tg0 = smem_u32(m.tab_g0);
+      opaque(tg1);   // the tables may just have been refreshed: no table load may move above this point
+      opaque(tg0);
 #pragma unroll 1
       for (int kc = 0; kc < 4; ++kc, ++acnt) {
         const int c0 = kc * 64 + h * 32;
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh, ++xg) {
           const uint32_t xslot = xg % kXs;
-          mbar_wait(m.bars + X_FULL + xslot, (xg / kXs) & 1);
+          mbar_wait_sleep(m.bars + X_FULL + xslot, (xg / kXs) & 1);
           if (hh == h) {
             const uint32_t xs = smem_u32(m.x_st + xslot * (kXSlice / 4)) + row * 4;
 #pragma unroll
@@ -411,14 +417,18 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
           if (lane == 0) mbar_arrive(m.bars + X_EMPTY + xslot);
         }
         const uint32_t slot = acnt & 1;
-        mbar_wait(m.bars + A_EMPTY + slot, ((acnt >> 1) & 1) ^ 1);
+        mbar_wait_sleep(m.bars + A_EMPTY + slot, ((acnt >> 1) & 1) ^ 1);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float y[8], t1[8], t0[8];
-          lds8(m.tab_g1 + c0 + g * 8, t1);
-          lds8(m.tab_g0 + c0 + g * 8, t0);
+          lds8(tg1 + (c0 + g * 8) * 4, t1);
+          lds8(tg0 + (c0 + g * 8) * 4, t0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = valid ? lrelu02(fmaf(cur[g * 8 + j], t1[j], t0[j])) : 0.f;
+          for (int j = 0; j < 8; ++j) y[j] = lrelu02(fmaf(cur[g * 8 + j], t1[j], t0[j]));
+          if (!valid) {   // only the last, partial tile of an image
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = 0.f;
+          }
           store_a8<kPasses == 3>(m.a_hi + slot * kAChunk, m.a_lo + slot * kAChunk, row, h * 32 + g * 8, y);
         }
         fence_proxy_async_smem();
@@ -431,6 +441,9 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
     const int q = warp - 8;
     const int row = q * 32 + lane;
     uint32_t sg = 0;   // residual slices consumed
+    uint32_t tbias = smem_u32(m.tab_bias), trgb = smem_u32(m.tab_rgbw);   // constant tables, written before init's barrier
+    opaque(tbias);
+    opaque(trgb);
     for (int it = 0; it < my_tiles; ++it) {
       int b, ti;
       tile_of(it, b, ti);
@@ -438,9 +451,12 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
       const int pix = ti * 128 + row;
       const bool valid = pix < a.HW;
       const long plane = (static_cast<long>(b) * T + ti) * kC * 128 + row;
-      mbar_wait(m.bars + ACC_FULL + buf, (it >> 1) & 1);
+      mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
       tc_fence_after();
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      // without a residual the 2 residual staging slots (32 KB) are free: use them as per-warp [32][33]
+      // transpose scratch for the statistics (32 STS + 32 LDS + 64 FP instead of a 248-instruction shuffle tree)
+      float* scratch = m.x_st + kXs * (kXSlice / 4) + q * (32 * 33);
 #pragma unroll 1
       for (int cg = 0; cg < 8; ++cg) {
         const int c0 = cg * 32;
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
         float sk[32];
         if (a.skip) {
           const uint32_t sslot = kXs + sg % kSs;
-          mbar_wait(m.bars + X_FULL + sslot, (sg / kSs) & 1);
+          mbar_wait_sleep(m.bars + X_FULL + sslot, (sg / kSs) & 1);
           const uint32_t xs = smem_u32(m.x_st + sslot * (kXSlice / 4)) + row * 4;
 #pragma unroll
           for (int j = 0; j < 32; ++j) sk[j] = lds_f32(xs + j * 512);
@@ -465,7 +481,7 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float bs[8];
-          lds8(m.tab_bias + c0 + g * 8, bs);
+          lds8(tbias + (c0 + g * 8) * 4, bs);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const int j = g * 8 + jj;
@@ -477,9 +493,9 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
           }
           if (a.rgb_w) {
             float w0[8], w1[8], w2[8];
-            lds8(m.tab_rgbw + c0 + g * 8, w0);
-            lds8(m.tab_rgbw + kC + c0 + g * 8, w1);
-            lds8(m.tab_rgbw + 2 * kC + c0 + g * 8, w2);
+            lds8(trgb + (c0 + g * 8) * 4, w0);
+            lds8(trgb + (kC + c0 + g * 8) * 4, w1);
+            lds8(trgb + (2 * kC + c0 + g * 8) * 4, w2);
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               r0 = fmaf(v[g * 8 + jj], w0[jj], r0);
@@ -489,8 +505,25 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
           }
         }
         if (a.stats) {
-          const float t1 = transpose_reduce32(v, lane);
-          const float t2 = transpose_reduce32(s2, lane);
+          float t1, t2;
+          if (a.skip) {
+            t1 = transpose_reduce32(v, lane);
+            t2 = transpose_reduce32(s2, lane);
+          } else {
+            const uint32_t sa = smem_u32(scratch);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + (lane * 33 + j) * 4), "f"(v[j]) : "memory");
+            __syncwarp();
+            t1 = 0.f;
+            t2 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const float x = lds_f32(sa + (r * 33 + lane) * 4);
+              t1 += x;
+              t2 = fmaf(x, x, t2);
+            }
+          }
           atomicAdd(m.st_sum + c0 + lane, t1);
           atomicAdd(m.st_sq + c0 + lane, t2);
         }
@@ -523,11 +556,11 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
       uint32_t acnt = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t buf = it & 1;
-        mbar_wait(m.bars + ACC_EMPTY + buf, ((it >> 1) & 1) ^ 1);
+        mbar_wait_sleep(m.bars + ACC_EMPTY + buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         for (int kc = 0; kc < 4; ++kc, ++acnt) {
           const uint32_t slot = acnt & 1;
-          mbar_wait(m.bars + A_FULL + slot, (acnt >> 1) & 1);
+          mbar_wait_sleep(m.bars + A_FULL + slot, (acnt >> 1) & 1);
           tc_fence_after();
           mma_chunk<kPasses>(m, p, tmem + buf * 256, smem_u32(m.a_hi + slot * kAChunk), smem_u32(m.a_lo + slot * kAChunk),
                              idesc, kc > 0);
@@ -621,6 +654,10 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
     const int row = q * 32 + lane;
     uint32_t acnt = 0;
     XConsumer xc;
+    uint32_t tg1 = smem_u32(m.tab_g1), tg0 = smem_u32(m.tab_g0), tbgb = smem_u32(m.tab_bgb);   // constant tables
+    opaque(tg1);
+    opaque(tg0);
+    opaque(tbgb);
     for (int it = 0; it < my_tiles; ++it) {
       int b, ti;
       tile_of(it, b, ti);
@@ -685,10 +722,10 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float y[8], bg[8], bb[8], t1[8], t0[8];
-          lds8(m.tab_bgb + col + g * 8, bg);
-          lds8(m.tab_bgb + col + 64 + g * 8, bb);
-          lds8(m.tab_g1 + c0 + g * 8, t1);
-          lds8(m.tab_g0 + c0 + g * 8, t0);
+          lds8(tbgb + (col + g * 8) * 4, bg);
+          lds8(tbgb + (col + 64 + g * 8) * 4, bb);
+          lds8(tg1 + (c0 + g * 8) * 4, t1);
+          lds8(tg0 + (c0 + g * 8) * 4, t0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int jj = g * 8 + j;

@@ -48,6 +48,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// row-warp waits that are expected to block for a while: a short sleep between polls frees issue slots for the
+// other team's warp on the same scheduler (spin loops were 42 % of the executed warp-instructions)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
 // producer threads run far ahead of their consumers: back off between polls so that their spin loops do
 // not steal issue slots from the row warps on the same scheduler (they were ~50 % of all issued
 // warp-instructions, profiles/r1_spade_const_v3_ncu_summary.md)
@@ -68,13 +73,22 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+// Operand-tile store.  Volatile (it has side effects) but WITHOUT a "memory" clobber: the clobber serialised
+// every 8-element group behind the previous group's store (table LDS -> math -> STS -> next table LDS ...).
+// Ordering against the consumers is provided by fence_proxy_async_smem() (which does clobber memory).
 __device__ __forceinline__ void sts_b32x4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
-// 8 consecutive fp32 table entries (two LDS.128; a warp-wide broadcast LDS.32 would cost one wavefront per value)
-__device__ __forceinline__ void lds8(const float* p, float (&o)[8]) {
-  const uint32_t a = smem_u32(p);
-  const float4 x = lds_f32x4(a), y = lds_f32x4(a + 16);
+// Makes the compiler forget what it knows about a register: loads whose address derives from it cannot be
+// hoisted above this point (used after a barrier / table refresh in front of NON-volatile table loads).
+__device__ __forceinline__ void opaque(uint32_t& r) { asm volatile("" : "+r"(r)); }
+// 8 consecutive fp32 entries of a read-mostly shared-memory TABLE (two LDS.128; a warp-wide broadcast LDS.32
+// would cost one wavefront per value).  Non-volatile on purpose: the scheduler may batch / hoist them freely;
+// callers pass an address made `opaque` after the last point at which the table may have changed.
+__device__ __forceinline__ void lds8(uint32_t a, float (&o)[8]) {
+  float4 x, y;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(a));
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(a + 16));
   o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
   o[4] = y.x; o[5] = y.y; o[6] = y.z; o[7] = y.w;
 }
