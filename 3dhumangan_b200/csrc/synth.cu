@@ -5,40 +5,49 @@
 //
 // Activations live in HBM as fp32 in a tile-blocked planar layout [B, T, C=256, 128] (T = ceil(HW/128)
 // tiles of 128 consecutive pixels): the 128 KB a CTA reads / writes per tile are CONTIGUOUS, and every
-// 32-channel slice of a tile is one contiguous 16 KB block.
+// 32-channel slice of a tile is one contiguous 16 KB block (one cp.async.bulk).
 //
-// Per CTA (352 threads), persistent over tiles of 128 pixels of one image:
-//   warps 0-7  "row" warps: read the activation slices from the shared-memory staging ring, apply
-//              BN scale/shift + SPADE modulation + LeakyReLU, split to bf16 hi/lo and write the A
-//              operand (2-slot ring of [128 x 64] K-major SW128 tiles); later drain the fp32
-//              accumulator from TMEM: bias, residual, ToRGB, per-channel sum / sum-of-squares for
-//              the NEXT BatchNorm (the SyncBN statistics never need their own pass), plane stores.
-//   warp 8     one thread issues tcgen05.mma (M=128, N=256, K=16; bf16x3 split or plain bf16).
-//   warp 9     one thread streams the packed weight tiles from L2 (cp.async.bulk, 2 x 32 KB stages).
-//   warp 10    one thread streams the activation (and residual) slices from HBM into a 5 x 16 KB
-//              staging ring with cp.async.bulk, several slices ahead of the row warps and across
-//              tile boundaries: ~80 KB in flight per SM without spending registers, which is what
-//              an HBM-bound kernel needs (v1 kept <= 32 KB in flight through registers and reached
-//              26 % of the HBM roofline, profiles/r1_*).
+// Per CTA (480 threads), persistent over tiles of 128 pixels of one image:
+//   warps 0-7   operand team: build the bf16 hi/lo A operand of the NEXT tile in a 2-slot ring of
+//               [128 x 64] K-major SW128 chunks (BN scale/shift, SPADE modulation, LeakyReLU fused)
+//   warps 8-11  epilogue team: drain the fp32 accumulator of the PREVIOUS tile from TMEM (warp 8+q owns lanes
+//               32q..32q+31, all 256 columns): bias, residual, ToRGB, per-channel sum / sum-of-squares for the
+//               next BatchNorm (so SyncBN statistics never need their own pass), plane stores
+//   warp 12     one thread issues tcgen05.mma (M=128, N=256, K=16; bf16x3 split or plain bf16)
+//   warp 13     one thread streams the packed weight tiles from L2 (cp.async.bulk, 2 x 32 KB stages)
+//   warp 14     one thread streams activation slices (ring slots 0-2, operand team) from HBM with cp.async.bulk
+//   warp 15     one thread streams residual slices (ring slots 3-4, epilogue team).  Two threads, not one: with a
+//               single producer the two rings are coupled by program order, and in the pixel-style variant
+//               (gamma/beta GEMM of tile t+1 waits for the epilogue of tile t) that coupling deadlocks.
+// The two TMEM halves (2 x 256 columns) alternate between tiles, so the epilogue of tile t, the MMAs of tile
+// t+1 and the operand production of tile t+1/t+2 overlap.
 //
 // Two variants:
-//   const-style : gamma/beta are per-sample vectors (blocks whose style map is spatially
-//                 constant, 12 of 18 half-blocks in 'mixed'/'isolated' mode).  Operand production of
-//                 tile t+1 overlaps the MMAs of tile t (2 TMEM accumulators).
+//   const-style : gamma/beta are per-sample vectors (blocks whose style map is spatially constant, 12 of 18
+//                 half-blocks in 'mixed'/'isolated' mode).
 //   pixel-style : gamma/beta come from a second GEMM on relu(bilinear_up(P_lr)) where
-//                 P_lr = W_shared . feature_maps + b at RENDER resolution (W_shared commutes with
-//                 the bilinear up-sample), so the 28x larger up-sampled style map of
-//                 map3d_generator.py:244-245 is never materialised.
+//                 P_lr = W_shared . feature_maps + b at RENDER resolution (W_shared commutes with the bilinear
+//                 up-sample), so the 28x larger up-sampled style map of map3d_generator.py:244-245 is never
+//                 materialised.  TMEM plan per tile t (R = half t&1, R' = the other, still being drained):
+//                 G1(gamma|beta, channels 0-127) -> R, G1(channels 128-255) -> R' once the epilogue of t-1 is
+//                 done, y chunks 0,1 <- R, conv accumulator -> R, y chunks 2,3 <- R'.
+//
+// Ring protocol note: every consumer warp of a staging ring waits for and releases EVERY slice in order
+// (only the owning column half reads it).  With per-half arrivals a slot of an odd-sized ring alternates
+// between halves, a fast half gets two phases ahead and the parity wait succeeds on a stale phase -- that race
+// produced launch failures in an earlier version (DESIGN.md "Pitfalls").
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace hg {
 
 constexpr int kC = 256;             // channels (hidden_dim == feature_dim == 256)
-constexpr int kSynThreads = 352;    // warps 0-7 rows, 8 MMA, 9 weight producer, 10 activation producer
+constexpr int kSynThreads = 512;
 constexpr int kSynStages = 2;       // weight stages
 constexpr int kASlots = 2;          // operand ring
-constexpr int kXSlots = 5;          // activation staging ring
+constexpr int kXSlots = 5;          // staging slots in total
+constexpr int kXs = 3;              //   slots 0..2: activation slices (operand team)
+constexpr int kSs = 2;              //   slots 3..4: residual slices (epilogue team)
 constexpr uint32_t kAChunk = 128 * 128;   // [128 x 64] bf16
 constexpr uint32_t kBStage = 256 * 128;   // [256 x 64] bf16
 constexpr uint32_t kXSlice = 32 * 128 * 4;  // 32 channels x 128 pixels fp32
@@ -77,7 +86,6 @@ struct SynSmem {
   float* tab_bgb;  // [512]
   float* st_sum;   // [C]
   float* st_sq;    // [C]
-  float* rgb_part; // [2][128][3]
   uint64_t* bars;
   uint32_t* tmem_slot;
 };
@@ -97,23 +105,21 @@ __device__ __forceinline__ SynSmem carve(uint8_t* raw) {
   m.tab_bgb = f; f += 512;
   m.st_sum = f; f += kC;
   m.st_sq = f; f += kC;
-  m.rgb_part = f; f += 2 * 128 * 3;
   m.bars = reinterpret_cast<uint64_t*>(f);
   m.tmem_slot = reinterpret_cast<uint32_t*>(m.bars + 40);
   return m;
 }
 constexpr uint32_t kSynSmemBytes = 2 * kASlots * kAChunk + kSynStages * kBStage + kXSlots * kXSlice +
-                                   (kC * 8 + 512 + 768) * 4 + 40 * 8 + 16 + 1024;
+                                   (kC * 8 + 512) * 4 + 40 * 8 + 16 + 1024;
 static_assert(kSynSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots
 enum { A_FULL = 0 /*2*/, A_EMPTY = 2 /*2*/, B_FULL = 4 /*2*/, B_EMPTY = 6 /*2*/, ACC_FULL = 8 /*2*/,
-       ACC_EMPTY = 10 /*2*/, G1_FULL = 12, A1_FULL = 13, X_FULL = 16 /*5*/, X_EMPTY = 24 /*5*/ };
+       ACC_EMPTY = 10 /*2*/, G1A_FULL = 12, G1B_FULL = 13, A1_FULL = 14, X_FULL = 16 /*5*/, X_EMPTY = 24 /*5*/ };
 
 __device__ __forceinline__ void rows_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
-
 
 // 32 lanes x 32 values: after the call lane j holds sum over lanes of v[j].
 __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
@@ -130,14 +136,61 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
+struct TileMap {
+  int T, first, stride, count;
+  __device__ __forceinline__ void get(int it, int& b, int& ti) const {
+    const int tile = first + it * stride;
+    b = tile / T;
+    ti = tile - b * T;
+  }
+};
+
 // ------------------------------------------------------------------------------------------
-// shared pieces
+// common setup
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void init_common(const SpadeArgs& a, const SynSmem& m, int warp) {
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) {
+    m.tab_bias[i] = a.bias[i];
+    m.st_sum[i] = 0.f;
+    m.st_sq[i] = 0.f;
+  }
+  if (a.rgb_w)
+    for (int i = threadIdx.x; i < 3 * kC; i += blockDim.x) m.tab_rgbw[i] = a.rgb_w[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kASlots; ++i) {
+      mbar_init(m.bars + A_FULL + i, 8);
+      mbar_init(m.bars + A_EMPTY + i, 1);
+    }
+    for (int i = 0; i < kSynStages; ++i) {
+      mbar_init(m.bars + B_FULL + i, 1);
+      mbar_init(m.bars + B_EMPTY + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(m.bars + ACC_FULL + i, 1);
+      mbar_init(m.bars + ACC_EMPTY + i, 4);     // the 4 epilogue warps
+    }
+    mbar_init(m.bars + G1A_FULL, 1);
+    mbar_init(m.bars + G1B_FULL, 1);
+    mbar_init(m.bars + A1_FULL, 8);
+    for (int i = 0; i < kXSlots; ++i) {
+      mbar_init(m.bars + X_FULL + i, 1);
+      mbar_init(m.bars + X_EMPTY + i, i < kXs ? 8 : 4);   // operand team: 8 warps, epilogue team: 4 warps
+    }
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc<512>(m.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+// ------------------------------------------------------------------------------------------
+// warp 13: weight stages.  Every tile consumes the same sequence: for each image `nstages` tiles of [256 x 64]
+// in storage order (kc-major, hi then lo); the lo tiles are skipped in 1-pass mode.
 // ------------------------------------------------------------------------------------------
 template <int kPasses>
 __device__ __forceinline__ void weight_producer_loop(const SynSmem& m, const uint8_t* const* imgs, const int* nstages,
                                                      int nimgs, int num_my_tiles) {
-  // Every tile consumes the same sequence of weight stages: for each image, `nstages` tiles of
-  // [256 x 64] in storage order (kc-major, hi then lo); the lo tiles are skipped in 1-pass mode.
   uint32_t st = 0, ph = 0;
   for (int t = 0; t < num_my_tiles; ++t)
     for (int g = 0; g < nimgs; ++g)
@@ -149,48 +202,6 @@ __device__ __forceinline__ void weight_producer_loop(const SynSmem& m, const uin
         if (++st == kSynStages) { st = 0; ph ^= 1; }
       }
 }
-
-// Activation staging ring, producer side: one 16 KB slice (32 channels x 128 pixels) per call.
-struct XProducer {
-  uint32_t g = 0;
-  __device__ __forceinline__ void emit(const SynSmem& m, const float* src) {
-    const uint32_t slot = g % kXSlots, ph = (g / kXSlots) & 1;
-    mbar_wait_backoff(m.bars + X_EMPTY + slot, ph ^ 1);
-    mbar_arrive_expect_tx(m.bars + X_FULL + slot, kXSlice);
-    bulk_g2s(m.x_st + slot * (kXSlice / 4), src, kXSlice, m.bars + X_FULL + slot);
-    ++g;
-  }
-};
-// Consumer side.  EVERY consuming warp waits for and releases EVERY slice, in order; only the owning
-// column half (slice index parity == h) actually reads it.  (With per-half arrivals a slot of an odd-sized
-// ring alternates between the halves and a fast half can get two phases ahead of the slot -- the parity wait
-// then succeeds on a stale phase.  That race produced launch failures; see DESIGN.md "Pitfalls".)
-struct XConsumer {
-  uint32_t g = 0;
-  uint32_t slot = 0;
-  __device__ __forceinline__ const float* begin(const SynSmem& m) {
-    slot = g % kXSlots;
-    mbar_wait(m.bars + X_FULL + slot, (g / kXSlots) & 1);
-    return m.x_st + slot * (kXSlice / 4);
-  }
-  __device__ __forceinline__ void end(const SynSmem& m, int lane) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(m.bars + X_EMPTY + slot);
-    ++g;
-  }
-  // read this warp's 32 values of the slice pair (2*kc, 2*kc+1): half h owns slice 2*kc + h
-  __device__ __forceinline__ void take_pair(const SynSmem& m, int h, int row, int lane, float (&dst)[32]) {
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const uint32_t xs = smem_u32(begin(m)) + row * 4;
-      if (hh == h) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = lds_f32(xs + j * 512);
-      }
-      end(m, lane);
-    }
-  }
-};
 
 struct MmaPipe {
   uint32_t st = 0, ph = 0;
@@ -215,178 +226,195 @@ __device__ __forceinline__ void mma_chunk(const SynSmem& m, MmaPipe& p, uint32_t
   }
 }
 
-// Drain one accumulator: bias, residual (from the staging ring), stats, ToRGB, plane stores.
-__device__ __forceinline__ void conv_epilogue(const SpadeArgs& a, const SynSmem& m, XConsumer& xc, uint32_t tmem_acc,
-                                              int b, int p0, int warp, int lane) {
-  const int q = warp & 3, h = warp >> 2;
+// ------------------------------------------------------------------------------------------
+// warp 14: activation slices (slots 0..2), warp 15: residual slices (slots 3..4): two independent rings.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ring_emit(const SynSmem& m, uint32_t& g, int base, int slots, const float* src) {
+  const uint32_t slot = base + g % slots;
+  mbar_wait_backoff(m.bars + X_EMPTY + slot, ((g / slots) & 1) ^ 1);
+  mbar_arrive_expect_tx(m.bars + X_FULL + slot, kXSlice);
+  bulk_g2s(m.x_st + slot * (kXSlice / 4), src, kXSlice, m.bars + X_FULL + slot);
+  ++g;
+}
+__device__ __forceinline__ void x_producer_loop(const SpadeArgs& a, const SynSmem& m, const TileMap& tm) {
+  uint32_t g = 0;
+  for (int it = 0; it < tm.count; ++it) {
+    int b, ti;
+    tm.get(it, b, ti);
+    const float* base = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * kC * 128;
+    for (int j = 0; j < 8; ++j) ring_emit(m, g, 0, kXs, base + j * 32 * 128);
+  }
+}
+__device__ __forceinline__ void skip_producer_loop(const SpadeArgs& a, const SynSmem& m, const TileMap& tm) {
+  if (!a.skip) return;
+  uint32_t g = 0;
+  for (int it = 0; it < tm.count; ++it) {
+    int b, ti;
+    tm.get(it, b, ti);
+    const float* base = a.skip + (static_cast<long>(b) * tm.T + ti) * kC * 128;
+    for (int j = 0; j < 8; ++j) ring_emit(m, g, kXs, kSs, base + j * 32 * 128);
+  }
+}
+
+// Operand-team side of the activation ring: every warp walks both slices of a chunk, half h reads slice 2kc+h.
+__device__ __forceinline__ void take_x_pair(const SynSmem& m, uint32_t& xg, int h, int row, int lane, float (&dst)[32]) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh, ++xg) {
+    const uint32_t xslot = xg % kXs;
+    mbar_wait_sleep(m.bars + X_FULL + xslot, (xg / kXs) & 1);
+    if (hh == h) {
+      const uint32_t xs = smem_u32(m.x_st + xslot * (kXSlice / 4)) + row * 4;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[j] = lds_f32(xs + j * 512);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(m.bars + X_EMPTY + xslot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// warps 8-11: epilogue team (identical for both variants): tile `it` lives in TMEM half it&1.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const SynSmem& m, const TileMap& tm, uint32_t tmem,
+                                                   int q, int lane) {
   const int row = q * 32 + lane;
-  const int pix = p0 + row;
-  const bool valid = pix < a.HW;
-  const int T = (a.HW + 127) / 128;
-  const long plane = (static_cast<long>(b) * T + (p0 >> 7)) * kC * 128 + row;   // + c * 128
-  float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+  uint32_t sg = 0;   // residual slices consumed
   uint32_t tbias = smem_u32(m.tab_bias), trgb = smem_u32(m.tab_rgbw);   // constant tables, written before init's barrier
   opaque(tbias);
   opaque(trgb);
+  // without a residual the 2 residual staging slots (32 KB) are free: per-warp [32][33] transpose scratch for the
+  // statistics (32 STS + 32 LDS + 64 FP instead of a 248-instruction shuffle tree)
+  const uint32_t scratch = smem_u32(m.x_st + kXs * (kXSlice / 4) + q * (32 * 33));
+  for (int it = 0; it < tm.count; ++it) {
+    int b, ti;
+    tm.get(it, b, ti);
+    const uint32_t buf = it & 1;
+    const int pix = ti * 128 + row;
+    const bool valid = pix < a.HW;
+    const long plane = (static_cast<long>(b) * tm.T + ti) * kC * 128 + row;
+    mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
+    tc_fence_after();
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 1
-  for (int kc = 0; kc < 4; ++kc) {
-    const int c0 = kc * 64 + h * 32;
-    uint32_t raw[32];
-    tmem_ld32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
-    float sk[32];
-    if (a.skip) {
-      xc.take_pair(m, h, row, lane, sk);
-    } else {
+    for (int cg = 0; cg < 8; ++cg) {
+      const int c0 = cg * 32;
+      uint32_t raw[32];
+      tmem_ld32(tmem + buf * 256 + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
+      float sk[32];
+      if (a.skip) {
+        const uint32_t sslot = kXs + sg % kSs;
+        mbar_wait_sleep(m.bars + X_FULL + sslot, (sg / kSs) & 1);
+        const uint32_t xs = smem_u32(m.x_st + sslot * (kXSlice / 4)) + row * 4;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sk[j] = 0.f;
-    }
-    tmem_ld_wait();
-    float v[32], s2[32];
+        for (int j = 0; j < 32; ++j) sk[j] = lds_f32(xs + j * 512);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(m.bars + X_EMPTY + sslot);
+        ++sg;
+      } else {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float bs[8];
-      lds8(tbias + (c0 + g * 8) * 4, bs);
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int j = g * 8 + jj;
-        float o = __uint_as_float(raw[j]) + bs[jj] + sk[j];
-        if (valid) a.out[plane + (c0 + j) * 128] = o;
-        o = valid ? o : 0.f;
-        v[j] = o;
-        s2[j] = o * o;
+        for (int j = 0; j < 32; ++j) sk[j] = 0.f;
       }
-      if (a.rgb_w) {
-        float w0[8], w1[8], w2[8];
-        lds8(trgb + (c0 + g * 8) * 4, w0);
-        lds8(trgb + (kC + c0 + g * 8) * 4, w1);
-        lds8(trgb + (2 * kC + c0 + g * 8) * 4, w2);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float bs[8];
+        lds8(tbias + (c0 + g * 8) * 4, bs);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          r0 = fmaf(v[g * 8 + jj], w0[jj], r0);
-          r1 = fmaf(v[g * 8 + jj], w1[jj], r1);
-          r2 = fmaf(v[g * 8 + jj], w2[jj], r2);
+          const int j = g * 8 + jj;
+          float o = __uint_as_float(raw[j]) + bs[jj] + sk[j];
+          if (valid) a.out[plane + (c0 + j) * 128] = o;
+          v[j] = valid ? o : 0.f;
+        }
+        if (a.rgb_w) {
+          float w0[8], w1[8], w2[8];
+          lds8(trgb + (c0 + g * 8) * 4, w0);
+          lds8(trgb + (kC + c0 + g * 8) * 4, w1);
+          lds8(trgb + (2 * kC + c0 + g * 8) * 4, w2);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            r0 = fmaf(v[g * 8 + jj], w0[jj], r0);
+            r1 = fmaf(v[g * 8 + jj], w1[jj], r1);
+            r2 = fmaf(v[g * 8 + jj], w2[jj], r2);
+          }
         }
       }
-    }
-    if (a.stats) {
-      const float t1 = transpose_reduce32(v, lane);
-      const float t2 = transpose_reduce32(s2, lane);
-      atomicAdd(m.st_sum + c0 + lane, t1);
-      atomicAdd(m.st_sq + c0 + lane, t2);
-    }
-  }
-  if (a.rgb_w) {
-    float* part = m.rgb_part + (h * 128 + row) * 3;
-    part[0] = r0; part[1] = r1; part[2] = r2;
-  }
-}
-
-__device__ __forceinline__ void rgb_finish(const SpadeArgs& a, const SynSmem& m, int b, int p0, int warp, int lane) {
-  // called by all row warps after rows_barrier(); warps with h == 0 combine the two channel halves
-  if ((warp >> 2) != 0) return;
-  const int row = (warp & 3) * 32 + lane;
-  const int pix = p0 + row;
-  if (pix >= a.HW) return;
+      if (a.stats) {
+        float t1, t2;
+        if (a.skip) {
+          float s2[32];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    float o = m.rgb_part[row * 3 + j] + m.rgb_part[(128 + row) * 3 + j] + a.rgb_b[j];
-    const long idx = (static_cast<long>(b) * 3 + j) * a.HW + pix;
-    if (a.rgb_in) o += a.rgb_in[idx];
-    a.rgb_out[idx] = o;
-  }
-}
-
-__device__ __forceinline__ void init_common(const SpadeArgs& a, const SynSmem& m, int tmem_warp, int warp, int acc_empty_count,
-                                            int x_slots, int x_count, int s_count) {
-  for (int i = threadIdx.x; i < kC; i += blockDim.x) {
-    m.tab_bias[i] = a.bias[i];
-    m.st_sum[i] = 0.f;
-    m.st_sq[i] = 0.f;
-  }
-  if (a.rgb_w)
-    for (int i = threadIdx.x; i < 3 * kC; i += blockDim.x) m.tab_rgbw[i] = a.rgb_w[i];
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kASlots; ++i) {
-      mbar_init(m.bars + A_FULL + i, 8);
-      mbar_init(m.bars + A_EMPTY + i, 1);
+          for (int j = 0; j < 32; ++j) s2[j] = v[j] * v[j];
+          t1 = transpose_reduce32(v, lane);
+          t2 = transpose_reduce32(s2, lane);
+        } else {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + (lane * 33 + j) * 4), "f"(v[j]) : "memory");
+          __syncwarp();
+          t1 = 0.f;
+          t2 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const float x = lds_f32(scratch + (r * 33 + lane) * 4);
+            t1 += x;
+            t2 = fmaf(x, x, t2);
+          }
+        }
+        atomicAdd(m.st_sum + c0 + lane, t1);
+        atomicAdd(m.st_sq + c0 + lane, t2);
+      }
     }
-    for (int i = 0; i < kSynStages; ++i) {
-      mbar_init(m.bars + B_FULL + i, 1);
-      mbar_init(m.bars + B_EMPTY + i, 1);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(m.bars + ACC_EMPTY + buf);
+    if (a.rgb_w && valid) {   // this thread saw all 256 channels of its pixel
+      const float r[3] = {r0, r1, r2};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const long idx = (static_cast<long>(b) * 3 + j) * a.HW + pix;
+        float o = r[j] + a.rgb_b[j];
+        if (a.rgb_in) o += a.rgb_in[idx];
+        a.rgb_out[idx] = o;
+      }
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(m.bars + ACC_FULL + i, 1);
-      mbar_init(m.bars + ACC_EMPTY + i, acc_empty_count);
-    }
-    mbar_init(m.bars + G1_FULL, 1);
-    mbar_init(m.bars + A1_FULL, 8);
-    for (int i = 0; i < kXSlots; ++i) {   // slots [0, x_slots): activation ring; the rest: residual ring (const kernel)
-      mbar_init(m.bars + X_FULL + i, 1);
-      mbar_init(m.bars + X_EMPTY + i, i < x_slots ? x_count : s_count);
-    }
-    fence_mbar_init();
   }
-  if (warp == tmem_warp) tmem_alloc<512>(m.tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-}
-
-__device__ __forceinline__ void flush_stats(const SpadeArgs& a, const SynSmem& m) {
-  // row warps only (256 threads), after a rows_barrier()
-  if (!a.stats) return;
-  const int c = threadIdx.x;
-  if (c < kC) {
-    atomicAdd(a.stats + c, static_cast<double>(m.st_sum[c]));
-    atomicAdd(a.stats + kC + c, static_cast<double>(m.st_sq[c]));
+  asm volatile("bar.sync 2, 128;" ::: "memory");
+  if (a.stats) {
+    for (int c = threadIdx.x - 256; c < kC; c += 128) {
+      atomicAdd(a.stats + c, static_cast<double>(m.st_sum[c]));
+      atomicAdd(a.stats + kC + c, static_cast<double>(m.st_sq[c]));
+    }
   }
-}
-
-// slices of one tile in consumption order: 8 x 16 KB (channels 32j .. 32j+31)
-__device__ __forceinline__ void emit_tile(const SynSmem& m, XProducer& xp, const float* tile_base) {
-  for (int j = 0; j < 8; ++j) xp.emit(m, tile_base + j * 32 * 128);
 }
 
 // ------------------------------------------------------------------------------------------
-// const-style variant: operand-producer team and epilogue team run CONCURRENTLY on different tiles
+// const-style variant
 // ------------------------------------------------------------------------------------------
-//   warps 0-7   P team: staging ring -> BN/modulation/lrelu -> bf16 hi/lo operand (tile t+1)
-//   warps 8-11  E team: TMEM accumulator of tile t -> bias/residual/ToRGB/statistics -> HBM; warp 8+q
-//               owns TMEM lanes 32q..32q+31 and all 256 columns
-//   warp 12 MMA issuer, warp 13 weight producer, warp 14 activation / residual producer
-// v2 ran prologue(t+1) and epilogue(t) back to back on the same 8 warps (2 per scheduler, latency-bound:
-// 26.6 % tensor, 45 % of DRAM peak).  Here a scheduler holds 2 P warps + 1 E warp and the tile period is
-// max(T_P, T_E, T_MMA) instead of T_P + T_E.
-constexpr int kConstThreads = 480;
-constexpr int kXs = 3;   // staging slots 0..2: activation slices (P team)
-constexpr int kSs = 2;   // staging slots 3..4: residual slices (E team)
-
 template <int kPasses>
-__global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs a) {
+__global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const SynSmem m = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  init_common(a, m, /*tmem_warp=*/12, warp, /*acc_empty_count=*/4, kXs, /*x_count=*/8, /*s_count=*/4);
+  init_common(a, m, warp);
   const uint32_t tmem = *m.tmem_slot;
-  const int T = (a.HW + 127) / 128;
-  const int num_tiles = a.B * T;
-  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  auto tile_of = [&](int it, int& b, int& ti) {
-    const int tile = blockIdx.x + it * gridDim.x;
-    b = tile / T;
-    ti = tile - b * T;
-  };
+  TileMap tm;
+  tm.T = (a.HW + 127) / 128;
+  tm.first = blockIdx.x;
+  tm.stride = gridDim.x;
+  tm.count = (a.B * tm.T - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp < 8) {
-    // ------------------------------------------------------------------ P team
+    // ------------------------------------------------------------------ operand team
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     int cur_b = -1;
     uint32_t acnt = 0;   // operand chunks produced (2-slot ring)
-    uint32_t xg = 0;     // activation slices: every P warp walks every slice, half h reads the ones with parity h
-    for (int it = 0; it < my_tiles; ++it) {
+    uint32_t xg = 0;     // activation slices walked
+    for (int it = 0; it < tm.count; ++it) {
       int b, ti;
-      tile_of(it, b, ti);
+      tm.get(it, b, ti);
       if (b != cur_b) {  // refresh the per-sample modulation table
         rows_barrier();
         for (int i = threadIdx.x; i < kC; i += 256) {
@@ -404,18 +432,7 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
       for (int kc = 0; kc < 4; ++kc, ++acnt) {
         const int c0 = kc * 64 + h * 32;
         float cur[32];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh, ++xg) {
-          const uint32_t xslot = xg % kXs;
-          mbar_wait_sleep(m.bars + X_FULL + xslot, (xg / kXs) & 1);
-          if (hh == h) {
-            const uint32_t xs = smem_u32(m.x_st + xslot * (kXSlice / 4)) + row * 4;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) cur[j] = lds_f32(xs + j * 512);
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(m.bars + X_EMPTY + xslot);
-        }
+        take_x_pair(m, xg, h, row, lane, cur);
         const uint32_t slot = acnt & 1;
         mbar_wait_sleep(m.bars + A_EMPTY + slot, ((acnt >> 1) & 1) ^ 1);
 #pragma unroll
@@ -437,124 +454,13 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
       }
     }
   } else if (warp < 12) {
-    // ------------------------------------------------------------------ E team
-    const int q = warp - 8;
-    const int row = q * 32 + lane;
-    uint32_t sg = 0;   // residual slices consumed
-    uint32_t tbias = smem_u32(m.tab_bias), trgb = smem_u32(m.tab_rgbw);   // constant tables, written before init's barrier
-    opaque(tbias);
-    opaque(trgb);
-    for (int it = 0; it < my_tiles; ++it) {
-      int b, ti;
-      tile_of(it, b, ti);
-      const uint32_t buf = it & 1;
-      const int pix = ti * 128 + row;
-      const bool valid = pix < a.HW;
-      const long plane = (static_cast<long>(b) * T + ti) * kC * 128 + row;
-      mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
-      tc_fence_after();
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-      // without a residual the 2 residual staging slots (32 KB) are free: use them as per-warp [32][33]
-      // transpose scratch for the statistics (32 STS + 32 LDS + 64 FP instead of a 248-instruction shuffle tree)
-      float* scratch = m.x_st + kXs * (kXSlice / 4) + q * (32 * 33);
-#pragma unroll 1
-      for (int cg = 0; cg < 8; ++cg) {
-        const int c0 = cg * 32;
-        uint32_t raw[32];
-        tmem_ld32(tmem + buf * 256 + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
-        float sk[32];
-        if (a.skip) {
-          const uint32_t sslot = kXs + sg % kSs;
-          mbar_wait_sleep(m.bars + X_FULL + sslot, (sg / kSs) & 1);
-          const uint32_t xs = smem_u32(m.x_st + sslot * (kXSlice / 4)) + row * 4;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sk[j] = lds_f32(xs + j * 512);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(m.bars + X_EMPTY + sslot);
-          ++sg;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sk[j] = 0.f;
-        }
-        tmem_ld_wait();
-        float v[32], s2[32];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float bs[8];
-          lds8(tbias + (c0 + g * 8) * 4, bs);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int j = g * 8 + jj;
-            float o = __uint_as_float(raw[j]) + bs[jj] + sk[j];
-            if (valid) a.out[plane + (c0 + j) * 128] = o;
-            o = valid ? o : 0.f;
-            v[j] = o;
-            s2[j] = o * o;
-          }
-          if (a.rgb_w) {
-            float w0[8], w1[8], w2[8];
-            lds8(trgb + (c0 + g * 8) * 4, w0);
-            lds8(trgb + (kC + c0 + g * 8) * 4, w1);
-            lds8(trgb + (2 * kC + c0 + g * 8) * 4, w2);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              r0 = fmaf(v[g * 8 + jj], w0[jj], r0);
-              r1 = fmaf(v[g * 8 + jj], w1[jj], r1);
-              r2 = fmaf(v[g * 8 + jj], w2[jj], r2);
-            }
-          }
-        }
-        if (a.stats) {
-          float t1, t2;
-          if (a.skip) {
-            t1 = transpose_reduce32(v, lane);
-            t2 = transpose_reduce32(s2, lane);
-          } else {
-            const uint32_t sa = smem_u32(scratch);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + (lane * 33 + j) * 4), "f"(v[j]) : "memory");
-            __syncwarp();
-            t1 = 0.f;
-            t2 = 0.f;
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const float x = lds_f32(sa + (r * 33 + lane) * 4);
-              t1 += x;
-              t2 = fmaf(x, x, t2);
-            }
-          }
-          atomicAdd(m.st_sum + c0 + lane, t1);
-          atomicAdd(m.st_sq + c0 + lane, t2);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(m.bars + ACC_EMPTY + buf);
-      if (a.rgb_w && valid) {   // this thread saw all 256 channels of its pixel
-        const float r[3] = {r0, r1, r2};
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const long idx = (static_cast<long>(b) * 3 + j) * a.HW + pix;
-          float o = r[j] + a.rgb_b[j];
-          if (a.rgb_in) o += a.rgb_in[idx];
-          a.rgb_out[idx] = o;
-        }
-      }
-    }
-    asm volatile("bar.sync 2, 128;" ::: "memory");
-    if (a.stats) {
-      for (int c = threadIdx.x - 256; c < kC; c += 128) {
-        atomicAdd(a.stats + c, static_cast<double>(m.st_sum[c]));
-        atomicAdd(a.stats + kC + c, static_cast<double>(m.st_sq[c]));
-      }
-    }
+    epilogue_team_loop(a, m, tm, tmem, warp - 8, lane);
   } else if (warp == 12) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 256);
       MmaPipe p;
       uint32_t acnt = 0;
-      for (int it = 0; it < my_tiles; ++it) {
+      for (int it = 0; it < tm.count; ++it) {
         const uint32_t buf = it & 1;
         mbar_wait_sleep(m.bars + ACC_EMPTY + buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -573,37 +479,12 @@ __global__ void __launch_bounds__(kConstThreads, 1) spade_const_kernel(SpadeArgs
     if (lane == 0) {
       const uint8_t* imgs[1] = {a.wimg};
       const int ns[1] = {8};
-      weight_producer_loop<kPasses>(m, imgs, ns, 1, my_tiles);
+      weight_producer_loop<kPasses>(m, imgs, ns, 1, tm.count);
     }
+  } else if (warp == 14) {
+    if (lane == 0) x_producer_loop(a, m, tm);
   } else {
-    if (lane == 0) {
-      // two independent rings: activation slices for the P team (slots 0..2), residual slices for the E team
-      // (slots 3..4).  The P team runs one tile ahead of the E team, so interleave x(it+1) with skip(it).
-      uint32_t xg = 0, sg = 0;
-      auto emit_x = [&](const float* src) {
-        const uint32_t slot = xg % kXs;
-        mbar_wait_backoff(m.bars + X_EMPTY + slot, ((xg / kXs) & 1) ^ 1);
-        mbar_arrive_expect_tx(m.bars + X_FULL + slot, kXSlice);
-        bulk_g2s(m.x_st + slot * (kXSlice / 4), src, kXSlice, m.bars + X_FULL + slot);
-        ++xg;
-      };
-      auto emit_s = [&](const float* src) {
-        const uint32_t slot = kXs + sg % kSs;
-        mbar_wait_backoff(m.bars + X_EMPTY + slot, ((sg / kSs) & 1) ^ 1);
-        mbar_arrive_expect_tx(m.bars + X_FULL + slot, kXSlice);
-        bulk_g2s(m.x_st + slot * (kXSlice / 4), src, kXSlice, m.bars + X_FULL + slot);
-        ++sg;
-      };
-      auto xbase = [&](int it) { int b, ti; tile_of(it, b, ti); return a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * kC * 128; };
-      auto sbase = [&](int it) { int b, ti; tile_of(it, b, ti); return a.skip + (static_cast<long>(b) * T + ti) * kC * 128; };
-      if (my_tiles > 0)
-        for (int j = 0; j < 8; ++j) emit_x(xbase(0) + j * 32 * 128);
-      for (int it = 0; it < my_tiles; ++it)
-        for (int j = 0; j < 8; ++j) {
-          if (it + 1 < my_tiles) emit_x(xbase(it + 1) + j * 32 * 128);
-          if (a.skip) emit_s(sbase(it) + j * 32 * 128);
-        }
-    }
+    if (lane == 0) skip_producer_loop(a, m, tm);
   }
   tc_fence_before();
   __syncthreads();
@@ -623,9 +504,6 @@ __device__ __forceinline__ void bilin(int dst, int in_size, float scale, int& i0
   l0 = 1.f - l1;
 }
 
-// Per tile: A1 = relu(bilinear(P_lr)+c) [2 chunks] -> GEMM1 (gamma|beta, 4 x N=256 accumulations into both
-// TMEM halves) -> y = lrelu(BN(x)*(1+gamma)+beta) [4 chunks through the 2-slot ring, chunk-pipelined with
-// GEMM2 from chunk 2 on] -> GEMM2 (conv) into TMEM half A (free once chunks 0,1 of y are built) -> epilogue.
 template <int kPasses>
 __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -636,36 +514,34 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
     m.tab_g0[i] = a.scsh[kC + i];
   }
   for (int i = threadIdx.x; i < 512; i += blockDim.x) m.tab_bgb[i] = a.bgb[i];
-  init_common(a, m, /*tmem_warp=*/8, warp, /*acc_empty_count=*/8, kXSlots, /*x_count=*/8, /*s_count=*/8);
+  init_common(a, m, warp);
   const uint32_t tmem = *m.tmem_slot;
-  const int T = (a.HW + 127) / 128;
-  const int num_tiles = a.B * T;
-  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  TileMap tm;
+  tm.T = (a.HW + 127) / 128;
+  tm.first = blockIdx.x;
+  tm.stride = gridDim.x;
+  tm.count = (a.B * tm.T - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const float sy = static_cast<float>(a.Rh) / static_cast<float>(a.Hg);
   const float sx = static_cast<float>(a.Rw) / static_cast<float>(a.Wg);
-  auto tile_of = [&](int it, int& b, int& ti) {
-    const int tile = blockIdx.x + it * gridDim.x;
-    b = tile / T;
-    ti = tile - b * T;
-  };
 
   if (warp < 8) {
+    // ------------------------------------------------------------------ operand team
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
-    uint32_t acnt = 0;
-    XConsumer xc;
+    uint32_t acnt = 0, xg = 0;
     uint32_t tg1 = smem_u32(m.tab_g1), tg0 = smem_u32(m.tab_g0), tbgb = smem_u32(m.tab_bgb);   // constant tables
     opaque(tg1);
     opaque(tg0);
     opaque(tbgb);
-    for (int it = 0; it < my_tiles; ++it) {
+    for (int it = 0; it < tm.count; ++it) {
       int b, ti;
-      tile_of(it, b, ti);
-      const int p0 = ti * 128;
-      const int pix = p0 + row;
+      tm.get(it, b, ti);
+      const int pix = ti * 128 + row;
       const bool valid = pix < a.HW;
-      // ---- phase 0: A1 = relu(bilinear(P_lr) + c): column half h builds K chunk h (slot h of the ring).
-      // The ring is empty here: the previous tile's GEMM2 finished before its epilogue (ACC_FULL).
+      const uint32_t R = (it & 1) * 256, Rp = 256 - R;      // TMEM halves of this tile
+      // ---- phase 0: A1 = relu(bilinear(P_lr) + c): column half h builds K chunk h into ring slot h.
+      // Both slots must have been consumed by the previous tile's conv (its chunks 2 and 3).
+      if (it > 0) mbar_wait_sleep(m.bars + A_EMPTY + h, 1);
       {
         const int py = valid ? pix / a.Wg : 0, px = valid ? pix % a.Wg : 0;
         int y0, y1, x0, x1;
@@ -703,22 +579,26 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
         __syncwarp();
         if (lane == 0) mbar_arrive(m.bars + A1_FULL);
       }
-      // ---- phase 1: gamma/beta accumulators -> y = lrelu(BN(x)*(1+gamma)+beta) -> operand ring
-      mbar_wait(m.bars + G1_FULL, it & 1);
-      tc_fence_after();
+      // ---- phase 1: y = lrelu(BN(x)*(1+gamma)+beta), chunks 0,1 from half R, chunks 2,3 from half R'
 #pragma unroll 1
       for (int kc = 0; kc < 4; ++kc, ++acnt) {
         const int c0 = kc * 64 + h * 32;
-        const uint32_t col = (kc >> 1) * 256 + (kc & 1) * 128 + h * 32;
-        uint32_t gr[32], br[32];
-        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + col, gr);
-        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + col + 64, br);
+        const uint32_t col = (kc >> 1) * 256 + (kc & 1) * 128 + h * 32;      // index into the bias table
+        const uint32_t tcol = (kc < 2 ? R : Rp) + (kc & 1) * 128 + h * 32;   // TMEM column
         float cur[32];
-        xc.take_pair(m, h, row, lane, cur);
+        take_x_pair(m, xg, h, row, lane, cur);
+        if (kc == 0) {   // gamma/beta of channels 0..127 ready; A1 may be overwritten only after BOTH gamma/beta GEMMs
+          mbar_wait_sleep(m.bars + G1A_FULL, it & 1);
+          mbar_wait_sleep(m.bars + G1B_FULL, it & 1);
+          tc_fence_after();
+        }
+        uint32_t gr[32], br[32];
+        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + tcol, gr);
+        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + tcol + 64, br);
         tmem_ld_wait();
         const uint32_t slot = acnt & 1;
-        // chunks 0,1 overwrite A1 (free: G1_FULL); chunks 2,3 wait for GEMM2 to have consumed chunks 0,1
-        mbar_wait(m.bars + A_EMPTY + slot, ((acnt >> 1) & 1) ^ 1);
+        // chunks 0,1 overwrite A1 (free: G1B_FULL); chunks 2,3 wait for the conv to have consumed chunks 0,1
+        mbar_wait_sleep(m.bars + A_EMPTY + slot, ((acnt >> 1) & 1) ^ 1);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float y[8], bg[8], bb[8], t1[8], t0[8];
@@ -741,74 +621,61 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
         __syncwarp();
         if (lane == 0) mbar_arrive(m.bars + A_FULL + slot);
       }
-      // ---- phase 2: conv accumulator
-      mbar_wait(m.bars + ACC_FULL, it & 1);
-      tc_fence_after();
-      conv_epilogue(a, m, xc, tmem, b, p0, warp, lane);
-      tc_fence_before();
-      rows_barrier();
-      if (a.rgb_w) {
-        rgb_finish(a, m, b, p0, warp, lane);
-        rows_barrier();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(m.bars + ACC_EMPTY);
     }
-    rows_barrier();
-    flush_stats(a, m);
-  } else if (warp == 8) {
+  } else if (warp < 12) {
+    epilogue_team_loop(a, m, tm, tmem, warp - 8, lane);
+  } else if (warp == 12) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 256);
       MmaPipe p;
       uint32_t acnt = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        // TMEM (both halves) is free once the previous tile's conv epilogue has drained
-        mbar_wait(m.bars + ACC_EMPTY, (it & 1) ^ 1);
-        mbar_wait(m.bars + A1_FULL, it & 1);
+      for (int it = 0; it < tm.count; ++it) {
+        const uint32_t R = (it & 1) * 256, Rp = 256 - R;
+        auto a1_hi = [&](int kc) { return smem_u32(m.a_hi + kc * kAChunk); };
+        auto a1_lo = [&](int kc) { return smem_u32(m.a_lo + kc * kAChunk); };
+        mbar_wait_sleep(m.bars + A1_FULL, it & 1);
         tc_fence_after();
-        for (int nb = 0; nb < 2; ++nb)
-          for (int kc = 0; kc < 2; ++kc)
-            mma_chunk<kPasses>(m, p, tmem + nb * 256, smem_u32(m.a_hi + kc * kAChunk), smem_u32(m.a_lo + kc * kAChunk),
-                               idesc, kc > 0);
-        umma_commit(m.bars + G1_FULL);
-        // y chunks 0 and 1 must BOTH exist before GEMM2 may overwrite TMEM half A (their gamma/beta live there)
+        // gamma|beta of channels 0..127 -> half R: free since the previous tile read its chunks 2,3 from it
+        // (that tile's A_FULL arrivals for chunks 2,3 precede this tile's A1_FULL)
+        for (int kc = 0; kc < 2; ++kc) mma_chunk<kPasses>(m, p, tmem + R, a1_hi(kc), a1_lo(kc), idesc, kc > 0);
+        umma_commit(m.bars + G1A_FULL);
+        // gamma|beta of channels 128..255 -> half R': holds the previous tile's conv accumulator until drained
+        if (it > 0) mbar_wait_sleep(m.bars + ACC_EMPTY + ((it - 1) & 1), ((it - 1) >> 1) & 1);
+        tc_fence_after();
+        for (int kc = 0; kc < 2; ++kc) mma_chunk<kPasses>(m, p, tmem + Rp, a1_hi(kc), a1_lo(kc), idesc, kc > 0);
+        umma_commit(m.bars + G1B_FULL);
+        // conv -> half R: y chunks 0 and 1 must BOTH exist first (their gamma/beta live in R)
         const uint32_t ph0 = (acnt >> 1) & 1;
-        mbar_wait(m.bars + A_FULL + 0, ph0);
-        mbar_wait(m.bars + A_FULL + 1, ph0);
+        mbar_wait_sleep(m.bars + A_FULL + 0, ph0);
+        mbar_wait_sleep(m.bars + A_FULL + 1, ph0);
         tc_fence_after();
         for (int kc = 0; kc < 4; ++kc, ++acnt) {
           const uint32_t slot = acnt & 1;
           if (kc >= 2) {
-            mbar_wait(m.bars + A_FULL + slot, (acnt >> 1) & 1);
+            mbar_wait_sleep(m.bars + A_FULL + slot, (acnt >> 1) & 1);
             tc_fence_after();
           }
-          mma_chunk<kPasses>(m, p, tmem, smem_u32(m.a_hi + slot * kAChunk), smem_u32(m.a_lo + slot * kAChunk), idesc, kc > 0);
+          mma_chunk<kPasses>(m, p, tmem + R, smem_u32(m.a_hi + slot * kAChunk), smem_u32(m.a_lo + slot * kAChunk), idesc, kc > 0);
           umma_commit(m.bars + A_EMPTY + slot);
         }
-        umma_commit(m.bars + ACC_FULL);
+        umma_commit(m.bars + ACC_FULL + (it & 1));
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     if (lane == 0) {
       // gamma/beta image: [2 nblocks][2 kchunks][hi,lo] = 8 stages, then the conv image: 8 stages
       const uint8_t* imgs[2] = {a.wgb, a.wimg};
       const int ns[2] = {8, 8};
-      weight_producer_loop<kPasses>(m, imgs, ns, 2, my_tiles);
+      weight_producer_loop<kPasses>(m, imgs, ns, 2, tm.count);
     }
+  } else if (warp == 14) {
+    if (lane == 0) x_producer_loop(a, m, tm);
   } else {
-    if (lane == 0) {
-      XProducer xp;
-      for (int it = 0; it < my_tiles; ++it) {
-        int b, ti;
-        tile_of(it, b, ti);
-        emit_tile(m, xp, a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * kC * 128);
-        if (a.skip) emit_tile(m, xp, a.skip + (static_cast<long>(b) * T + ti) * kC * 128);
-      }
-    }
+    if (lane == 0) skip_producer_loop(a, m, tm);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tmem);
+  if (warp == 12) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -924,7 +791,7 @@ int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float*
     KERNEL<<<grid, THREADS, hg::kSynSmemBytes, st>>>(a);                                                          \
   } while (0)
   if (mod) {
-    if (passes == 3) HG_LAUNCH(hg::spade_const_kernel<3>, hg::kConstThreads); else HG_LAUNCH(hg::spade_const_kernel<1>, hg::kConstThreads);
+    if (passes == 3) HG_LAUNCH(hg::spade_const_kernel<3>, hg::kSynThreads); else HG_LAUNCH(hg::spade_const_kernel<1>, hg::kSynThreads);
   } else {
     if (passes == 3) HG_LAUNCH(hg::spade_pixel_kernel<3>, hg::kSynThreads); else HG_LAUNCH(hg::spade_pixel_kernel<1>, hg::kSynThreads);
   }
