@@ -287,19 +287,19 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
         if (lane == 0) mbar_arrive(m.bars + RA_FULL + 0);
       }
       // ---- E0 .. E6
-      mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+      mbar_wait_sleep(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
       film_epilogue<kPasses, 0>(m, accA, 0, warp, lane, /*defer=*/true);
-      mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+      mbar_wait_sleep(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
       film_epilogue<kPasses, 0>(m, accB, 1, warp, lane, false);
-      mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+      mbar_wait_sleep(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
       film_epilogue<kPasses, 0>(m, accA, 2, warp, lane, false);
-      mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+      mbar_wait_sleep(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
       film_epilogue<kPasses, 0>(m, accB, 3, warp, lane, false);
-      mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+      mbar_wait_sleep(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
       film_epilogue<kPasses, 0>(m, accA, 4, warp, lane, false);
-      mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+      mbar_wait_sleep(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
       film_epilogue<kPasses, 1>(m, accB, 5, warp, lane, false);
-      mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+      mbar_wait_sleep(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
       film_epilogue<kPasses, 2>(m, accA, 6, warp, lane, false);
 
       if (a.raw_out) {
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
             po[j] = 1.f / (1.f + expf(-dot));
           }
         }
-        mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+        mbar_wait_sleep(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
 #pragma unroll 1
         for (int kc = 0; kc < 4; ++kc) {
           const int c0 = kc * 64 + h * 32;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
       const float back = a.white_back ? 1.f - Wsum : 0.f;
 
       // ---- E7: feature accumulator -> weighted sum over the ray
-      mbar_wait(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
+      mbar_wait_sleep(m.bars + RL_FULL, lph); lph ^= 1; tc_fence_after();
       float* ro = a.ray_out + (static_cast<long>(b) * a.R + ray) * kRayOut;
       if (S == 32) {
         // one warp == one ray: shuffle transpose-reduce, lane j ends with column j's sum

@@ -393,11 +393,24 @@ class Map3DGenerator(nn.Module):
                 latent = self.latent_pool(latent_indices)
             passes = _precision_passes(kwargs)
             use_graph = kwargs.get("hg_cuda_graph", os.environ.get("HG3D_CUDA_GRAPH", "0") == "1")
-            if use_graph and torch.distributed.is_available() and torch.distributed.is_initialized() \
-                    and torch.distributed.get_world_size() > 1 and self.training:
-                use_graph = False      # SyncBatchNorm all-reduces stay eager (NCCL inside a capture is not enabled here)
-            fn = self._forward_graphed if use_graph else self._forward_eager
-            rgb, rgb_render, _ = fn(latent, conditions, cfg, passes)
+            multi = torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1 and self.training
+            if use_graph and multi and not kwargs.get("hg_cuda_graph_nccl", os.environ.get("HG3D_CUDA_GRAPH_NCCL", "0") == "1"):
+                use_graph = False      # SyncBatchNorm all-reduces (NCCL) are captured only on explicit request
+            if use_graph and getattr(self, "_graph_broken", False):
+                use_graph = False
+            if use_graph:
+                try:
+                    rgb, rgb_render, _ = self._forward_graphed(latent, conditions, cfg, passes)
+                except RuntimeError as err:          # capture refused (e.g. a collective that cannot be captured here)
+                    if "hg3d:" in str(err):
+                        raise
+                    self._graph_broken = True
+                    import warnings
+                    warnings.warn(f"hg3d: CUDA-graph capture failed ({str(err)[:200]}); launching eagerly from now on")
+                    rgb, rgb_render, _ = self._forward_eager(latent, conditions, cfg, passes)
+            else:
+                rgb, rgb_render, _ = self._forward_eager(latent, conditions, cfg, passes)
         return {"rgbs": rgb, "rgbs_render": rgb_render}
 
     def staged_forward(self, latent, conditions, render_height, render_width, truncation_psi, **kwargs):

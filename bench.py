@@ -176,6 +176,7 @@ def run_gpu(args, pkg):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # the watchdog must not query events of a capturing stream
         dist.init_process_group("nccl", device_id=dev)
     abi.require_device()
 
@@ -186,7 +187,7 @@ def run_gpu(args, pkg):
     G.set_device(dev)
     G.train()
     passes_mode = args.precision
-    kw = dict(cfg, hg_precision=passes_mode, hg_cuda_graph=not args.no_graph)
+    kw = dict(cfg, hg_precision=passes_mode, hg_cuda_graph=not args.no_graph, hg_cuda_graph_nccl=not args.no_graph)
 
     # host (pinned) inputs: per-rank latents and poses
     cond_h = {k: v.pin_memory() for k, v in pkg.synthetic.make_conditions(B, seed=1 + rank).items()}
@@ -324,7 +325,8 @@ def run_gpu(args, pkg):
                    "parallelism": f"dp{world} (SyncBatchNorm statistics all-reduced over NCCL)" if world > 1 else "single GPU",
                    "l2": "activations are 2.1 GB per tensor (>> 126 MB L2): inputs larger than L2, no flush needed",
                    "precision": passes_mode,
-                   "launch": "eager" if args.no_graph or (world > 1) else "whole forward replayed as one CUDA graph"},
+                   "launch": "eager" if (args.no_graph or getattr(G, "_graph_broken", False)) else
+                   "whole forward replayed as one CUDA graph" + (" (NCCL all-reduces captured)" if world > 1 else "")},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
