@@ -36,6 +36,7 @@ SIGNATURES = {
     "hg_render_weight_blob_bytes": (c_size_t, []),
     "hg_render_mlp": (c_int, [c_void_p] * 12 + [c_int] * 4 + [c_float] + [c_int] * 4 + [c_void_p]),
     "hg_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    "hg_bias_act_grad": (c_int, [c_void_p] * 6 + [c_long, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 14 + [c_float, c_void_p]),
     "hg_conv2d": (c_int, [c_void_p, c_int, c_void_p, c_int] + [c_int] * 6 + [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
                               c_void_p, c_int, c_void_p]),

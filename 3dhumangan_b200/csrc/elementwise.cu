@@ -49,6 +49,55 @@ __global__ void bias_act_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
+
+// First / second derivative of act at the pre-activation t, written in terms of the saved forward OUTPUT
+// (yy = y / gain) wherever the function allows it, so that backward never needs the forward input
+// (bias_act.py:22-32 `ref='y'`; swish is the one activation that needs t itself).  order 1: act'(t), 2: act''(t).
+__device__ __forceinline__ float act_derivative(float t, float yy, int act, float alpha, int order) {
+  const float kS = 1.0507009873554805f, kSA = 1.0507009873554805f * 1.6732632423543772f;
+  if (order == 1) {
+    switch (act) {
+      case 2: return yy > 0.f ? 1.f : 0.f;
+      case 3: return yy > 0.f ? 1.f : alpha;
+      case 4: return 1.f - yy * yy;
+      case 5: return yy * (1.f - yy);
+      case 6: return yy >= 0.f ? 1.f : yy + 1.f;
+      case 7: return yy >= 0.f ? kS : yy + kSA;
+      case 8: return 1.f - expf(-yy);
+      case 9: { const float s = 1.f / (1.f + expf(-t)); return s * (1.f + t * (1.f - s)); }
+      default: return 1.f;
+    }
+  }
+  switch (act) {
+    case 4: return (1.f - yy * yy) * (-2.f * yy);
+    case 5: return yy * (1.f - yy) * (1.f - 2.f * yy);
+    case 6: return yy >= 0.f ? 0.f : yy + 1.f;
+    case 7: return yy >= 0.f ? 0.f : yy + kSA;
+    case 8: { const float c = expf(-yy); return c * (1.f - c); }
+    case 9: { const float s = 1.f / (1.f + expf(-t)); const float q = s * (1.f - s); return 2.f * q + t * q * (1.f - 2.f * s); }
+    default: return 0.f;
+  }
+}
+
+// out = g * gain * act^(order)(xref + b) * dy, zero where the forward output was clamped.
+__global__ void bias_act_grad_kernel(const float* __restrict__ g, const float* __restrict__ b,
+                                     const float* __restrict__ xref, const float* __restrict__ yref,
+                                     const float* __restrict__ dy, float* __restrict__ out, long n, int stepB, int sizeB,
+                                     int order, int act, float alpha, float gain, float clamp) {
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+  const float inv_gain = gain != 0.f ? 1.f / gain : 0.f;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float t = xref ? xref[i] : 0.f;
+    if (b) t += b[(i / stepB) % sizeB];
+    float y = yref ? yref[i] : 0.f;
+    if (act == 9) y = act_apply(t, 9, alpha) * gain;       // swish keeps x, not y: rebuild y for the clamp mask
+    float v = g[i] * gain * act_derivative(t, y * inv_gain, act, alpha, order);
+    if (dy) v *= dy[i];
+    if (clamp >= 0.f && !(y > -clamp && y < clamp)) v = 0.f;
+    out[i] = v;
+  }
+}
+
 // out[n,c,oy,ox] = sum_{ky,kx} xup[oy*downy + ky - pady0, ox*downx + kx - padx0] * g[ky,kx]
 // where xup is x with (up-1) zeros inserted and g is the (optionally pre-flipped) filter.
 __global__ void upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ f, float* __restrict__ y,
@@ -102,6 +151,25 @@ int hg_bias_act(const float* x, const float* b, float* y, long n, int stepB, int
   hg::bias_act_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, b, y, n, stepB, sizeB, act, alpha, gain, clamp);
   return hg::check_launch("hg_bias_act");
+}
+
+int hg_bias_act_grad(const float* g, const float* b, const float* xref, const float* yref, const float* dy, float* out,
+                     long n, int stepB, int sizeB, int order, int act, float alpha, float gain, float clamp,
+                     void* stream) {
+  HG_REQUIRE(g && out, "hg_bias_act_grad: null pointer");
+  HG_REQUIRE(act >= 1 && act <= 9, "hg_bias_act_grad: unknown activation id %d", act);
+  HG_REQUIRE(order == 1 || order == 2, "hg_bias_act_grad: derivative order must be 1 or 2 (got %d)", order);
+  HG_REQUIRE(!b || (stepB > 0 && sizeB > 0), "hg_bias_act_grad: bad bias geometry");
+  HG_REQUIRE(act == 1 || (act == 9 ? xref != nullptr : yref != nullptr),
+             "hg_bias_act_grad: activation %d needs its saved %s", act, act == 9 ? "input (xref)" : "output (yref)");
+  HG_REQUIRE(clamp < 0.f || act == 9 || yref, "hg_bias_act_grad: clamp needs the saved output (yref)");
+  if (n <= 0) return 0;
+  long blocks = (n + 255) / 256;
+  const long cap = static_cast<long>(hg::num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  hg::bias_act_grad_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, b, xref, yref, dy, out, n, stepB, sizeB, order, act, alpha, gain, clamp);
+  return hg::check_launch("hg_bias_act_grad");
 }
 
 int hg_upfirdn2d(const float* x, const float* f, float* y, int NC, int inH, int inW, int outH, int outW, int fH, int fW,

@@ -79,4 +79,6 @@ class UNetDiscriminator(nn.Module):
         if torch.is_grad_enabled() and (images.requires_grad or any(p.requires_grad for p in self.parameters())):
             raise RuntimeError("hg3d: the backward kernels of the sm_100a path are not built yet; call the "
                                "discriminator under torch.no_grad()")
-        return discriminator_ops.discriminator_forward(self, images)
+        from .generator import _precision_passes
+        passes = _precision_passes(kwargs)
+        return discriminator_ops.discriminator_forward(self, images, passes=passes)

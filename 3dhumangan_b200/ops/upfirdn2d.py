@@ -1,6 +1,10 @@
 """upfirdn2d: pad / zero-insert up-sample / FIR / decimate  (reference: lib/components/ops/upfirdn2d.py:117-161,
 upfirdn2d.cu:29-375).  Same Python signatures (`upfirdn2d`, `setup_filter`, `filter2d`, `upsample2d`,
-`downsample2d`); one implementation, the sm_100a kernel behind `hg_upfirdn2d`.  Forward only in this round.
+`downsample2d`); one implementation, the sm_100a kernel behind `hg_upfirdn2d`.
+
+Differentiable to any order in x: the adjoint of an up/FIR/down pass is the same kind of pass with up and
+down exchanged, the filter flipped and the padding mirrored (upfirdn2d.py:213-231 does the same), so the
+backward of the autograd op below is another application of itself.
 """
 import numpy as np
 import torch
@@ -61,23 +65,46 @@ def _run(x, f2d, upx, upy, downx, downy, px0, px1, py0, py1, flip, gain):
     return y
 
 
+class _Pass(torch.autograd.Function):
+    """One 2-D up/FIR/down pass.  geom = (upx, upy, downx, downy, px0, px1, py0, py1, flip, gain)."""
+
+    @staticmethod
+    def forward(ctx, x, f2d, geom):
+        ctx.geom, ctx.in_hw = geom, (x.shape[2], x.shape[3])
+        ctx.save_for_backward(f2d)
+        return _run(x.contiguous(), f2d, *geom)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (f2d,) = ctx.saved_tensors
+        upx, upy, downx, downy, px0, px1, py0, py1, flip, gain = ctx.geom
+        ih, iw = ctx.in_hw
+        oh, ow = dy.shape[2], dy.shape[3]
+        fh, fw = f2d.shape
+        # dx[i] = sum_o dy[o] * g[i*up - o*down + pad0]: a pass over dy with up<->down, the filter mirrored
+        # (pad0' = taps - 1 - pad0) and pad1' whatever makes the output the input's size again
+        back = (downx, downy, upx, upy, fw - px0 - 1, iw * upx - ow * downx + px0 - upx + 1, fh - py0 - 1,
+                ih * upy - oh * downy + py0 - upy + 1, not flip, gain)
+        dx = _Pass.apply(dy, f2d, back) if ctx.needs_input_grad[0] else None
+        return dx, None, None
+
+
 def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl="cuda"):
-    if torch.is_grad_enabled() and x.requires_grad:
-        raise RuntimeError("hg3d: upfirdn2d backward is not built yet; call under torch.no_grad()")
     assert x.ndim == 4
     upx, upy = _pair(up)
     downx, downy = _pair(down)
     px0, px1, py0, py1 = _padding(padding)
-    xin = x.detach().float().contiguous()
+    xin = x.float()
     if f is None:
         f = torch.ones(1, 1, dtype=torch.float32, device=x.device)
-    f = f.to(device=x.device, dtype=torch.float32).contiguous()
+    f = f.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    flip = bool(flip_filter)
     if f.ndim == 2:
-        y = _run(xin, f, upx, upy, downx, downy, px0, px1, py0, py1, flip_filter, gain)
+        y = _Pass.apply(xin, f, (upx, upy, downx, downy, px0, px1, py0, py1, flip, float(gain)))
     else:  # separable: a [1,fw] pass then a [fh,1] pass, gain split as in upfirdn2d.py:243-244
         g = float(gain) ** 0.5
-        y = _run(xin, f[None, :].contiguous(), upx, 1, downx, 1, px0, px1, 0, 0, flip_filter, g)
-        y = _run(y, f[:, None].contiguous(), 1, upy, 1, downy, 0, 0, py0, py1, flip_filter, g)
+        y = _Pass.apply(xin, f[None, :].contiguous(), (upx, 1, downx, 1, px0, px1, 0, 0, flip, g))
+        y = _Pass.apply(y, f[:, None].contiguous(), (1, upy, 1, downy, 0, 0, py0, py1, flip, g))
     return y.to(x.dtype)
 
 

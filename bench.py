@@ -279,8 +279,7 @@ def run_gpu(args, pkg):
     e2e = imgs / (ms_e2e / 1000.0)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(world, G)
         return
 
     # per-kernel device time from the events recorded inside the timed region
@@ -337,8 +336,19 @@ def run_gpu(args, pkg):
         "kernels": breakdown,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _leave(world, G)
+
+
+def _leave(world, G):
+    """End a multi-rank run without tearing NCCL down: destroying a communicator whose kernels are still referenced
+    by live CUDA graphs blocks, so drop the graphs, drain the device and leave the process directly."""
+    if world <= 1:
+        return
+    getattr(G, "_graphs", {}).clear()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

@@ -142,6 +142,15 @@ int hg_dense(const float* x, const float* w, const float* bias, float* out, int 
 int hg_bias_act(const float* x, const float* b, float* y, long n, int stepB, int sizeB, int act, float alpha,
                 float gain, float clamp, void* stream);
 
+/* Derivatives of bias_act   replaces the grad=1 / grad=2 modes of bias_act.cpp:32 (bias_act.cu:46-150).
+ * out = g * gain * act'(xref + b)            (order 1; g = incoming gradient)
+ * out = g * gain * act''(xref + b) * dy      (order 2; g = gradient of the first-order result, dy = its upstream)
+ * both zeroed where the forward output was clamped.  yref (forward output) is needed by every activation
+ * except linear and swish; swish needs xref (forward input, bias NOT added) and b.  Null = absent. */
+int hg_bias_act_grad(const float* g, const float* b, const float* xref, const float* yref, const float* dy, float* out,
+                     long n, int stepB, int sizeB, int order, int act, float alpha, float gain, float clamp,
+                     void* stream);
+
 /* Zero-insert up-sample, pad/crop, 2-D FIR, decimate   replaces upfirdn2d.cpp:16 / upfirdn2d.cu:29-375.
  * x [NC,inH,inW] -> y [NC,outH,outW]; f [fH,fW]; the filter is flipped unless flip_filter (conv2d is a correlation). */
 int hg_upfirdn2d(const float* x, const float* f, float* y, int NC, int inH, int inW, int outH, int outW, int fH,

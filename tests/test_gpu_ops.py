@@ -60,3 +60,54 @@ def test_upsample_downsample_wrappers(port):
     p_dn = [-6 + (fw - 1) // 2, -6 + (fw - 2) // 2] * 2
     ref_dn = port.upfirdn2d_ref(ref_up, f, down=2, padding=p_dn, flip_filter=True)
     assert torch.allclose(dn.cpu(), ref_dn, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("act", ["linear", "relu", "lrelu", "tanh", "sigmoid", "elu", "selu", "softplus", "swish"])
+def test_bias_act_gradients(port, act):
+    """First- and second-order gradients (bias_act.py:124-207) against autograd through the restated reference."""
+    ba = importlib.import_module("3dhumangan_b200.ops.bias_act")
+    g = torch.Generator().manual_seed(4)
+    x0 = torch.randn(3, 5, 7, 4, generator=g) * 1.5
+    if act in ("relu", "lrelu", "elu", "selu"):          # keep away from the kink, where one-sided derivatives differ
+        x0 = torch.where(x0.abs() < 0.05, torch.full_like(x0, 0.3), x0)
+    b0 = torch.randn(5, generator=g) * 0.1
+    w = torch.randn(3, 5, 7, 4, generator=g)
+    for clamp in (None, 0.9):
+        outs = []
+        for dev, fn in (("cpu", port.bias_act_ref), ("cuda", ba.bias_act)):
+            x = x0.to(dev).requires_grad_(True)
+            b = b0.to(dev).requires_grad_(True)
+            y = fn(x, b, dim=1, act=act, clamp=clamp)
+            gx, gb = torch.autograd.grad((y * w.to(dev)).sum(), (x, b), create_graph=True)
+            # a scalar of the first-order gradients -> second-order terms towards x, b (R1-style penalty)
+            pen = (gx * gx).sum() + (gb * gb).sum()
+            hx, hb = torch.autograd.grad(pen, (x, b), allow_unused=True)
+            hx = torch.zeros_like(x) if hx is None else hx
+            hb = torch.zeros_like(b) if hb is None else hb
+            outs.append([t.detach().cpu() for t in (y, gx, gb, hx, hb)])
+        for name, r, c in zip(("y", "dx", "db", "d2x", "d2b"), *outs):
+            assert torch.allclose(c, r, rtol=2e-4, atol=2e-5), (act, clamp, name, (c - r).abs().max())
+
+
+def test_upfirdn2d_gradients(port):
+    """The adjoint pass (and its own adjoint) against autograd through the restated reference."""
+    uf = importlib.import_module("3dhumangan_b200.ops.upfirdn2d")
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(2, 3, 14, 10, generator=g)
+    f2 = uf.setup_filter([1, 3, 3, 1])
+    f1 = uf.setup_filter([0.1, 0.2, 0.3, 0.25, 0.1, 0.05, 0.0, 0.0, 0.1, 0.2, 0.05, 0.02])
+    cases = [dict(f=f2), dict(f=f2, up=2, padding=[2, 1, 2, 1], gain=4), dict(f=f2, down=2, padding=1),
+             dict(f=f2, up=(2, 1), down=(1, 2), padding=[1, 2, 0, 3], flip_filter=True),
+             dict(f=f1, up=2, padding=[6, 5, 6, 5], gain=4), dict(f=f1, down=2, padding=[1, 2, 5, 5], flip_filter=True),
+             dict(f=f2, down=2, padding=[-1, -2, 0, -3]), dict(f=f2, up=3, down=2, padding=[2, 0, 1, 3])]
+    for kw in cases:
+        res = []
+        for dev, fn in (("cpu", port.upfirdn2d_ref), ("cuda", uf.upfirdn2d)):
+            x = x0.to(dev).requires_grad_(True)
+            y = fn(x, **{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in kw.items()})
+            w = torch.randn(y.shape, generator=torch.Generator().manual_seed(6)).to(dev).requires_grad_(True)
+            (gx,) = torch.autograd.grad((y * w).sum(), x, create_graph=True)
+            (gw,) = torch.autograd.grad((gx * gx).sum(), w)       # double backward: adjoint of the adjoint
+            res.append((gx.detach().cpu(), gw.detach().cpu()))
+        assert torch.allclose(res[1][0], res[0][0], rtol=1e-5, atol=1e-5), kw
+        assert torch.allclose(res[1][1], res[0][1], rtol=1e-4, atol=1e-4), kw
