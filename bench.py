@@ -99,7 +99,7 @@ def run_reference(args, pkg):
     cfg = workload_cfg(pkg, args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": t * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": describe(cfg, args.workload, 8), "timing": "host wall clock, bounded sample"},
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
@@ -322,7 +322,8 @@ def run_gpu(args, pkg):
         "data": "synthetic",
         "config": {"workload": describe(cfg, args.workload, B), "global_batch": B * world,
                    "parallelism": f"dp{world} (SyncBatchNorm statistics all-reduced over NCCL)" if world > 1 else "single GPU",
-                   "l2": "activations are 2.1 GB per tensor (>> 126 MB L2): inputs larger than L2, no flush needed",
+                   "l2": "every synthesis activation is %.2f GB (>> 126 MB L2): inputs larger than L2, no flush needed"
+                         % (B * 256 * cfg["gen_height"] * cfg["gen_width"] * 4 / 1e9),
                    "precision": passes_mode,
                    "launch": "eager" if (args.no_graph or getattr(G, "_graph_broken", False)) else
                    "whole forward replayed as one CUDA graph" + (" (NCCL all-reduces captured)" if world > 1 else "")},

@@ -81,7 +81,7 @@ def test_bias_act_gradients(port, act):
             gx, gb = torch.autograd.grad((y * w.to(dev)).sum(), (x, b), create_graph=True)
             # a scalar of the first-order gradients -> second-order terms towards x, b (R1-style penalty)
             pen = (gx * gx).sum() + (gb * gb).sum()
-            hx, hb = torch.autograd.grad(pen, (x, b), allow_unused=True)
+            hx, hb = torch.autograd.grad(pen, (x, b), allow_unused=True) if pen.requires_grad else (None, None)
             hx = torch.zeros_like(x) if hx is None else hx
             hb = torch.zeros_like(b) if hb is None else hb
             outs.append([t.detach().cpu() for t in (y, gx, gb, hx, hb)])

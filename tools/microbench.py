@@ -42,7 +42,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     args = ap.parse_args()
     pkg = importlib.import_module("3dhumangan_b200")
-    abi = pkg.abi
+    abi = importlib.import_module("3dhumangan_b200.abi")
     abi.require_device()
     peaks = {"hbm_gbps": 6573.8, "bf16_tflops": 1600.0, "source": "fallback"}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -58,7 +58,8 @@ def main():
     # ---- discriminator forward (a14): 386.8 GFLOP / image at 512^2 as executed by the reference
     cfg = pkg.configs.baseline_config("C2")
     torch.manual_seed(0)
-    D = pkg.dropin.lib.discriminators.UNetDiscriminator(**cfg).to(dev).train()
+    disc = importlib.import_module("3dhumangan_b200.modules.discriminator")
+    D = disc.UNetDiscriminator(**cfg).to(dev).train()
     img = torch.randn(B, 3, S, S, device=dev).clamp_(-1, 1)
     for mode in ("fp32x3", "bf16"):
         with torch.no_grad():
