@@ -35,6 +35,10 @@ SIGNATURES = {
     "hg_synth_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "hg_render_weight_blob_bytes": (c_size_t, []),
     "hg_render_mlp": (c_int, [c_void_p] * 12 + [c_int] * 4 + [c_float] + [c_int] * 4 + [c_void_p]),
+    "hg_spade_bwd_dgrad": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "hg_spade_bwd_wgrad_workspace_bytes": (c_size_t, []),
+    "hg_spade_bwd_wgrad": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "hg_spade_bwd_combine": (c_int, [c_void_p, c_void_p, c_long] + [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
     "hg_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_bias_act_grad": (c_int, [c_void_p] * 6 + [c_long, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 14 + [c_float, c_void_p]),
@@ -208,6 +212,40 @@ def spade_conv(x, x_bstride, wimg, bias, out, *, B, Hg, Wg, mod=None, scsh=None,
                                   ptr(rgb_w), ptr(rgb_b), ptr(rgb_in), ptr(rgb_out), B, 256, Hg, Wg, Rh, Rw, passes,
                                   stream())
     return out
+
+
+def spade_bwd_dgrad(dout, x, x_bstride, mod, wimg_t, dpre, sums, *, B, Hg, Wg, passes=3):
+    """dpre = (W^T dout) * lrelu'(x*g1+g0); sums [B,2,C] float64 += (sum dpre, sum dpre*x)  (csrc/synth.cu)."""
+    with torch.cuda.device_of(dout):
+        call("hg_spade_bwd_dgrad", ptr(dout), ptr(x), int(x_bstride), ptr(mod), ptr(wimg_t), ptr(dpre), ptr(sums), B, 256,
+             Hg, Wg, passes, stream())
+    return dpre
+
+
+_WGRAD_WS = {}
+
+
+def spade_bwd_wgrad(dout, x, x_bstride, mod, *, B, Hg, Wg, passes=3, want_bias=True):
+    """dW [C,C] = sum dout (x) lrelu(x*g1+g0), dbias [C] = sum dout  (csrc/synth_bwd.cu)."""
+    dev = dout.device
+    ws = _WGRAD_WS.get(dev)
+    if ws is None:
+        ws = _WGRAD_WS[dev] = torch.empty(int(lib().hg_spade_bwd_wgrad_workspace_bytes()) // 4, dtype=torch.float32, device=dev)
+    dw = torch.empty(256, 256, dtype=torch.float32, device=dev)
+    db = torch.empty(256, dtype=torch.float32, device=dev) if want_bias else None
+    with torch.cuda.device_of(dout):
+        call("hg_spade_bwd_wgrad", ptr(dout), ptr(x), int(x_bstride), ptr(mod), ptr(dw), ptr(db), ptr(ws), B, 256, Hg, Wg,
+             passes, stream())
+    return dw, db
+
+
+def spade_bwd_combine(dx, *, B, Hg, Wg, dpre=None, x=None, x_bstride=0, g1=None, ak=None, dskip=None, drgb=None, rgb_w=None,
+                      dwrgb=None):
+    """dx = dpre*g1 + a + k*x (+ dskip) (+ rgb_w^T drgb); dwrgb [3,C] float64 += drgb . x^T  (csrc/synth_bwd.cu)."""
+    with torch.cuda.device_of(dx):
+        call("hg_spade_bwd_combine", ptr(dpre), ptr(x), int(x_bstride), ptr(g1), ptr(ak), ptr(dskip), ptr(drgb), ptr(rgb_w),
+             ptr(dx), ptr(dwrgb), B, 256, Hg, Wg, stream())
+    return dx
 
 
 def bn_finalize(stats, weight, bias, running_mean, running_var, training, *, count=0.0, count_dev=None, gb=None, B=0,

@@ -21,34 +21,55 @@ __device__ __forceinline__ float act_apply(float x, int act, float alpha) {
   }
 }
 
-__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y,
-                                long n, int stepB, int sizeB, int act, float alpha, float gain, float clamp) {
-  const long i4 = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  if (i4 >= n) return;
-  float v[4];
-  const bool vec = (i4 + 4 <= n);
-  if (vec) {
-    const float4 t = *reinterpret_cast<const float4*>(x + i4);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  } else {
-    for (int j = 0; j < 4; ++j) v[j] = (i4 + j < n) ? x[i4 + j] : 0.f;
-  }
+// One float4 per lane and iteration, two iterations in flight; Idx = uint32_t whenever the tensor has < 2^32
+// elements (a 64-bit division per element costs more than the activation).  kVecBias: stepB % 4 == 0, so the
+// four lanes of a float4 share one bias element.
+template <typename Idx, bool kVecBias>
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                                       float* __restrict__ y, long n, Idx stepB, Idx sizeB, int act,
+                                                       float alpha, float gain, float clamp) {
+  const Idx nvec = static_cast<Idx>(n >> 2);
+  const Idx stride = static_cast<Idx>(gridDim.x) * blockDim.x;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  auto apply = [&](float4 t, Idx i) {
+    float v[4] = {t.x, t.y, t.z, t.w};
+    if (b) {
+      const Idx e = i * 4;
+      if (kVecBias) {
+        const float bb = __ldg(b + (e / stepB) % sizeB);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float t = v[j];
-    if (b) t += b[((i4 + j) / stepB) % sizeB];
-    t = act_apply(t, act, alpha) * gain;
-    if (clamp >= 0.f) t = fminf(fmaxf(t, -clamp), clamp);
-    v[j] = t;
+        for (int j = 0; j < 4; ++j) v[j] += bb;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += __ldg(b + ((e + j) / stepB) % sizeB);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float u = act_apply(v[j], act, alpha) * gain;
+      if (clamp >= 0.f) u = fminf(fmaxf(u, -clamp), clamp);
+      v[j] = u;
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+  };
+  Idx i = static_cast<Idx>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + stride < nvec; i += 2 * stride) {
+    const float4 t0 = __ldcs(x4 + i), t1 = __ldcs(x4 + i + stride);
+    __stcs(y4 + i, apply(t0, i));
+    __stcs(y4 + i + stride, apply(t1, i + stride));
   }
-  if (vec) {
-    *reinterpret_cast<float4*>(y + i4) = make_float4(v[0], v[1], v[2], v[3]);
-  } else {
-    for (int j = 0; j < 4; ++j)
-      if (i4 + j < n) y[i4 + j] = v[j];
+  if (i < nvec) __stcs(y4 + i, apply(__ldcs(x4 + i), i));
+  // tail (n % 4 elements)
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long e = (n & ~3L) + threadIdx.x;
+    float u = x[e];
+    if (b) u += b[(e / static_cast<long>(stepB)) % static_cast<long>(sizeB)];
+    u = act_apply(u, act, alpha) * gain;
+    if (clamp >= 0.f) u = fminf(fmaxf(u, -clamp), clamp);
+    y[e] = u;
   }
 }
-
 
 // First / second derivative of act at the pre-activation t, written in terms of the saved forward OUTPUT
 // (yy = y / gain) wherever the function allows it, so that backward never needs the forward input
@@ -80,29 +101,54 @@ __device__ __forceinline__ float act_derivative(float t, float yy, int act, floa
 }
 
 // out = g * gain * act^(order)(xref + b) * dy, zero where the forward output was clamped.
-__global__ void bias_act_grad_kernel(const float* __restrict__ g, const float* __restrict__ b,
+template <typename Idx>
+__global__ void __launch_bounds__(256) bias_act_grad_kernel(const float* __restrict__ g, const float* __restrict__ b,
                                      const float* __restrict__ xref, const float* __restrict__ yref,
-                                     const float* __restrict__ dy, float* __restrict__ out, long n, int stepB, int sizeB,
+                                     const float* __restrict__ dy, float* __restrict__ out, long n, Idx stepB, Idx sizeB,
                                      int order, int act, float alpha, float gain, float clamp) {
-  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   const float inv_gain = gain != 0.f ? 1.f / gain : 0.f;
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float t = xref ? xref[i] : 0.f;
-    if (b) t += b[(i / stepB) % sizeB];
-    float y = yref ? yref[i] : 0.f;
+  auto one = [&](float gv, float t, float y, float d) {
     if (act == 9) y = act_apply(t, 9, alpha) * gain;       // swish keeps x, not y: rebuild y for the clamp mask
-    float v = g[i] * gain * act_derivative(t, y * inv_gain, act, alpha, order);
-    if (dy) v *= dy[i];
+    float v = gv * gain * act_derivative(t, y * inv_gain, act, alpha, order) * d;
     if (clamp >= 0.f && !(y > -clamp && y < clamp)) v = 0.f;
-    out[i] = v;
+    return v;
+  };
+  const Idx nvec = static_cast<Idx>(n >> 2);
+  const Idx stride = static_cast<Idx>(gridDim.x) * blockDim.x;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (Idx i = static_cast<Idx>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 g4 = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 t4 = xref ? __ldcs(reinterpret_cast<const float4*>(xref) + i) : zero4;
+    const float4 y4 = yref ? __ldcs(reinterpret_cast<const float4*>(yref) + i) : zero4;
+    const float4 d4 = dy ? __ldcs(reinterpret_cast<const float4*>(dy) + i) : one4;
+    if (b) {
+      const Idx e = i * 4;
+      t4.x += __ldg(b + (e / stepB) % sizeB);
+      t4.y += __ldg(b + ((e + 1) / stepB) % sizeB);
+      t4.z += __ldg(b + ((e + 2) / stepB) % sizeB);
+      t4.w += __ldg(b + ((e + 3) / stepB) % sizeB);
+    }
+    __stcs(reinterpret_cast<float4*>(out) + i,
+           make_float4(one(g4.x, t4.x, y4.x, d4.x), one(g4.y, t4.y, y4.y, d4.y), one(g4.z, t4.z, y4.z, d4.z),
+                       one(g4.w, t4.w, y4.w, d4.w)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long e = (n & ~3L) + threadIdx.x;
+    float t = xref ? xref[e] : 0.f;
+    if (b) t += b[(e / static_cast<long>(stepB)) % static_cast<long>(sizeB)];
+    out[e] = one(g[e], t, yref ? yref[e] : 0.f, dy ? dy[e] : 1.f);
   }
 }
 
 // out[n,c,oy,ox] = sum_{ky,kx} xup[oy*downy + ky - pady0, ox*downx + kx - padx0] * g[ky,kx]
-// where xup is x with (up-1) zeros inserted and g is the (optionally pre-flipped) filter.
-__global__ void upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ f, float* __restrict__ y,
-                                 int NC, int inH, int inW, int outH, int outW, int fH, int fW, int upx, int upy,
-                                 int downx, int downy, int padx0, int pady0, int flip, float gain) {
+// where xup is x with (up-1) zeros inserted and g is the (optionally pre-flipped) filter.  Polyphase form: only
+// the taps with (o*down + k - pad0) % up == 0 touch a sample, i.e. k = k0, k0+up, ... with consecutive
+// input indices, so the inner loops carry no division.  One thread per output, x fastest (coalesced loads and
+// stores; tap re-use is served by L1/L2).  grid: (ceil(outW/128), outH chunks, NC chunks).
+__global__ void __launch_bounds__(128) upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ f,
+                                                        float* __restrict__ y, int NC, int inH, int inW, int outH,
+                                                        int outW, int fH, int fW, int upx, int upy, int downx, int downy,
+                                                        int padx0, int pady0, int flip, float gain) {
   extern __shared__ float sf[];
   for (int i = threadIdx.x; i < fH * fW; i += blockDim.x) {
     // conv2d is a cross-correlation: the reference flips the filter unless flip_filter (upfirdn2d.py:200-203)
@@ -110,28 +156,36 @@ __global__ void upfirdn2d_kernel(const float* __restrict__ x, const float* __res
     sf[i] = (flip ? f[i] : f[(fH - 1 - ky) * fW + (fW - 1 - kx)]) * gain;
   }
   __syncthreads();
-  const long total = static_cast<long>(NC) * outH * outW;
-  for (long o = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; o < total;
-       o += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int ox = static_cast<int>(o % outW);
-    const int oy = static_cast<int>((o / outW) % outH);
-    const long nc = o / (static_cast<long>(outW) * outH);
-    const float* xp = x + nc * inH * inW;
-    float acc = 0.f;
-    for (int ky = 0; ky < fH; ++ky) {
-      const int uy = oy * downy + ky - pady0;
-      if (uy < 0 || uy % upy != 0) continue;
-      const int iy = uy / upy;
-      if (iy >= inH) continue;
-      for (int kx = 0; kx < fW; ++kx) {
-        const int ux = ox * downx + kx - padx0;
-        if (ux < 0 || ux % upx != 0) continue;
-        const int ix = ux / upx;
-        if (ix >= inW) continue;
-        acc = fmaf(xp[static_cast<long>(iy) * inW + ix], sf[ky * fW + kx], acc);
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= outW) return;
+  // horizontal phase of this column: first tap kx0 >= 0 with (ox*downx + kx0 - padx0) % upx == 0
+  const int bx = ox * downx - padx0;
+  int kx0 = ((-bx) % upx + upx) % upx;
+  int ix0 = (bx + kx0) / upx;                        // exact division (may be negative)
+  if (ix0 < 0) { kx0 += -ix0 * upx; ix0 = 0; }
+  int nx = kx0 < fW ? (fW - kx0 + upx - 1) / upx : 0;
+  if (ix0 + nx > inW) nx = inW - ix0;
+  for (int nc = blockIdx.z; nc < NC; nc += gridDim.z) {
+    const float* xp = x + static_cast<long>(nc) * inH * inW;
+    float* yp = y + static_cast<long>(nc) * outH * outW;
+    // a contiguous band of rows per block: consecutive output rows re-read the same input rows (L1 hits)
+    const int band = (outH + gridDim.y - 1) / gridDim.y;
+    const int oy_end = min(outH, static_cast<int>(blockIdx.y + 1) * band);
+    for (int oy = blockIdx.y * band; oy < oy_end; ++oy) {
+      const int by = oy * downy - pady0;
+      int ky0 = ((-by) % upy + upy) % upy;
+      int iy0 = (by + ky0) / upy;
+      if (iy0 < 0) { ky0 += -iy0 * upy; iy0 = 0; }
+      int ny = ky0 < fH ? (fH - ky0 + upy - 1) / upy : 0;
+      if (iy0 + ny > inH) ny = inH - iy0;
+      float acc = 0.f;
+      for (int a = 0; a < ny; ++a) {
+        const float* row = xp + static_cast<long>(iy0 + a) * inW + ix0;
+        const float* frow = sf + (ky0 + a * upy) * fW + kx0;
+        for (int c = 0; c < nx; ++c) acc = fmaf(__ldg(row + c), frow[c * upx], acc);
       }
+      yp[static_cast<long>(oy) * outW + ox] = acc;
     }
-    y[o] = acc;
   }
 }
 
@@ -147,9 +201,23 @@ int hg_bias_act(const float* x, const float* b, float* y, long n, int stepB, int
   HG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
              "hg_bias_act: x / y must be 16-byte aligned");
   if (n <= 0) return 0;
-  const long threads = (n + 3) / 4;
-  hg::bias_act_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, b, y, n, stepB, sizeB, act, alpha, gain, clamp);
+  const long nvec = (n + 3) / 4;
+  long blocks = (nvec + 511) / 512;                    // two float4 per thread and pass
+  const long cap = static_cast<long>(hg::num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  auto st = static_cast<cudaStream_t>(stream);
+  const bool vec_bias = b && (stepB % 4 == 0);
+  const unsigned grid = static_cast<unsigned>(blocks);
+  if (n < (1L << 32)) {
+    const uint32_t sB = b ? static_cast<uint32_t>(stepB) : 1u, zB = b ? static_cast<uint32_t>(sizeB) : 1u;
+    if (vec_bias) hg::bias_act_kernel<uint32_t, true><<<grid, 256, 0, st>>>(x, b, y, n, sB, zB, act, alpha, gain, clamp);
+    else hg::bias_act_kernel<uint32_t, false><<<grid, 256, 0, st>>>(x, b, y, n, sB, zB, act, alpha, gain, clamp);
+  } else {
+    const unsigned long long sB = b ? stepB : 1, zB = b ? sizeB : 1;
+    if (vec_bias) hg::bias_act_kernel<unsigned long long, true><<<grid, 256, 0, st>>>(x, b, y, n, sB, zB, act, alpha, gain, clamp);
+    else hg::bias_act_kernel<unsigned long long, false><<<grid, 256, 0, st>>>(x, b, y, n, sB, zB, act, alpha, gain, clamp);
+  }
   return hg::check_launch("hg_bias_act");
 }
 
@@ -163,12 +231,20 @@ int hg_bias_act_grad(const float* g, const float* b, const float* xref, const fl
   HG_REQUIRE(act == 1 || (act == 9 ? xref != nullptr : yref != nullptr),
              "hg_bias_act_grad: activation %d needs its saved %s", act, act == 9 ? "input (xref)" : "output (yref)");
   HG_REQUIRE(clamp < 0.f || act == 9 || yref, "hg_bias_act_grad: clamp needs the saved output (yref)");
+  for (const float* ptr : {g, xref, yref, dy, static_cast<const float*>(out)})
+    HG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "hg_bias_act_grad: tensors must be 16-byte aligned");
   if (n <= 0) return 0;
-  long blocks = (n + 255) / 256;
-  const long cap = static_cast<long>(hg::num_sms()) * 16;
+  long blocks = ((n + 3) / 4 + 255) / 256;
+  const long cap = static_cast<long>(hg::num_sms()) * 32;
   if (blocks > cap) blocks = cap;
-  hg::bias_act_grad_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      g, b, xref, yref, dy, out, n, stepB, sizeB, order, act, alpha, gain, clamp);
+  auto st = static_cast<cudaStream_t>(stream);
+  if (n < (1L << 32))
+    hg::bias_act_grad_kernel<uint32_t><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        g, b, xref, yref, dy, out, n, b ? static_cast<uint32_t>(stepB) : 1u, b ? static_cast<uint32_t>(sizeB) : 1u, order,
+        act, alpha, gain, clamp);
+  else
+    hg::bias_act_grad_kernel<unsigned long long><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        g, b, xref, yref, dy, out, n, b ? stepB : 1, b ? sizeB : 1, order, act, alpha, gain, clamp);
   return hg::check_launch("hg_bias_act_grad");
 }
 
@@ -179,11 +255,13 @@ int hg_upfirdn2d(const float* x, const float* f, float* y, int NC, int inH, int 
   HG_REQUIRE(upx >= 1 && upy >= 1 && downx >= 1 && downy >= 1, "hg_upfirdn2d: up/down factors must be >= 1");
   HG_REQUIRE(fH >= 1 && fW >= 1 && fH * fW <= 4096, "hg_upfirdn2d: filter too large");
   if (NC <= 0 || outH <= 0 || outW <= 0) return 0;
-  const long total = static_cast<long>(NC) * outH * outW;
-  long blocks = (total + 255) / 256;
-  const long cap = static_cast<long>(hg::num_sms()) * 32;
-  if (blocks > cap) blocks = cap;
-  hg::upfirdn2d_kernel<<<static_cast<unsigned>(blocks), 256, fH * fW * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  const int gx = (outW + 127) / 128;
+  int gy = (outH + 15) / 16;                       // >= 16 rows per block amortise the per-block filter setup
+  const int want = hg::num_sms() * 16;             // enough blocks to fill the machine
+  int gz = NC < 65535 ? NC : 65535;
+  while (gy > 1 && static_cast<long>(gx) * gy * gz > 4L * want && gz > 1) gz = (gz + 1) / 2;
+  dim3 grid(gx, gy, gz);
+  hg::upfirdn2d_kernel<<<grid, 128, fH * fW * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       x, f, y, NC, inH, inW, outH, outW, fH, fW, upx, upy, downx, downy, padx0, pady0, flip_filter, gain);
   return hg::check_launch("hg_upfirdn2d");
 }

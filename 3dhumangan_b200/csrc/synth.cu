@@ -64,7 +64,8 @@ struct SpadeArgs {
   const float* bgb;      // pixel-style: [512] bias in the same interleaved order (gamma part includes +1)
   const uint8_t* wimg;   // packed conv weight [256 x 256] (already divided by sigma)
   const float* bias;     // [C]
-  const float* skip;     // [B,T,C,128] residual or null
+  const float* skip;     // [B,T,C,128] residual or null   (backward: the forward input x of the half-block)
+  long skip_bstride;     // T*C*128, or 0 when shared by the whole batch
   float* out;            // [B,T,C,128]
   double* stats;         // [2,C] accumulated sum / sumsq of out, or null
   const float* rgb_w;    // [3,C] or null
@@ -251,7 +252,7 @@ __device__ __forceinline__ void skip_producer_loop(const SpadeArgs& a, const Syn
   for (int it = 0; it < tm.count; ++it) {
     int b, ti;
     tm.get(it, b, ti);
-    const float* base = a.skip + (static_cast<long>(b) * tm.T + ti) * kC * 128;
+    const float* base = a.skip + static_cast<long>(b) * a.skip_bstride + static_cast<long>(ti) * kC * 128;
     for (int j = 0; j < 8; ++j) ring_emit(m, g, kXs, kSs, base + j * 32 * 128);
   }
 }
@@ -389,10 +390,100 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
   }
 }
 
+
 // ------------------------------------------------------------------------------------------
-// const-style variant
+// warps 8-11 of the BACKWARD (data-gradient) variant.  The accumulator holds dL/dy = W^T dL/dout for the 128
+// pixels of the tile; the forward input x of the half-block arrives through the residual ring, so that
+//     pre = x*g1[b,c] + g0[b,c]            (the folded BatchNorm + SPADE modulation of the forward pass)
+//     dpre = dL/dy * lrelu'(pre)           -> stored (tile-blocked, like every activation)
+//     S1[b,c] += dpre,  S2[b,c] += dpre*x  -> everything BatchNorm / gamma / beta need (DESIGN.md "Backward")
 // ------------------------------------------------------------------------------------------
-template <int kPasses>
+__device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynSmem& m, const TileMap& tm, uint32_t tmem,
+                                                  int q, int lane) {
+  const int row = q * 32 + lane;
+  const int et = threadIdx.x - 256;   // 0..127 within the epilogue team
+  uint32_t sg = 0;
+  int cur_b = -1;
+  auto flush = [&](int b) {
+    for (int c = et; c < kC; c += 128) {
+      atomicAdd(a.stats + (static_cast<long>(b) * 2 + 0) * kC + c, static_cast<double>(m.st_sum[c]));
+      atomicAdd(a.stats + (static_cast<long>(b) * 2 + 1) * kC + c, static_cast<double>(m.st_sq[c]));
+      m.st_sum[c] = 0.f;
+      m.st_sq[c] = 0.f;
+    }
+  };
+  for (int it = 0; it < tm.count; ++it) {
+    int b, ti;
+    tm.get(it, b, ti);
+    if (b != cur_b) {   // per-sample tables and per-sample sums
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (cur_b >= 0) flush(cur_b);
+      for (int c = et; c < kC; c += 128) {
+        m.tab_g1[c] = a.mod[(static_cast<long>(b) * 2 + 0) * kC + c];
+        m.tab_g0[c] = a.mod[(static_cast<long>(b) * 2 + 1) * kC + c];
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      cur_b = b;
+    }
+    uint32_t tg1 = smem_u32(m.tab_g1), tg0 = smem_u32(m.tab_g0);
+    opaque(tg1);   // no table load may move above the refresh
+    opaque(tg0);
+    const uint32_t buf = it & 1;
+    const bool valid = ti * 128 + row < a.HW;
+    const long plane = (static_cast<long>(b) * tm.T + ti) * kC * 128 + row;
+    mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int cg = 0; cg < 8; ++cg) {
+      const int c0 = cg * 32;
+      uint32_t raw[32];
+      tmem_ld32(tmem + buf * 256 + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
+      float xs_[32];
+      {
+        const uint32_t sslot = kXs + sg % kSs;
+        mbar_wait_sleep(m.bars + X_FULL + sslot, (sg / kSs) & 1);
+        const uint32_t xs = smem_u32(m.x_st + sslot * (kXSlice / 4)) + row * 4;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xs_[j] = lds_f32(xs + j * 512);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(m.bars + X_EMPTY + sslot);
+        ++sg;
+      }
+      tmem_ld_wait();
+      float v[32], w[32];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float t1[8], t0[8];
+        lds8(tg1 + (c0 + g * 8) * 4, t1);
+        lds8(tg0 + (c0 + g * 8) * 4, t0);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = g * 8 + jj;
+          const float pre = fmaf(xs_[j], t1[jj], t0[jj]);
+          const float d = __uint_as_float(raw[j]) * (pre > 0.f ? 1.f : 0.2f);
+          if (valid) a.out[plane + (c0 + j) * 128] = d;
+          v[j] = valid ? d : 0.f;
+          w[j] = v[j] * xs_[j];
+        }
+      }
+      const float s1 = transpose_reduce32(v, lane);
+      const float s2 = transpose_reduce32(w, lane);
+      atomicAdd(m.st_sum + c0 + lane, s1);
+      atomicAdd(m.st_sq + c0 + lane, s2);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(m.bars + ACC_EMPTY + buf);
+  }
+  asm volatile("bar.sync 2, 128;" ::: "memory");
+  if (cur_b >= 0) flush(cur_b);
+}
+
+// ------------------------------------------------------------------------------------------
+// const-style variant.  kBwd: data gradient of the same half-block: the operand is dL/dout passed through
+// unchanged, the weight image is W^T, the epilogue is `epilogue_bwd_loop`.
+// ------------------------------------------------------------------------------------------
+template <int kPasses, bool kBwd>
 __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const SynSmem m = carve(smem_raw);
@@ -415,7 +506,7 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
     for (int it = 0; it < tm.count; ++it) {
       int b, ti;
       tm.get(it, b, ti);
-      if (b != cur_b) {  // refresh the per-sample modulation table
+      if (!kBwd && b != cur_b) {  // refresh the per-sample modulation table
         rows_barrier();
         for (int i = threadIdx.x; i < kC; i += 256) {
           m.tab_g1[i] = a.mod[(static_cast<long>(b) * 2 + 0) * kC + i];
@@ -438,10 +529,12 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float y[8], t1[8], t0[8];
-          lds8(tg1 + (c0 + g * 8) * 4, t1);
-          lds8(tg0 + (c0 + g * 8) * 4, t0);
+          if (!kBwd) {
+            lds8(tg1 + (c0 + g * 8) * 4, t1);
+            lds8(tg0 + (c0 + g * 8) * 4, t0);
+          }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = lrelu02(fmaf(cur[g * 8 + j], t1[j], t0[j]));
+          for (int j = 0; j < 8; ++j) y[j] = kBwd ? cur[g * 8 + j] : lrelu02(fmaf(cur[g * 8 + j], t1[j], t0[j]));
           if (!valid) {   // only the last, partial tile of an image
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = 0.f;
@@ -454,7 +547,8 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
       }
     }
   } else if (warp < 12) {
-    epilogue_team_loop(a, m, tm, tmem, warp - 8, lane);
+    if (kBwd) epilogue_bwd_loop(a, m, tm, tmem, warp - 8, lane);
+    else epilogue_team_loop(a, m, tm, tmem, warp - 8, lane);
   } else if (warp == 12) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 256);
@@ -779,7 +873,8 @@ int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float*
     HG_REQUIRE(!p_bias || (reinterpret_cast<uintptr_t>(p_bias) & 15) == 0, "hg_spade_conv: p_bias must be 16-byte aligned");
   }
   hg::SpadeArgs a{x, x_bstride, mod, scsh, p_lr, p_stride, p_bias, static_cast<const uint8_t*>(wgb), bgb,
-                  static_cast<const uint8_t*>(wimg), bias, skip, out, stats, rgb_w, rgb_b, rgb_in, rgb_out,
+                  static_cast<const uint8_t*>(wimg), bias, skip,
+                  static_cast<long>((Hg * Wg + 127) / 128) * hg::kC * 128, out, stats, rgb_w, rgb_b, rgb_in, rgb_out,
                   B, Hg * Wg, Hg, Wg, Rh, Rw};
   const int tiles = B * ((Hg * Wg + 127) / 128);
   const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
@@ -791,12 +886,44 @@ int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float*
     KERNEL<<<grid, THREADS, hg::kSynSmemBytes, st>>>(a);                                                          \
   } while (0)
   if (mod) {
-    if (passes == 3) HG_LAUNCH(hg::spade_const_kernel<3>, hg::kSynThreads); else HG_LAUNCH(hg::spade_const_kernel<1>, hg::kSynThreads);
+    if (passes == 3) HG_LAUNCH((hg::spade_const_kernel<3, false>), hg::kSynThreads); else HG_LAUNCH((hg::spade_const_kernel<1, false>), hg::kSynThreads);
   } else {
     if (passes == 3) HG_LAUNCH(hg::spade_pixel_kernel<3>, hg::kSynThreads); else HG_LAUNCH(hg::spade_pixel_kernel<1>, hg::kSynThreads);
   }
 #undef HG_LAUNCH
   return hg::check_launch("hg_spade_conv");
+}
+
+int hg_spade_bwd_dgrad(const float* dout, const float* x, long x_bstride, const float* mod, const void* wimg_t, float* dpre,
+                       double* sums, int B, int C, int Hg, int Wg, int passes, void* stream) {
+  HG_REQUIRE(C == hg::kC, "hg_spade_bwd_dgrad: only %d channels are supported (got %d)", hg::kC, C);
+  HG_REQUIRE(dout && x && mod && wimg_t && dpre && sums, "hg_spade_bwd_dgrad: null pointer");
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_spade_bwd_dgrad: passes must be 1 or 3");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_spade_bwd_dgrad: bad shape");
+  const long T = (Hg * Wg + 127) / 128;
+  hg::SpadeArgs a{};
+  a.x = dout;
+  a.x_bstride = T * hg::kC * 128;
+  a.mod = mod;
+  a.wimg = static_cast<const uint8_t*>(wimg_t);
+  a.bias = mod;            // unused by the backward epilogue; init_common reads C floats
+  a.skip = x;
+  a.skip_bstride = x_bstride;
+  a.out = dpre;
+  a.stats = sums;
+  a.B = B; a.HW = Hg * Wg; a.Hg = Hg; a.Wg = Wg;
+  const int tiles = B * static_cast<int>(T);
+  const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
+  auto st = static_cast<cudaStream_t>(stream);
+#define HG_LAUNCH_BWD(KERNEL)                                                                                     \
+  do {                                                                                                            \
+    cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kSynSmemBytes); \
+    if (e != cudaSuccess) { hg::set_error("hg_spade_bwd_dgrad: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; } \
+    KERNEL<<<grid, hg::kSynThreads, hg::kSynSmemBytes, st>>>(a);                                                  \
+  } while (0)
+  if (passes == 3) HG_LAUNCH_BWD((hg::spade_const_kernel<3, true>)); else HG_LAUNCH_BWD((hg::spade_const_kernel<1, true>));
+#undef HG_LAUNCH_BWD
+  return hg::check_launch("hg_spade_bwd_dgrad");
 }
 
 int hg_bn_finalize(const double* stats, double count, const double* count_dev, const float* weight, const float* bias, float* running_mean,

@@ -120,6 +120,27 @@ int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float*
                   const float* rgb_b, const float* rgb_in, float* rgb_out, int B, int C, int Hg, int Wg, int Rh, int Rw,
                   int passes, void* stream);
 
+/* ---- backward of a const-style SPADE half-block (autograd through map3d_layers.py:176-190, 218-238) ----
+ * Forward, folded:  pre = x*g1[b,c] + g0[b,c],  y = lrelu_0.2(pre),  out = W y + bias (+ skip);  mod = [B,2,C] (g1,g0).
+ *
+ * hg_spade_bwd_dgrad: dpre = (W^T dout) * lrelu'(pre) and sums[b,0,c] += sum_p dpre, sums[b,1,c] += sum_p dpre*x
+ *   (fp64, caller zeroes).  dout, dpre [B,T,C,128]; x [B or 1,T,C,128] with batch stride x_bstride;
+ *   wimg_t = hg_pack_weight of W^T (rows = ci, K = co).
+ * hg_spade_bwd_wgrad: dw[co,ci] = sum_{b,p} dout[b,co,p] * y[b,ci,p] (y recomputed from x, mod) and
+ *   dbias[co] = sum dout (NULL = skip).  workspace: hg_spade_bwd_wgrad_workspace_bytes() bytes of device memory.
+ * hg_spade_bwd_combine: dx = dpre*g1[b,c] + a[c] + k[c]*x (+ dskip) (+ rgb_w^T drgb), the gradient w.r.t. the
+ *   half-block input; ak = [2,C] (a, k) carries the terms that reach x through the batch statistics.  dwrgb [3,C]
+ *   (fp64, accumulated; NULL = skip) += sum_{b,p} drgb[b,j,p]*x[b,c,p].  Any of dpre/ak/dskip/drgb may be NULL. */
+int hg_spade_bwd_dgrad(const float* dout, const float* x, long x_bstride, const float* mod, const void* wimg_t,
+                       float* dpre, double* sums, int B, int C, int Hg, int Wg, int passes, void* stream);
+size_t hg_spade_bwd_wgrad_workspace_bytes(void);
+int hg_spade_bwd_wgrad(const float* dout, const float* x, long x_bstride, const float* mod, float* dw, float* dbias,
+                       void* workspace, int B, int C, int Hg, int Wg, int passes, void* stream);
+int hg_spade_bwd_combine(const float* dpre, const float* x, long x_bstride, const float* g1, const float* ak,
+                         const float* dskip, const float* drgb, const float* rgb_w, float* dx, double* dwrgb, int B,
+                         int C, int Hg, int Wg, void* stream);
+
+
 /* ---- discriminator --------------------------------------------------------------------------- */
 /* 3x3 (pad 1) / 1x1 convolution over NCHW fp32 planes as an implicit GEMM; replaces the conv2d calls of
  * ResBlock / UNetDiscriminator (unet_discriminators.py:7-72, 114-160) with the surrounding ops folded in:
