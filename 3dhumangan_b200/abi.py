@@ -39,6 +39,7 @@ SIGNATURES = {
     "hg_spade_bwd_wgrad_workspace_bytes": (c_size_t, []),
     "hg_spade_bwd_wgrad": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "hg_spade_bwd_combine": (c_int, [c_void_p, c_void_p, c_long] + [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
+    "hg_synth_input_bwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p]),
     "hg_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_bias_act_grad": (c_int, [c_void_p] * 6 + [c_long, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 14 + [c_float, c_void_p]),
@@ -246,6 +247,16 @@ def spade_bwd_combine(dx, *, B, Hg, Wg, dpre=None, x=None, x_bstride=0, g1=None,
         call("hg_spade_bwd_combine", ptr(dpre), ptr(x), int(x_bstride), ptr(g1), ptr(ak), ptr(dskip), ptr(drgb), ptr(rgb_w),
              ptr(dx), ptr(dwrgb), B, 256, Hg, Wg, stream())
     return dx
+
+
+def synth_input_bwd(dx, w, bias, ic, jc, B):
+    C = w.shape[0]
+    dw = torch.empty(C, 2, dtype=torch.float32, device=dx.device)
+    db = torch.empty(C, dtype=torch.float32, device=dx.device)
+    with torch.cuda.device_of(dx):
+        call("hg_synth_input_bwd", ptr(dx), ptr(w), ptr(bias), ptr(ic), ptr(jc), B, C, ic.numel(), jc.numel(), ptr(dw), ptr(db),
+             stream())
+    return dw, db
 
 
 def bn_finalize(stats, weight, bias, running_mean, running_var, training, *, count=0.0, count_dev=None, gb=None, B=0,

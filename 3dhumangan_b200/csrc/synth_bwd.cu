@@ -313,6 +313,46 @@ __global__ void __launch_bounds__(256) spade_combine_kernel(CombineArgs a) {
     for (int i = threadIdx.x; i < 3 * kWC; i += blockDim.x) atomicAdd(a.dwrgb + i, static_cast<double>(s_acc[i]));
 }
 
+
+// ------------------------------------------------------------------------------------------
+// synthesis input backward: x0[c,p] = sin(w[c,0]*i(p) + w[c,1]*j(p) + b[c]) is shared by the batch, so
+//   darg[c,p] = cos(arg) * sum_b dx[b,c,p];  dw[c,0] = sum_p darg*i,  dw[c,1] = sum_p darg*j,  db[c] = sum_p darg
+// (autograd through SynthesisInput.forward, map3d_layers.py:260-275).  One block per channel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) synth_input_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, const float* __restrict__ ic,
+                                                              const float* __restrict__ jc, int B, int Hg, int Wg,
+                                                              float* __restrict__ dw, float* __restrict__ db) {
+  const int c = blockIdx.x;
+  const int HW = Hg * Wg, T = (HW + 127) / 128;
+  const float w0 = w[c * 2 + 0], w1 = w[c * 2 + 1], bb = bias[c];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const float iv = ic[p / Wg], jv = jc[p % Wg];
+    float g = 0.f;
+    for (int b = 0; b < B; ++b) g += dx[((static_cast<long>(b) * T + (p >> 7)) * kWC + c) * 128 + (p & 127)];
+    const float d = g * cosf(fmaf(w1, jv, fmaf(w0, iv, bb)));
+    a0 += static_cast<double>(d * iv);
+    a1 += static_cast<double>(d * jv);
+    a2 += static_cast<double>(d);
+  }
+  __shared__ double red[3][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a0; red[1][threadIdx.x >> 5] = a1; red[2][threadIdx.x >> 5] = a2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0, t1 = 0, t2 = 0;
+    for (int i = 0; i < 8; ++i) { t0 += red[0][i]; t1 += red[1][i]; t2 += red[2][i]; }
+    dw[c * 2 + 0] = static_cast<float>(t0);
+    dw[c * 2 + 1] = static_cast<float>(t1);
+    db[c] = static_cast<float>(t2);
+  }
+}
+
 }  // namespace hg
 
 extern "C" {
@@ -369,6 +409,15 @@ int hg_spade_bwd_combine(const float* dpre, const float* x, long x_bstride, cons
   hg::CombineArgs a{dpre, x, x_bstride, g1, ak, dskip, drgb, rgb_w, dx, dwrgb, B, Hg * Wg};
   hg::spade_combine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return hg::check_launch("hg_spade_bwd_combine");
+}
+
+int hg_synth_input_bwd(const float* dx, const float* w, const float* bias, const float* ic, const float* jc, int B, int C,
+                       int Hg, int Wg, float* dw, float* db, void* stream) {
+  HG_REQUIRE(C == hg::kWC, "hg_synth_input_bwd: only %d channels are supported (got %d)", hg::kWC, C);
+  HG_REQUIRE(dx && w && bias && ic && jc && dw && db, "hg_synth_input_bwd: null pointer");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_synth_input_bwd: bad shape");
+  hg::synth_input_bwd_kernel<<<C, 256, 0, static_cast<cudaStream_t>(stream)>>>(dx, w, bias, ic, jc, B, Hg, Wg, dw, db);
+  return hg::check_launch("hg_synth_input_bwd");
 }
 
 }  // extern "C"

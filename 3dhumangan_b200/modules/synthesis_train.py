@@ -1,0 +1,228 @@
+"""Training-mode forward + backward of the SPADE synthesis network on the sm_100a kernels.
+
+Forward: the same 18 fused half-block launches as `synthesis_ops.synthesis_forward`, but every half-block
+input is kept (18 activations of B*HW*256 fp32 -- 2.1 GB each at the C2 workload; sized for 180 GB of HBM)
+and every [B,C]- / [C]-sized quantity the kernels consume (folded BatchNorm+SPADE tables, spectrally
+normalised weights) is built with torch autograd from its leaves.
+
+Backward (autograd through SynthesisNetwork.forward map3d_generator.py:58-97, SPADEBlock.forward
+map3d_layers.py:218-238, SPADE2d.forward :176-190, ToRGB :346-352, SynthesisInput :260-275), walking the
+half-blocks in reverse; per half-block
+    hg_spade_bwd_combine  dL/dout   from the next half-block's dpre (+ skip gradient, + ToRGB^T drgb)
+    hg_spade_bwd_dgrad    dpre = (W^T dL/dout) * lrelu'(pre), S1 = sum dpre, S2 = sum dpre*x     (tcgen05)
+    hg_spade_bwd_wgrad    dW = dL/dout . y^T, dbias                                              (tcgen05)
+and the small chains on the host side: d(g1,g0) = (S2,S1) -> BatchNorm weight/bias, gamma/beta MLP, fixed style,
+and -- through the leaves sum(x), sum(x^2) of the batch statistics -- the a[c] + k[c]*x term of dL/dx
+(SyncBatchNorm: those two leaf gradients are SUM-all-reduced, like the statistics themselves).
+
+Only const-style half-blocks (per-sample gamma/beta; 12 of 18 in the shipped 'mixed'/'isolated' curricula)
+have backward kernels so far; pixel-style half-blocks raise.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .. import abi
+from .synthesis_ops import STAT_STRIDE, all_reduce_stats, is_pixel_style, _spade
+
+C = 256
+
+
+def _sn_weight(P, name, training, eps=1e-12):
+    """W / sigma with torch.nn.utils.spectral_norm semantics: power iteration without autograd (buffers updated
+    in place when training), sigma = u^T W v differentiable w.r.t. W only."""
+    w = P[name + "weight_orig"].reshape(C, C)
+    u, v = P[name + "weight_u"], P[name + "weight_v"]
+    with torch.no_grad():
+        if training:
+            v.copy_(F.normalize(torch.mv(w.t(), u), dim=0, eps=eps))
+            u.copy_(F.normalize(torch.mv(w, v), dim=0, eps=eps))
+    sigma = torch.dot(u.detach().clone(), torch.mv(w, v.detach().clone()))
+    return w / sigma
+
+
+class SynthesisTape:
+    """Everything `synthesis_backward` needs from one training forward."""
+
+    def __init__(self):
+        self.halves = []      # per half-block: dict(x, x_bstride, mod, w_sn, ssum, ssq, conv, skip_from, rgb_w ...)
+        self.cfg = None
+        self.B = 0
+        self.rgb = None
+
+
+def synthesis_forward_train(params, feat_lr, fixed_style, cfg, *, passes=3, prefix="synthesis_network.",
+                            input_prefix="synthesis_input.", process_group=None):
+    """-> (rgb [B,3,Hg,Wg] (no autograd history), tape).  `params`: name -> tensor (Parameters keep their .grad)."""
+    abi.require_device()
+    P = params
+    dev = fixed_style.device
+    B = fixed_style.shape[0]
+    Hg, Wg = cfg["gen_height"], cfg["gen_width"]
+    if cfg["hidden_dim"] != C or cfg["feature_dim"] != C:
+        raise RuntimeError("hg3d: the sm_100a synthesis kernels are built for hidden_dim == feature_dim == 256")
+    HW = Hg * Wg
+    T = (HW + 127) // 128
+    nb = cfg["synthesis_blocks"]
+    halves = [(k, j) for k in range(nb) for j in range(2)]
+    if any(is_pixel_style(cfg, k) for k, _ in halves):
+        raise RuntimeError("hg3d: backward of pixel-style SPADE half-blocks (mod_blocks) is not built yet")
+    world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+    f32 = dict(dtype=torch.float32, device=dev)
+    blk = lambda k: f"{prefix}network.m3d_{k}."
+    sp = lambda k, j: blk(k) + f"spade_{j}."
+    fs = fixed_style.detach().reshape(B, C).float().requires_grad_(True)     # leaf: its .grad is returned by backward
+
+    tape = SynthesisTape()
+    tape.cfg, tape.B, tape.fixed_style = cfg, B, fs
+    tape.process_group, tape.world = process_group, world
+
+    # ---- per-sample (1+gamma, beta) of every half-block, with autograd history (tiny)
+    GB = {}
+    for k, j in halves:
+        s = sp(k, j)
+        actv = torch.relu(F.linear(fs, P[s + "mlp_shared.0.weight"].reshape(128, C), P[s + "mlp_shared.0.bias"]))
+        G = 1.0 + F.linear(actv, P[s + "mlp_gamma.weight"].reshape(C, 128), P[s + "mlp_gamma.bias"])
+        Bt = F.linear(actv, P[s + "mlp_beta.weight"].reshape(C, 128), P[s + "mlp_beta.bias"])
+        GB[(k, j)] = (G, Bt)
+
+    # ---- synthesis input (shared by the batch) + its statistics
+    stats = torch.zeros(len(halves) + 1, STAT_STRIDE, dtype=torch.float64, device=dev)
+    stats[:, 512] = float(B * HW)
+    ic = torch.linspace(-1, 1, Hg, **f32)
+    jc = torch.linspace(-1, 1, Wg, **f32)
+    x0 = torch.empty(T, C, 128, **f32)
+    w_in = P[input_prefix + "network.0.weight"].detach().reshape(C, 2).contiguous()
+    abi.synth_input(w_in, P[input_prefix + "network.0.bias"].detach(), ic, jc, x0, stats[0], B)
+    tape.input = dict(w=w_in, ic=ic, jc=jc, prefix=input_prefix)
+
+    rgb_cur = None
+    cur, cur_bstride = x0, 0
+    block_in = None
+    for idx, (k, j) in enumerate(halves):
+        bn = sp(k, j) + "first_norm."
+        srow = stats[idx]
+        if world > 1:
+            all_reduce_stats(srow, process_group)
+        count = float(B * HW * world)
+        # leaves of the batch statistics: their gradients are the a[c], k[c] of dL/dx
+        ssum = srow[:C].clone().requires_grad_(True)
+        ssq = srow[C:2 * C].clone().requires_grad_(True)
+        mean = ssum / count
+        var = (ssq / count - mean * mean).clamp_min(0.0)
+        rstd = torch.rsqrt(var + 1e-5)
+        sc = P[bn + "weight"].double() * rstd
+        sh = P[bn + "bias"].double() - mean * sc
+        G, Bt = GB[(k, j)]
+        mod = torch.stack([sc[None, :] * G.double(), sh[None, :] * G.double() + Bt.double()], dim=1).float()   # [B,2,C]
+        with torch.no_grad():       # running statistics (momentum 0.1, unbiased variance), map3d_layers.py:162
+            P[bn + "running_mean"].mul_(0.9).add_(0.1 * mean.float())
+            P[bn + "running_var"].mul_(0.9).add_(0.1 * (var * count / max(count - 1, 1)).float())
+            if (bn + "num_batches_tracked") in P:
+                P[bn + "num_batches_tracked"] += 1
+        conv = blk(k) + f"conv_{j}."
+        w_sn = _sn_weight(P, conv, True)
+        wimg = abi.pack_weight(w_sn.detach().contiguous(), Nb=256)[0]
+        if j == 0:
+            block_in = (cur, cur_bstride, idx)
+        out = torch.empty(B, T, C, 128, **f32)
+        last_half = j == 1
+        use_skip = last_half and k >= nb // 2 and block_in[1] != 0
+        use_rgb = last_half and k >= nb // 2 - 1
+        kw = {}
+        rgb_name = None
+        if use_rgb:
+            rgb_name = f"{prefix}to_rgbs.m3d_{k}.linear."
+            rgb_next = torch.empty(B, 3, HW, **f32)
+            kw = dict(rgb_w=P[rgb_name + "weight"].detach().reshape(3, C).contiguous(), rgb_b=P[rgb_name + "bias"].detach(),
+                      rgb_in=rgb_cur, rgb_out=rgb_next)
+        mod_d = mod.detach().contiguous()
+        _spade(cur, cur_bstride, wimg, P[conv + "bias"].detach(), out, B, Hg, Wg, passes, mod=mod_d,
+               skip=block_in[0] if use_skip else None, stats=stats[idx + 1], **kw)
+        if use_rgb:
+            rgb_cur = rgb_next
+        tape.halves.append(dict(x=cur, x_bstride=cur_bstride, mod=mod, mod_d=mod_d, w_sn=w_sn, ssum=ssum, ssq=ssq, conv=conv,
+                                skip_from=block_in[2] if use_skip else None, rgb=rgb_name, out=out))
+        cur, cur_bstride = out, T * C * 128
+    tape.rgb = rgb_cur.reshape(B, 3, Hg, Wg)
+    return tape.rgb, tape
+
+
+def synthesis_backward(params, tape, drgb, *, passes=3):
+    """Accumulates `.grad` of every synthesis parameter in `params` (those that require grad) and returns
+    d(fixed_style) [B,256]."""
+    P = params
+    cfg, B = tape.cfg, tape.B
+    Hg, Wg = cfg["gen_height"], cfg["gen_width"]
+    HW = Hg * Wg
+    T = (HW + 127) // 128
+    dev = drgb.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    drgb = drgb.reshape(B, 3, HW).float().contiguous()
+    H = tape.halves
+    n = len(H)
+    full = T * C * 128
+
+    def acc(p, g):
+        if p.requires_grad:
+            p.grad = g.to(p.dtype).reshape(p.shape) if p.grad is None else p.grad + g.to(p.dtype).reshape(p.shape)
+
+    # every ToRGB bias sees the full drgb
+    drgb_sum = drgb.sum((0, 2))
+    small_out, small_grad = [], []          # (tensor with autograd history, its gradient): one autograd.backward at the end
+    dout = {}                               # half index -> dL/d(out of that half)   (only the live ones are kept)
+    nxt = None                              # (dpre, g1 table [B,2,C], ak [2,C]) of half h+1
+    for h in range(n - 1, -1, -1):
+        rec = H[h]
+        # ---- dL/d(out_h): from half h+1 (dpre*g1 + a + k*x), the skip of the block two halves later, ToRGB
+        dskip = None
+        if h + 2 < n and H[h + 2]["skip_from"] == h + 1:      # out_h is the input of a block with a residual skip
+            dskip = dout[h + 2]
+        d = torch.empty(B, T, C, 128, **f32)
+        dwrgb = None
+        kw = {}
+        if rec["rgb"] is not None:
+            dwrgb = torch.zeros(3, C, dtype=torch.float64, device=dev)
+            kw = dict(drgb=drgb, rgb_w=P[rec["rgb"] + "weight"].detach().reshape(3, C).contiguous(), dwrgb=dwrgb)
+        if nxt is not None:
+            kw.update(dpre=nxt[0], g1=nxt[1], ak=nxt[2])
+        abi.spade_bwd_combine(d, B=B, Hg=Hg, Wg=Wg, x=rec["out"], x_bstride=full, dskip=dskip, **kw)
+        if dwrgb is not None:
+            acc(P[rec["rgb"] + "weight"], dwrgb.float())
+            acc(P[rec["rgb"] + "bias"], drgb_sum)
+        dout[h] = d
+        dout.pop(h + 3, None)
+        # ---- this half-block
+        wimg_t = abi.pack_weight(rec["w_sn"].detach().t().contiguous(), Nb=256)[0]
+        dpre = torch.empty(B, T, C, 128, **f32)
+        sums = torch.zeros(B, 2, C, dtype=torch.float64, device=dev)
+        abi.spade_bwd_dgrad(d, rec["x"], rec["x_bstride"], rec["mod_d"], wimg_t, dpre, sums, B=B, Hg=Hg, Wg=Wg, passes=passes)
+        dw, db = abi.spade_bwd_wgrad(d, rec["x"], rec["x_bstride"], rec["mod_d"], B=B, Hg=Hg, Wg=Wg, passes=passes)
+        acc(P[rec["conv"] + "bias"], db)
+        small_out.append(rec["w_sn"])
+        small_grad.append(dw)
+        dmod = torch.stack([sums[:, 1], sums[:, 0]], dim=1).float()           # d g1 = sum dpre*x, d g0 = sum dpre
+        ga, gk = torch.autograd.grad(rec["mod"], [rec["ssum"], rec["ssq"]], grad_outputs=dmod, retain_graph=True)
+        ak = torch.stack([ga, gk])
+        if tape.world > 1:          # every rank's loss depends on the global statistics
+            dist.all_reduce(ak, group=tape.process_group)
+        ak = torch.stack([ak[0], 2.0 * ak[1]]).float().contiguous()      # d(sum x)/dx = 1, d(sum x^2)/dx = 2x
+        small_out.append(rec["mod"])
+        small_grad.append(dmod)
+        nxt = (dpre, rec["mod_d"], ak)
+    # ---- gradient w.r.t. the shared synthesis input x0, then its two parameters
+    dx0 = torch.empty(B, T, C, 128, **f32)
+    abi.spade_bwd_combine(dx0, B=B, Hg=Hg, Wg=Wg, x=H[0]["x"], x_bstride=0, dpre=nxt[0], g1=nxt[1], ak=nxt[2])
+    ip = tape.input["prefix"]
+    dw_in, db_in = abi.synth_input_bwd(dx0, tape.input["w"], P[ip + "network.0.bias"].detach(), tape.input["ic"], tape.input["jc"], B)
+    acc(P[ip + "network.0.weight"], dw_in)
+    acc(P[ip + "network.0.bias"], db_in)
+    # ---- all [C]- and [B,C]-sized chains in one autograd pass (accumulates into the Parameters' .grad)
+    fs = tape.fixed_style
+    leaves = [t for t in small_out if t.requires_grad]
+    grads = [g for t, g in zip(small_out, small_grad) if t.requires_grad]
+    inputs = [p for p in P.values() if isinstance(p, torch.Tensor) and p.requires_grad and p.is_leaf] + [fs]
+    torch.autograd.backward(leaves, grads, inputs=inputs)
+    return fs.grad

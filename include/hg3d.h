@@ -136,6 +136,9 @@ int hg_spade_bwd_dgrad(const float* dout, const float* x, long x_bstride, const 
 size_t hg_spade_bwd_wgrad_workspace_bytes(void);
 int hg_spade_bwd_wgrad(const float* dout, const float* x, long x_bstride, const float* mod, float* dw, float* dbias,
                        void* workspace, int B, int C, int Hg, int Wg, int passes, void* stream);
+/* Backward of hg_synth_input: dx [B,T,C,128] (gradient w.r.t. the batch-shared x0, per sample) -> dw [C,2], db [C]. */
+int hg_synth_input_bwd(const float* dx, const float* w, const float* bias, const float* ic, const float* jc, int B, int C,
+                       int Hg, int Wg, float* dw, float* db, void* stream);
 int hg_spade_bwd_combine(const float* dpre, const float* x, long x_bstride, const float* g1, const float* ak,
                          const float* dskip, const float* drgb, const float* rgb_w, float* dx, double* dwrgb, int B,
                          int C, int Hg, int Wg, void* stream);

@@ -264,8 +264,9 @@ def spectral_weight(w_orig, u, v, training, eps=1e-12):
     Returns (W / sigma, u', v')."""
     wm = w_orig.reshape(w_orig.shape[0], -1)
     if training:
-        v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps)
-        u = F.normalize(torch.mv(wm, v), dim=0, eps=eps)
+        with torch.no_grad():      # the power iteration is not differentiated (spectral_norm.py: `with torch.no_grad()`)
+            v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps)
+            u = F.normalize(torch.mv(wm, v), dim=0, eps=eps)
     sigma = torch.dot(u, torch.mv(wm, v))
     return w_orig / sigma, u, v
 
