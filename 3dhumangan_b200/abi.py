@@ -39,6 +39,13 @@ SIGNATURES = {
     "hg_spade_bwd_wgrad_workspace_bytes": (c_size_t, []),
     "hg_spade_bwd_wgrad": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "hg_spade_bwd_combine": (c_int, [c_void_p, c_void_p, c_long] + [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
+    "hg_conv1x1_blocked": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "hg_conv1x1_blocked_bwd": (c_int, [c_void_p] * 7 + [c_int, c_float, c_int] + [c_int] * 4 + [c_void_p]),
+    "hg_wgrad_blocked": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "hg_spade_a1": (c_int, [c_void_p, c_long, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "hg_spade_pixel_pre": (c_int, [c_void_p, c_long, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "hg_spade_pixel_mod_bwd": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "hg_bilinear_adjoint": (c_int, [c_void_p, c_void_p, c_long] + [c_int] * 5 + [c_void_p]),
     "hg_synth_input_bwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p]),
     "hg_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_bias_act_grad": (c_int, [c_void_p] * 6 + [c_long, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
@@ -226,18 +233,55 @@ def spade_bwd_dgrad(dout, x, x_bstride, mod, wimg_t, dpre, sums, *, B, Hg, Wg, p
 _WGRAD_WS = {}
 
 
-def spade_bwd_wgrad(dout, x, x_bstride, mod, *, B, Hg, Wg, passes=3, want_bias=True):
-    """dW [C,C] = sum dout (x) lrelu(x*g1+g0), dbias [C] = sum dout  (csrc/synth_bwd.cu)."""
+def spade_bwd_wgrad(dout, x, x_bstride, mod, *, B, Hg, Wg, passes=3, want_bias=True, Cx=256):
+    """dW [C,Cx] = sum dout (x) lrelu(x*g1+g0), dbias [C] = sum dout  (csrc/synth_bwd.cu); mod None: y = lrelu(x)."""
     dev = dout.device
     ws = _WGRAD_WS.get(dev)
     if ws is None:
         ws = _WGRAD_WS[dev] = torch.empty(int(lib().hg_spade_bwd_wgrad_workspace_bytes()) // 4, dtype=torch.float32, device=dev)
-    dw = torch.empty(256, 256, dtype=torch.float32, device=dev)
+    dw = torch.empty(256, Cx, dtype=torch.float32, device=dev)
     db = torch.empty(256, dtype=torch.float32, device=dev) if want_bias else None
     with torch.cuda.device_of(dout):
-        call("hg_spade_bwd_wgrad", ptr(dout), ptr(x), int(x_bstride), ptr(mod), ptr(dw), ptr(db), ptr(ws), B, 256, Hg, Wg,
+        call("hg_wgrad_blocked", ptr(dout), ptr(x), int(x_bstride), Cx, ptr(mod), ptr(dw), ptr(db), ptr(ws), B, 256, Hg, Wg,
              passes, stream())
     return dw, db
+
+
+def conv1x1_blocked(x, Cin, wimg, bias, out, *, B, Hg, Wg, passes=3):
+    with torch.cuda.device_of(x):
+        call("hg_conv1x1_blocked", ptr(x), Cin, ptr(wimg), ptr(bias), ptr(out), B, Hg, Wg, passes, stream())
+    return out
+
+
+def conv1x1_blocked_bwd(g, aux, wimg_t, out, sums, *, B, Hg, Wg, g2=None, mod=None, Cout=256, slope=0.2, pixel_major=False,
+                        passes=3):
+    with torch.cuda.device_of(g):
+        call("hg_conv1x1_blocked_bwd", ptr(g), ptr(g2), ptr(aux), ptr(mod), ptr(wimg_t), ptr(out), ptr(sums), Cout,
+             float(slope), int(bool(pixel_major)), B, Hg, Wg, passes, stream())
+    return out
+
+
+def spade_a1(p_lr, p_stride, p_bias, a1, *, B, Hg, Wg, Rh, Rw):
+    with torch.cuda.device_of(a1):
+        call("hg_spade_a1", ptr(p_lr), int(p_stride), ptr(p_bias), ptr(a1), B, Hg, Wg, Rh, Rw, stream())
+    return a1
+
+
+def spade_pixel_pre(x, x_bstride, scsh, gam, bet_pre, *, B, Hg, Wg):
+    with torch.cuda.device_of(gam):
+        call("hg_spade_pixel_pre", ptr(x), int(x_bstride), ptr(scsh), ptr(gam), ptr(bet_pre), B, 256, Hg, Wg, stream())
+    return bet_pre
+
+
+def spade_pixel_mod_bwd(dpre, x, x_bstride, scsh, gam_dgam, dxn, sums, *, B, Hg, Wg):
+    with torch.cuda.device_of(dpre):
+        call("hg_spade_pixel_mod_bwd", ptr(dpre), ptr(x), int(x_bstride), ptr(scsh), ptr(gam_dgam), ptr(dxn), ptr(sums), B, 256,
+             Hg, Wg, stream())
+
+
+def bilinear_adjoint(da1, dp, dp_stride, *, B, Hg, Wg, Rh, Rw):
+    with torch.cuda.device_of(da1):
+        call("hg_bilinear_adjoint", ptr(da1), ptr(dp), int(dp_stride), B, Hg, Wg, Rh, Rw, stream())
 
 
 def spade_bwd_combine(dx, *, B, Hg, Wg, dpre=None, x=None, x_bstride=0, g1=None, ak=None, dskip=None, drgb=None, rgb_w=None,

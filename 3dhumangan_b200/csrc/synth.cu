@@ -73,6 +73,13 @@ struct SpadeArgs {
   const float* rgb_in;   // [B,3,HW] or null
   float* rgb_out;        // [B,3,HW]
   int B, HW, Hg, Wg, Rh, Rw;
+  // generalisations used by the backward schedule (defaults reproduce the forward half-block):
+  int nkc;               // K chunks of 64 input channels per tile: 2, 4 or 8
+  int xC;                // channels per source tile (128 or 256); chunks beyond xC/64 come from x2
+  const float* x2;       // second source [B,T,xC,128] (K = 512 products) or null
+  float slope;           // operand LeakyReLU slope (1 = identity); backward epilogue: slope of the mask (0.2 / 0 = ReLU)
+  int cout;              // output channels written by the epilogue: 256 or 128 (the MMA always runs N = 256)
+  int out_pm;            // backward epilogue: write pixel-major [B,HW,cout] instead of tile-blocked
 };
 
 struct SynSmem {
@@ -242,8 +249,11 @@ __device__ __forceinline__ void x_producer_loop(const SpadeArgs& a, const SynSme
   for (int it = 0; it < tm.count; ++it) {
     int b, ti;
     tm.get(it, b, ti);
-    const float* base = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * kC * 128;
-    for (int j = 0; j < 8; ++j) ring_emit(m, g, 0, kXs, base + j * 32 * 128);
+    const int per_src = a.xC / 32;                 // 32-channel slices per source tile
+    const float* base = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * a.xC * 128;
+    const float* base2 = a.x2 ? a.x2 + (static_cast<long>(b) * tm.T + ti) * a.xC * 128 : nullptr;
+    for (int j = 0; j < 2 * a.nkc; ++j)
+      ring_emit(m, g, 0, kXs, (j < per_src ? base : base2 - per_src * 32 * 128) + j * 32 * 128);
   }
 }
 __device__ __forceinline__ void skip_producer_loop(const SpadeArgs& a, const SynSmem& m, const TileMap& tm) {
@@ -252,8 +262,8 @@ __device__ __forceinline__ void skip_producer_loop(const SpadeArgs& a, const Syn
   for (int it = 0; it < tm.count; ++it) {
     int b, ti;
     tm.get(it, b, ti);
-    const float* base = a.skip + static_cast<long>(b) * a.skip_bstride + static_cast<long>(ti) * kC * 128;
-    for (int j = 0; j < 8; ++j) ring_emit(m, g, kXs, kSs, base + j * 32 * 128);
+    const float* base = a.skip + static_cast<long>(b) * a.skip_bstride + static_cast<long>(ti) * a.cout * 128;
+    for (int j = 0; j < a.cout / 32; ++j) ring_emit(m, g, kXs, kSs, base + j * 32 * 128);
   }
 }
 
@@ -292,12 +302,13 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
     const uint32_t buf = it & 1;
     const int pix = ti * 128 + row;
     const bool valid = pix < a.HW;
-    const long plane = (static_cast<long>(b) * tm.T + ti) * kC * 128 + row;
+    const long plane = (static_cast<long>(b) * tm.T + ti) * a.cout * 128 + row;
     mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
     tc_fence_after();
     float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    const int ncg = a.cout >> 5;
 #pragma unroll 1
-    for (int cg = 0; cg < 8; ++cg) {
+    for (int cg = 0; cg < ncg; ++cg) {
       const int c0 = cg * 32;
       uint32_t raw[32];
       tmem_ld32(tmem + buf * 256 + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
@@ -405,22 +416,24 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
   uint32_t sg = 0;
   int cur_b = -1;
   auto flush = [&](int b) {
-    for (int c = et; c < kC; c += 128) {
-      atomicAdd(a.stats + (static_cast<long>(b) * 2 + 0) * kC + c, static_cast<double>(m.st_sum[c]));
-      atomicAdd(a.stats + (static_cast<long>(b) * 2 + 1) * kC + c, static_cast<double>(m.st_sq[c]));
+    for (int c = et; c < a.cout; c += 128) {
+      atomicAdd(a.stats + (static_cast<long>(b) * 2 + 0) * a.cout + c, static_cast<double>(m.st_sum[c]));
+      atomicAdd(a.stats + (static_cast<long>(b) * 2 + 1) * a.cout + c, static_cast<double>(m.st_sq[c]));
       m.st_sum[c] = 0.f;
       m.st_sq[c] = 0.f;
     }
   };
+  const float mslope = a.slope;
+  const int ncg = a.cout >> 5;
   for (int it = 0; it < tm.count; ++it) {
     int b, ti;
     tm.get(it, b, ti);
     if (b != cur_b) {   // per-sample tables and per-sample sums
       asm volatile("bar.sync 2, 128;" ::: "memory");
       if (cur_b >= 0) flush(cur_b);
-      for (int c = et; c < kC; c += 128) {
-        m.tab_g1[c] = a.mod[(static_cast<long>(b) * 2 + 0) * kC + c];
-        m.tab_g0[c] = a.mod[(static_cast<long>(b) * 2 + 1) * kC + c];
+      for (int c = et; c < a.cout; c += 128) {
+        m.tab_g1[c] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 0) * a.cout + c] : 1.f;
+        m.tab_g0[c] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 1) * a.cout + c] : 0.f;
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
       cur_b = b;
@@ -430,11 +443,12 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
     opaque(tg0);
     const uint32_t buf = it & 1;
     const bool valid = ti * 128 + row < a.HW;
-    const long plane = (static_cast<long>(b) * tm.T + ti) * kC * 128 + row;
+    const long plane = a.out_pm ? (static_cast<long>(b) * a.HW + ti * 128 + row) * a.cout
+                                : (static_cast<long>(b) * tm.T + ti) * a.cout * 128 + row;
     mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
     tc_fence_after();
 #pragma unroll 1
-    for (int cg = 0; cg < 8; ++cg) {
+    for (int cg = 0; cg < ncg; ++cg) {
       const int c0 = cg * 32;
       uint32_t raw[32];
       tmem_ld32(tmem + buf * 256 + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
@@ -460,11 +474,16 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
         for (int jj = 0; jj < 8; ++jj) {
           const int j = g * 8 + jj;
           const float pre = fmaf(xs_[j], t1[jj], t0[jj]);
-          const float d = __uint_as_float(raw[j]) * (pre > 0.f ? 1.f : 0.2f);
-          if (valid) a.out[plane + (c0 + j) * 128] = d;
+          const float d = __uint_as_float(raw[j]) * (pre > 0.f ? 1.f : mslope);
+          if (valid && !a.out_pm) a.out[plane + (c0 + j) * 128] = d;
           v[j] = valid ? d : 0.f;
           w[j] = v[j] * xs_[j];
         }
+      }
+      if (valid && a.out_pm) {
+        float4* o = reinterpret_cast<float4*>(a.out + plane + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
       const float s1 = transpose_reduce32(v, lane);
       const float s2 = transpose_reduce32(w, lane);
@@ -508,9 +527,9 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
       tm.get(it, b, ti);
       if (!kBwd && b != cur_b) {  // refresh the per-sample modulation table
         rows_barrier();
-        for (int i = threadIdx.x; i < kC; i += 256) {
-          m.tab_g1[i] = a.mod[(static_cast<long>(b) * 2 + 0) * kC + i];
-          m.tab_g0[i] = a.mod[(static_cast<long>(b) * 2 + 1) * kC + i];
+        for (int i = threadIdx.x; i < kC; i += 256) {   // no table = identity (plain 1x1 convolution)
+          m.tab_g1[i] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 0) * kC + i] : 1.f;
+          m.tab_g0[i] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 1) * kC + i] : 0.f;
         }
         rows_barrier();
         cur_b = b;
@@ -519,9 +538,10 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
       uint32_t tg1 = smem_u32(m.tab_g1), tg0 = smem_u32(m.tab_g0);
       opaque(tg1);   // the tables may just have been refreshed: no table load may move above this point
       opaque(tg0);
+      const float slope = a.slope;
 #pragma unroll 1
-      for (int kc = 0; kc < 4; ++kc, ++acnt) {
-        const int c0 = kc * 64 + h * 32;
+      for (int kc = 0; kc < a.nkc; ++kc, ++acnt) {
+        const int c0 = (kc * 64 + h * 32) & (kC - 1);
         float cur[32];
         take_x_pair(m, xg, h, row, lane, cur);
         const uint32_t slot = acnt & 1;
@@ -534,7 +554,10 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
             lds8(tg0 + (c0 + g * 8) * 4, t0);
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = kBwd ? cur[g * 8 + j] : lrelu02(fmaf(cur[g * 8 + j], t1[j], t0[j]));
+          for (int j = 0; j < 8; ++j) {
+            const float v = fmaf(cur[g * 8 + j], t1[j], t0[j]);
+            y[j] = kBwd ? cur[g * 8 + j] : (v > 0.f ? v : slope * v);
+          }
           if (!valid) {   // only the last, partial tile of an image
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = 0.f;
@@ -558,7 +581,7 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
         const uint32_t buf = it & 1;
         mbar_wait_sleep(m.bars + ACC_EMPTY + buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int kc = 0; kc < 4; ++kc, ++acnt) {
+        for (int kc = 0; kc < a.nkc; ++kc, ++acnt) {
           const uint32_t slot = acnt & 1;
           mbar_wait_sleep(m.bars + A_FULL + slot, (acnt >> 1) & 1);
           tc_fence_after();
@@ -572,7 +595,7 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
   } else if (warp == 13) {
     if (lane == 0) {
       const uint8_t* imgs[1] = {a.wimg};
-      const int ns[1] = {8};
+      const int ns[1] = {2 * a.nkc};
       weight_producer_loop<kPasses>(m, imgs, ns, 1, tm.count);
     }
   } else if (warp == 14) {
@@ -876,6 +899,7 @@ int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float*
                   static_cast<const uint8_t*>(wimg), bias, skip,
                   static_cast<long>((Hg * Wg + 127) / 128) * hg::kC * 128, out, stats, rgb_w, rgb_b, rgb_in, rgb_out,
                   B, Hg * Wg, Hg, Wg, Rh, Rw};
+  a.nkc = 4; a.xC = hg::kC; a.x2 = nullptr; a.slope = 0.2f; a.cout = hg::kC; a.out_pm = 0;
   const int tiles = B * ((Hg * Wg + 127) / 128);
   const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
   auto st = static_cast<cudaStream_t>(stream);
@@ -892,6 +916,25 @@ int hg_spade_conv(const float* x, long x_bstride, const float* mod, const float*
   }
 #undef HG_LAUNCH
   return hg::check_launch("hg_spade_conv");
+}
+
+static int launch_blocked_gemm(const hg::SpadeArgs& a, int passes, bool bwd, cudaStream_t st, const char* who) {
+  const int tiles = a.B * ((a.HW + 127) / 128);
+  const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
+  cudaError_t e;
+#define HG_LAUNCH_G(KERNEL)                                                                             \
+  do {                                                                                                  \
+    e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kSynSmemBytes);   \
+    if (e == cudaSuccess) KERNEL<<<grid, hg::kSynThreads, hg::kSynSmemBytes, st>>>(a);                   \
+  } while (0)
+  if (bwd) {
+    if (passes == 3) HG_LAUNCH_G((hg::spade_const_kernel<3, true>)); else HG_LAUNCH_G((hg::spade_const_kernel<1, true>));
+  } else {
+    if (passes == 3) HG_LAUNCH_G((hg::spade_const_kernel<3, false>)); else HG_LAUNCH_G((hg::spade_const_kernel<1, false>));
+  }
+#undef HG_LAUNCH_G
+  if (e != cudaSuccess) { hg::set_error("%s: smem opt-in failed: %s", who, cudaGetErrorString(e)); return 2; }
+  return hg::check_launch(who);
 }
 
 int hg_spade_bwd_dgrad(const float* dout, const float* x, long x_bstride, const float* mod, const void* wimg_t, float* dpre,
@@ -912,18 +955,52 @@ int hg_spade_bwd_dgrad(const float* dout, const float* x, long x_bstride, const 
   a.out = dpre;
   a.stats = sums;
   a.B = B; a.HW = Hg * Wg; a.Hg = Hg; a.Wg = Wg;
-  const int tiles = B * static_cast<int>(T);
-  const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
-  auto st = static_cast<cudaStream_t>(stream);
-#define HG_LAUNCH_BWD(KERNEL)                                                                                     \
-  do {                                                                                                            \
-    cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kSynSmemBytes); \
-    if (e != cudaSuccess) { hg::set_error("hg_spade_bwd_dgrad: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; } \
-    KERNEL<<<grid, hg::kSynThreads, hg::kSynSmemBytes, st>>>(a);                                                  \
-  } while (0)
-  if (passes == 3) HG_LAUNCH_BWD((hg::spade_const_kernel<3, true>)); else HG_LAUNCH_BWD((hg::spade_const_kernel<1, true>));
-#undef HG_LAUNCH_BWD
-  return hg::check_launch("hg_spade_bwd_dgrad");
+  a.nkc = 4; a.xC = hg::kC; a.slope = 0.2f; a.cout = hg::kC;
+  return launch_blocked_gemm(a, passes, true, static_cast<cudaStream_t>(stream), "hg_spade_bwd_dgrad");
+}
+
+int hg_conv1x1_blocked(const float* x, int Cin, const void* wimg, const float* bias, float* out, int B, int Hg, int Wg,
+                       int passes, void* stream) {
+  HG_REQUIRE(x && wimg && bias && out, "hg_conv1x1_blocked: null pointer");
+  HG_REQUIRE(Cin == 128 || Cin == 256, "hg_conv1x1_blocked: Cin must be 128 or 256 (got %d)", Cin);
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_conv1x1_blocked: passes must be 1 or 3");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_conv1x1_blocked: bad shape");
+  const long T = (Hg * Wg + 127) / 128;
+  hg::SpadeArgs a{};
+  a.x = x;
+  a.x_bstride = T * Cin * 128;
+  a.wimg = static_cast<const uint8_t*>(wimg);
+  a.bias = bias;
+  a.skip_bstride = T * hg::kC * 128;
+  a.out = out;
+  a.B = B; a.HW = Hg * Wg; a.Hg = Hg; a.Wg = Wg;
+  a.nkc = Cin / 64; a.xC = Cin; a.slope = 1.f; a.cout = hg::kC;
+  return launch_blocked_gemm(a, passes, false, static_cast<cudaStream_t>(stream), "hg_conv1x1_blocked");
+}
+
+int hg_conv1x1_blocked_bwd(const float* g, const float* g2, const float* aux, const float* mod, const void* wimg_t,
+                           float* out, double* sums, int Cout, float slope, int pixel_major, int B, int Hg, int Wg,
+                           int passes, void* stream) {
+  HG_REQUIRE(g && aux && wimg_t && out && sums, "hg_conv1x1_blocked_bwd: null pointer");
+  HG_REQUIRE(Cout == 128 || Cout == 256, "hg_conv1x1_blocked_bwd: Cout must be 128 or 256 (got %d)", Cout);
+  HG_REQUIRE(!pixel_major || Cout == 128, "hg_conv1x1_blocked_bwd: the pixel-major output is built for Cout == 128");
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_conv1x1_blocked_bwd: passes must be 1 or 3");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_conv1x1_blocked_bwd: bad shape");
+  const long T = (Hg * Wg + 127) / 128;
+  hg::SpadeArgs a{};
+  a.x = g;
+  a.x_bstride = T * hg::kC * 128;
+  a.x2 = g2;
+  a.mod = mod;
+  a.wimg = static_cast<const uint8_t*>(wimg_t);
+  a.bias = static_cast<const float*>(wimg_t);   // unused by the backward epilogue; init_common reads C floats
+  a.skip = aux;
+  a.skip_bstride = T * Cout * 128;
+  a.out = out;
+  a.stats = sums;
+  a.B = B; a.HW = Hg * Wg; a.Hg = Hg; a.Wg = Wg;
+  a.nkc = g2 ? 8 : 4; a.xC = hg::kC; a.slope = slope; a.cout = Cout; a.out_pm = pixel_major;
+  return launch_blocked_gemm(a, passes, true, static_cast<cudaStream_t>(stream), "hg_conv1x1_blocked_bwd");
 }
 
 int hg_bn_finalize(const double* stats, double count, const double* count_dev, const float* weight, const float* bias, float* running_mean,

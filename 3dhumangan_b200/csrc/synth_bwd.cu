@@ -34,9 +34,10 @@ struct WgradArgs {
   const float* x;        // [B or 1,T,C,128]
   long x_bstride;
   const float* mod;      // [B,2,C] g1, g0
-  float* part_w;         // [grid, C, C]
+  float* part_w;         // [grid, C, nq]
   float* part_b;         // [grid, C]
   int B, HW;
+  int nq;                // rows (channels) of the second operand x: 256, or 128 (gamma/beta weight gradients)
 };
 
 enum { WG_FULL = 0, WG_EMPTY = 1, WG_DONE = 2 };
@@ -84,13 +85,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
       const int b = tile / T, ti = tile - b * T;
       if (b != cur_b) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        tab_g1[threadIdx.x] = a.mod[(static_cast<long>(b) * 2 + 0) * kWC + threadIdx.x];
-        tab_g0[threadIdx.x] = a.mod[(static_cast<long>(b) * 2 + 1) * kWC + threadIdx.x];
+        tab_g1[threadIdx.x] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 0) * kWC + threadIdx.x] : 1.f;   // no table: y = lrelu(x)
+        tab_g0[threadIdx.x] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 1) * kWC + threadIdx.x] : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_b = b;
       }
       const float* dbase = a.dout + (static_cast<long>(b) * T + ti) * kWC * 128;
-      const float* xbase = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * kWC * 128;
+      const float* xbase = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * a.nq * 128;
 #pragma unroll 1
       for (int kc = 0; kc < 2; ++kc, ++chunk) {
         const int p0 = kc * 64 + sub * 8;                 // first pixel (within the tile) of this thread's 8
@@ -116,14 +117,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
           store_a8<kPasses == 3>(a_hi, a_lo, st * 32 + rsub, sub * 8, y);
         }
         // ---- x rows -> y = lrelu(x*g1 + g0) -> B image
+        const int nst = a.nq >> 5;
 #pragma unroll
         for (int st = 0; st < 8; ++st) {
-          const float4* src = reinterpret_cast<const float4*>(xbase + (st * 32 + rsub) * 128 + p0);
-          va[2 * st] = __ldcs(src);
-          va[2 * st + 1] = __ldcs(src + 1);
+          if (st < nst) {
+            const float4* src = reinterpret_cast<const float4*>(xbase + (st * 32 + rsub) * 128 + p0);
+            va[2 * st] = __ldcs(src);
+            va[2 * st + 1] = __ldcs(src + 1);
+          }
         }
 #pragma unroll
         for (int st = 0; st < 8; ++st) {
+          if (st >= nst) break;
           const int row = st * 32 + rsub;
           const float g1 = tab_g1[row], g0 = tab_g0[row];
           float y[8] = {va[2 * st].x, va[2 * st].y, va[2 * st].z, va[2 * st].w,
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
       if (sub == 0) a.part_b[static_cast<long>(blockIdx.x) * kWC + st * 32 + rsub] = v;
     }
   } else if (lane == 0) {
-    const uint32_t idesc = umma_idesc_bf16(128, 256);
+    const uint32_t idesc = umma_idesc_bf16(128, a.nq);
     uint32_t chunk = 0;
     for (int it = 0; it < count; ++it)
       for (int kc = 0; kc < 2; ++kc, ++chunk) {
@@ -172,17 +177,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
   }
   // ---- drain: warps 0-3 own TMEM lanes 32w..32w+31 (co within the half), 2 x 256 columns (ci)
   if (warp < 4) {
-    float* dst = a.part_w + static_cast<long>(blockIdx.x) * kWC * kWC;
+    float* dst = a.part_w + static_cast<long>(blockIdx.x) * kWC * a.nq;
     if (count > 0) {
       mbar_wait_sleep(bars + WG_DONE, 0);
       tc_fence_after();
       for (int mh = 0; mh < 2; ++mh) {
         const int co = mh * 128 + warp * 32 + lane;
-        for (int cg = 0; cg < 8; ++cg) {
+        for (int cg = 0; cg < (a.nq >> 5); ++cg) {
           uint32_t raw[32];
           tmem_ld32(tmem + mh * 256 + (static_cast<uint32_t>(warp * 32) << 16) + cg * 32, raw);
           tmem_ld_wait();
-          float4* o = reinterpret_cast<float4*>(dst + static_cast<long>(co) * kWC + cg * 32);
+          float4* o = reinterpret_cast<float4*>(dst + static_cast<long>(co) * a.nq + cg * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             o[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
         }
       }
     } else {
-      for (int i = threadIdx.x; i < kWC * kWC; i += 128) dst[i] = 0.f;
+      for (int i = threadIdx.x; i < kWC * a.nq; i += 128) dst[i] = 0.f;
     }
   }
   if (count == 0 && warp >= 4 && warp < 8) {     // an idle CTA still owns a (zero) bias partial
@@ -203,11 +208,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
 
 // dW[i] = sum over CTAs of part[cta][i] (fp64 accumulation, fixed order -> deterministic), likewise the bias.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int nparts,
-                                    float* __restrict__ dw, float* __restrict__ db) {
+                                    int nw, float* __restrict__ dw, float* __restrict__ db) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < kWC * kWC) {
+  if (i < nw) {
     double acc = 0.0;
-    for (int p = 0; p < nparts; ++p) acc += static_cast<double>(part_w[static_cast<long>(p) * kWC * kWC + i]);
+    for (int p = 0; p < nparts; ++p) acc += static_cast<double>(part_w[static_cast<long>(p) * nw + i]);
     dw[i] = static_cast<float>(acc);
   }
   if (db && i < kWC) {
@@ -353,9 +358,174 @@ __global__ void __launch_bounds__(256) synth_input_bwd_kernel(const float* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Pixel-style half-blocks (gamma/beta per pixel).  Forward, per pixel p of sample b:
+//   A1 = relu(bilinear_up(P_lr)[p] + c[b])            [128]   (P_lr = W_shared . feature_maps at render resolution)
+//   gam = Wg A1 + bg + 1,  bet = Wb A1 + bb           [256]
+//   pre = (x*sc + sh)*gam + bet,  y = lrelu(pre),  out = W y + bias
+// The backward schedule (modules/synthesis_train.py) recomputes A1, gam, bet, pre with the kernels below + the
+// generic blocked 1x1 convolution, then re-uses the const-style dgrad / wgrad / combine kernels on `pre`.
+// ------------------------------------------------------------------------------------------
+// PyTorch's bilinear source index (align_corners=False): src = max(scale*(dst+0.5)-0.5, 0)
+__device__ __forceinline__ void bilin_src(int dst, int in_size, float scale, int& i0, int& i1, float& l0, float& l1) {
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+  l0 = 1.f - l1;
+}
+
+// A1 in the tile-blocked layout [B,T,128,128]; one block = one tile, one thread = one pixel.
+__global__ void __launch_bounds__(128) a1_gather_kernel(const float* __restrict__ p_lr, long p_stride,
+                                                        const float* __restrict__ p_bias, float* __restrict__ a1, int B,
+                                                        int Hg, int Wg, int Rh, int Rw) {
+  const int HW = Hg * Wg, T = (HW + 127) / 128;
+  const int tile = blockIdx.x, b = tile / T, ti = tile - b * T;
+  const int pix = ti * 128 + threadIdx.x;
+  const bool valid = pix < HW;
+  const int py = valid ? pix / Wg : 0, px = valid ? pix % Wg : 0;
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  bilin_src(py, Rh, static_cast<float>(Rh) / static_cast<float>(Hg), y0, y1, ly0, ly1);
+  bilin_src(px, Rw, static_cast<float>(Rw) / static_cast<float>(Wg), x0, x1, lx0, lx1);
+  const float* base = p_lr + static_cast<long>(b) * Rh * Rw * p_stride;
+  const float4* n00 = reinterpret_cast<const float4*>(base + (static_cast<long>(y0) * Rw + x0) * p_stride);
+  const float4* n01 = reinterpret_cast<const float4*>(base + (static_cast<long>(y0) * Rw + x1) * p_stride);
+  const float4* n10 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * Rw + x0) * p_stride);
+  const float4* n11 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * Rw + x1) * p_stride);
+  const float4* pb = p_bias ? reinterpret_cast<const float4*>(p_bias + static_cast<long>(b) * 128) : nullptr;
+  float* dst = a1 + static_cast<long>(tile) * 128 * 128 + threadIdx.x;
+#pragma unroll 4
+  for (int f4 = 0; f4 < 32; ++f4) {
+    const float4 v00 = __ldg(n00 + f4), v01 = __ldg(n01 + f4), v10 = __ldg(n10 + f4), v11 = __ldg(n11 + f4);
+    // same association as the forward kernel (csrc/synth.cu) and upsample_bilinear2d
+    float4 y;
+    y.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+    y.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+    y.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+    y.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+    if (pb) {
+      const float4 c4 = __ldg(pb + f4);
+      y.x += c4.x; y.y += c4.y; y.z += c4.z; y.w += c4.w;
+    }
+    dst[(f4 * 4 + 0) * 128] = valid ? fmaxf(y.x, 0.f) : 0.f;
+    dst[(f4 * 4 + 1) * 128] = valid ? fmaxf(y.y, 0.f) : 0.f;
+    dst[(f4 * 4 + 2) * 128] = valid ? fmaxf(y.z, 0.f) : 0.f;
+    dst[(f4 * 4 + 3) * 128] = valid ? fmaxf(y.w, 0.f) : 0.f;
+  }
+}
+
+// pre = (x*sc[c] + sh[c])*gam + bet, written over bet.  All tensors tile-blocked [B,T,C,128].
+__global__ void __launch_bounds__(256) pixel_pre_kernel(const float* __restrict__ x, long x_bstride, const float* __restrict__ scsh,
+                                                        const float* __restrict__ gam, float* __restrict__ bet_pre, int B,
+                                                        int T) {
+  const long per_b = static_cast<long>(T) * kWC * 32;     // float4 per sample
+  const long n4 = per_b * B;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>((i >> 5) & (kWC - 1));
+    const long b = i / per_b;
+    const float sc = scsh[c], sh = scsh[kWC + c];
+    const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + b * x_bstride) + (i - b * per_b));
+    const float4 g = __ldcs(reinterpret_cast<const float4*>(gam) + i);
+    float4 t = __ldcs(reinterpret_cast<const float4*>(bet_pre) + i);
+    t.x = fmaf(fmaf(xv.x, sc, sh), g.x, t.x);
+    t.y = fmaf(fmaf(xv.y, sc, sh), g.y, t.y);
+    t.z = fmaf(fmaf(xv.z, sc, sh), g.z, t.z);
+    t.w = fmaf(fmaf(xv.w, sc, sh), g.w, t.w);
+    __stcs(reinterpret_cast<float4*>(bet_pre) + i, t);
+  }
+}
+
+// dxn = dpre*gam (over `pre_dxn`), dgam = dpre*(x*sc+sh) (over `gam_dgam`); per-channel sums
+//   sums[0][c] = sum dxn*x, sums[1][c] = sum dxn, sums[2][c] = sum dgam     (fp64, accumulated)
+// Same mapping as the combine kernel: warp w owns channels w, w+8, ..., a lane owns 4 pixels of the tile.
+__global__ void __launch_bounds__(256) pixel_mod_bwd_kernel(const float* __restrict__ dpre, const float* __restrict__ x,
+                                                            long x_bstride, const float* __restrict__ scsh,
+                                                            float* __restrict__ gam_dgam, float* __restrict__ dxn,
+                                                            double* __restrict__ sums, int B, int T) {
+  __shared__ float s_acc[3 * kWC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 3 * kWC; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int total = B * T;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int b = tile / T, ti = tile - b * T;
+    const long off = static_cast<long>(tile) * kWC * 128 + lane * 4;
+    const long xoff = static_cast<long>(b) * x_bstride + static_cast<long>(ti) * kWC * 128 + lane * 4;
+#pragma unroll 4
+    for (int c = warp; c < kWC; c += 8) {
+      const float sc = scsh[c], sh = scsh[kWC + c];
+      const float4 d = __ldcs(reinterpret_cast<const float4*>(dpre + off + c * 128));
+      const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + xoff + c * 128));
+      const float4 g = __ldcs(reinterpret_cast<const float4*>(gam_dgam + off + c * 128));
+      const float4 dx = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      const float4 dg = make_float4(d.x * fmaf(xv.x, sc, sh), d.y * fmaf(xv.y, sc, sh), d.z * fmaf(xv.z, sc, sh),
+                                    d.w * fmaf(xv.w, sc, sh));
+      __stcs(reinterpret_cast<float4*>(dxn + off + c * 128), dx);
+      __stcs(reinterpret_cast<float4*>(gam_dgam + off + c * 128), dg);
+      float t0 = (dx.x * xv.x + dx.y * xv.y) + (dx.z * xv.z + dx.w * xv.w);
+      float t1 = (dx.x + dx.y) + (dx.z + dx.w);
+      float t2 = (dg.x + dg.y) + (dg.z + dg.w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+      }
+      if (lane == 0) {
+        s_acc[c] += t0;
+        s_acc[kWC + c] += t1;
+        s_acc[2 * kWC + c] += t2;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * kWC; i += blockDim.x) atomicAdd(sums + i, static_cast<double>(s_acc[i]));
+}
+
+// Adjoint of the bilinear up-sample: dP[b, s, :] = sum over the output pixels whose footprint contains texel s of
+// weight * dA1[b, p, :].  Gather form (deterministic, no atomics): one block per texel, one thread per channel;
+// the candidate pixels are enumerated from the inverse of the source-index formula and checked with the forward one.
+__global__ void __launch_bounds__(128) bilinear_adjoint_kernel(const float* __restrict__ da1 /* [B,HW,128] */,
+                                                               float* __restrict__ dp, long dp_stride, int B, int Hg,
+                                                               int Wg, int Rh, int Rw) {
+  const int s = blockIdx.x;                       // b*Rh*Rw + sy*Rw + sx
+  const int b = s / (Rh * Rw), r = s - b * Rh * Rw, sy = r / Rw, sx = r - sy * Rw;
+  const float ry = static_cast<float>(Rh) / static_cast<float>(Hg), rx = static_cast<float>(Rw) / static_cast<float>(Wg);
+  int ylo = static_cast<int>(floorf((static_cast<float>(sy) - 0.5f) / ry - 0.5f)) - 1;
+  int yhi = static_cast<int>(ceilf((static_cast<float>(sy) + 1.5f) / ry - 0.5f)) + 1;
+  int xlo = static_cast<int>(floorf((static_cast<float>(sx) - 0.5f) / rx - 0.5f)) - 1;
+  int xhi = static_cast<int>(ceilf((static_cast<float>(sx) + 1.5f) / rx - 0.5f)) + 1;
+  ylo = ylo < 0 ? 0 : ylo; xlo = xlo < 0 ? 0 : xlo;
+  yhi = yhi > Hg - 1 ? Hg - 1 : yhi; xhi = xhi > Wg - 1 ? Wg - 1 : xhi;
+  const float* src = da1 + static_cast<long>(b) * Hg * Wg * 128 + threadIdx.x;
+  float acc = 0.f;
+  for (int py = ylo; py <= yhi; ++py) {
+    int y0, y1;
+    float ly0, ly1;
+    bilin_src(py, Rh, ry, y0, y1, ly0, ly1);
+    const float wy = (y0 == sy ? ly0 : 0.f) + (y1 == sy ? ly1 : 0.f);
+    if (wy == 0.f) continue;
+    for (int px = xlo; px <= xhi; ++px) {
+      int x0, x1;
+      float lx0, lx1;
+      bilin_src(px, Rw, rx, x0, x1, lx0, lx1);
+      const float wx = (x0 == sx ? lx0 : 0.f) + (x1 == sx ? lx1 : 0.f);
+      if (wx == 0.f) continue;
+      acc = fmaf(wy * wx, src[(static_cast<long>(py) * Wg + px) * 128], acc);
+    }
+  }
+  dp[static_cast<long>(s) * dp_stride + threadIdx.x] = acc;
+}
+
 }  // namespace hg
 
 extern "C" {
+
+int hg_wgrad_blocked(const float* dout, const float* x, long x_bstride, int Cx, const float* mod, float* dw, float* dbias,
+                     void* workspace, int B, int C, int Hg, int Wg, int passes, void* stream);
 
 size_t hg_spade_bwd_wgrad_workspace_bytes(void) {
   return static_cast<size_t>(hg::num_sms()) * (hg::kWC * hg::kWC + hg::kWC) * sizeof(float);
@@ -363,18 +533,24 @@ size_t hg_spade_bwd_wgrad_workspace_bytes(void) {
 
 int hg_spade_bwd_wgrad(const float* dout, const float* x, long x_bstride, const float* mod, float* dw, float* dbias,
                        void* workspace, int B, int C, int Hg, int Wg, int passes, void* stream) {
-  HG_REQUIRE(C == hg::kWC, "hg_spade_bwd_wgrad: only %d channels are supported (got %d)", hg::kWC, C);
-  HG_REQUIRE(dout && x && mod && dw && workspace, "hg_spade_bwd_wgrad: null pointer");
-  HG_REQUIRE(passes == 1 || passes == 3, "hg_spade_bwd_wgrad: passes must be 1 or 3");
-  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_spade_bwd_wgrad: bad shape");
+  return hg_wgrad_blocked(dout, x, x_bstride, C, mod, dw, dbias, workspace, B, C, Hg, Wg, passes, stream);
+}
+
+int hg_wgrad_blocked(const float* dout, const float* x, long x_bstride, int Cx, const float* mod, float* dw, float* dbias,
+                     void* workspace, int B, int C, int Hg, int Wg, int passes, void* stream) {
+  HG_REQUIRE(C == hg::kWC, "hg_wgrad_blocked: only %d gradient channels are supported (got %d)", hg::kWC, C);
+  HG_REQUIRE(Cx == 128 || Cx == 256, "hg_wgrad_blocked: the second operand must have 128 or 256 channels (got %d)", Cx);
+  HG_REQUIRE(dout && x && dw && workspace, "hg_wgrad_blocked: null pointer");
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_wgrad_blocked: passes must be 1 or 3");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_wgrad_blocked: bad shape");
   HG_REQUIRE(((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
-             "hg_spade_bwd_wgrad: tensors must be 16-byte aligned");
+             "hg_wgrad_blocked: tensors must be 16-byte aligned");
   const int T = (Hg * Wg + 127) / 128;
   const int tiles = B * T;
   const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
   float* part_w = static_cast<float*>(workspace);
   float* part_b = part_w + static_cast<size_t>(hg::num_sms()) * hg::kWC * hg::kWC;
-  hg::WgradArgs a{dout, x, x_bstride, mod, part_w, part_b, B, Hg * Wg};
+  hg::WgradArgs a{dout, x, x_bstride, mod, part_w, part_b, B, Hg * Wg, Cx};
   auto st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (passes == 3) {
@@ -387,7 +563,7 @@ int hg_spade_bwd_wgrad(const float* dout, const float* x, long x_bstride, const 
   if (e != cudaSuccess) { hg::set_error("hg_spade_bwd_wgrad: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; }
   int rc = hg::check_launch("hg_spade_bwd_wgrad");
   if (rc) return rc;
-  hg::wgrad_reduce_kernel<<<(hg::kWC * hg::kWC + 255) / 256, 256, 0, st>>>(part_w, part_b, grid, dw, dbias);
+  hg::wgrad_reduce_kernel<<<(hg::kWC * Cx + 255) / 256, 256, 0, st>>>(part_w, part_b, grid, hg::kWC * Cx, dw, dbias);
   return hg::check_launch("hg_spade_bwd_wgrad(reduce)");
 }
 
@@ -418,6 +594,45 @@ int hg_synth_input_bwd(const float* dx, const float* w, const float* bias, const
   HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_synth_input_bwd: bad shape");
   hg::synth_input_bwd_kernel<<<C, 256, 0, static_cast<cudaStream_t>(stream)>>>(dx, w, bias, ic, jc, B, Hg, Wg, dw, db);
   return hg::check_launch("hg_synth_input_bwd");
+}
+
+int hg_spade_a1(const float* p_lr, long p_stride, const float* p_bias, float* a1, int B, int Hg, int Wg, int Rh, int Rw,
+                void* stream) {
+  HG_REQUIRE(p_lr && a1, "hg_spade_a1: null pointer");
+  HG_REQUIRE((reinterpret_cast<uintptr_t>(p_lr) & 15) == 0 && p_stride >= 128 && (p_stride & 3) == 0,
+             "hg_spade_a1: p_lr must be 16-byte aligned with a row stride >= 128 that is a multiple of 4");
+  HG_REQUIRE(!p_bias || (reinterpret_cast<uintptr_t>(p_bias) & 15) == 0, "hg_spade_a1: p_bias must be 16-byte aligned");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0 && Rh > 0 && Rw > 0, "hg_spade_a1: bad shape");
+  const int tiles = B * ((Hg * Wg + 127) / 128);
+  hg::a1_gather_kernel<<<tiles, 128, 0, static_cast<cudaStream_t>(stream)>>>(p_lr, p_stride, p_bias, a1, B, Hg, Wg, Rh, Rw);
+  return hg::check_launch("hg_spade_a1");
+}
+
+int hg_spade_pixel_pre(const float* x, long x_bstride, const float* scsh, const float* gam, float* bet_pre, int B, int C,
+                       int Hg, int Wg, void* stream) {
+  HG_REQUIRE(C == hg::kWC, "hg_spade_pixel_pre: only %d channels are supported (got %d)", hg::kWC, C);
+  HG_REQUIRE(x && scsh && gam && bet_pre, "hg_spade_pixel_pre: null pointer");
+  const int T = (Hg * Wg + 127) / 128;
+  hg::pixel_pre_kernel<<<hg::num_sms() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_bstride, scsh, gam, bet_pre, B, T);
+  return hg::check_launch("hg_spade_pixel_pre");
+}
+
+int hg_spade_pixel_mod_bwd(const float* dpre, const float* x, long x_bstride, const float* scsh, float* gam_dgam, float* dxn,
+                           double* sums, int B, int C, int Hg, int Wg, void* stream) {
+  HG_REQUIRE(C == hg::kWC, "hg_spade_pixel_mod_bwd: only %d channels are supported (got %d)", hg::kWC, C);
+  HG_REQUIRE(dpre && x && scsh && gam_dgam && dxn && sums, "hg_spade_pixel_mod_bwd: null pointer");
+  const int T = (Hg * Wg + 127) / 128;
+  int grid = hg::num_sms() * 4;
+  if (grid > B * T) grid = B * T;
+  hg::pixel_mod_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dpre, x, x_bstride, scsh, gam_dgam, dxn, sums, B, T);
+  return hg::check_launch("hg_spade_pixel_mod_bwd");
+}
+
+int hg_bilinear_adjoint(const float* da1, float* dp, long dp_stride, int B, int Hg, int Wg, int Rh, int Rw, void* stream) {
+  HG_REQUIRE(da1 && dp && dp_stride >= 128, "hg_bilinear_adjoint: bad arguments");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0 && Rh > 0 && Rw > 0, "hg_bilinear_adjoint: bad shape");
+  hg::bilinear_adjoint_kernel<<<B * Rh * Rw, 128, 0, static_cast<cudaStream_t>(stream)>>>(da1, dp, dp_stride, B, Hg, Wg, Rh, Rw);
+  return hg::check_launch("hg_bilinear_adjoint");
 }
 
 }  // extern "C"
