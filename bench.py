@@ -48,6 +48,18 @@ def peaks():
     return dict(FALLBACK_PEAKS, _source="fallback")
 
 
+def ncu_traffic(entry, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of the C2 workload (profiles/r1_final_ncu_summary.md); null for workloads that were not captured."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if entry != "hg_spade_conv" or workload != "C2" or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    # the 18 launches of a forward: 6 pixel-style + 12 const-style half-blocks (captured: one of each kind, no skip)
+    c, x = d["spade_const_kernel<3,0>"], d["spade_pixel_kernel<3>"]
+    return (12 * (c["dram_read"] + c["dram_write"]) + 6 * (x["dram_read"] + x["dram_write"])) / 18.0
+
+
 def workload_cfg(pkg, name):
     cfg = pkg.configs.baseline_config(name)
     cfg["nerf_noise"] = 0.0
@@ -305,7 +317,7 @@ def run_gpu(args, pkg):
         else:
             roof = {"bound": "tensor", "achieved": fl / sec / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof.update(kernel=dom, traffic=None, peak_source=pk["_source"], algorithmic_flops_per_launch=fl,
+        roof.update(kernel=dom, traffic=ncu_traffic(dom, args.workload), peak_source=pk["_source"], algorithmic_flops_per_launch=fl,
                     algorithmic_bytes_per_launch=by, mma_passes=int(mult),
                     tensor_frac_issued=fl * mult / sec / (pk["bf16_tflops"] * 1e12),
                     hbm_frac=by / sec / (pk["hbm_gbs"] * 1e9))

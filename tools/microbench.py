@@ -106,6 +106,45 @@ def main():
                                         "in": list(xi.shape), "out": list(up.shape)}
     out["upfirdn2d_downsample2d_sym6"] = {"ms": ms_dn, "bytes": b_dn, "gbps": b_dn / ms_dn / 1e6, "hbm_frac": b_dn / ms_dn / 1e6 / peaks["hbm_gbps"],
                                           "in": list(up.shape), "out": list(dn.shape)}
+    # ---- synthesis network, training mode: forward (keeping the half-block inputs) + backward, C2 shape
+    del D, img, xi, up, dn
+    torch.cuda.empty_cache()
+    st = importlib.import_module("3dhumangan_b200.modules.synthesis_train")
+    gen = importlib.import_module("3dhumangan_b200.modules.generator")
+    cfg = pkg.configs.baseline_config("C2")
+    cfg.update(gen_height=S, gen_width=S)
+    G = gen.Map3DGenerator(**cfg).to(dev).train()
+    P = {k: v for k, v in list(G.named_parameters()) + list(G.named_buffers()) if k.startswith(("synthesis_network.", "synthesis_input."))}
+    Rh, Rw = cfg["render_height"], cfg["render_width"]
+    feat = torch.randn(B, Rh * Rw, 256, device=dev)
+    fs = torch.randn(B, 256, device=dev) * 0.5
+    drgb = torch.randn(B, 3, S, S, device=dev)
+
+    def step():
+        rgb, tape = st.synthesis_forward_train(P, feat, fs, cfg)
+        st.synthesis_backward(P, tape, drgb)
+        for p_ in P.values():
+            p_.grad = None
+
+    def fwd_only():
+        st.synthesis_forward_train(P, feat, fs, cfg)
+
+    abi.TIMING = None
+    ms_f = timed(fwd_only, 3, warmup=2)
+    ms_fb = timed(step, 3, warmup=2)
+    torch.cuda.synchronize()
+    abi.TIMING = []
+    step()
+    torch.cuda.synchronize()
+    per = {}
+    for name, s_, e_ in abi.TIMING:
+        d = per.setdefault(name, [0.0, 0])
+        d[0] += s_.elapsed_time(e_)
+        d[1] += 1
+    abi.TIMING = None
+    out["synthesis_train_fp32x3"] = {"forward_ms": ms_f, "forward_backward_ms": ms_fb, "images_per_s_fwd_bwd": B / ms_fb * 1e3,
+                                     "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                                     "kernels_ms": {k: [round(v[0], 3), v[1]] for k, v in sorted(per.items(), key=lambda t: -t[1][0])}}
     print(json.dumps(out, indent=1))
 
 
