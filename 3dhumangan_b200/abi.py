@@ -40,7 +40,15 @@ SIGNATURES = {
     "hg_spade_bwd_wgrad": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "hg_spade_bwd_combine": (c_int, [c_void_p, c_void_p, c_long] + [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
     "hg_conv1x1_blocked": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
-    "hg_conv1x1_blocked_bwd": (c_int, [c_void_p] * 7 + [c_int, c_float, c_int] + [c_int] * 4 + [c_void_p]),
+    "hg_conv1x1_blocked_bwd": (c_int, [c_void_p] * 7 + [c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int]
+                               + [c_int] * 4 + [c_void_p]),
+    "hg_act_conv1x1_blocked": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "hg_act_wgrad_blocked": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+                             + [c_int] * 5 + [c_void_p]),
+    "hg_render_heads": (c_int, [c_void_p] * 8 + [c_int, c_int, c_void_p]),
+    "hg_render_heads_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
+    "hg_render_composite": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
+    "hg_render_composite_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "hg_wgrad_blocked": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "hg_spade_a1": (c_int, [c_void_p, c_long, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "hg_spade_pixel_pre": (c_int, [c_void_p, c_long, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
@@ -254,11 +262,67 @@ def conv1x1_blocked(x, Cin, wimg, bias, out, *, B, Hg, Wg, passes=3):
 
 
 def conv1x1_blocked_bwd(g, aux, wimg_t, out, sums, *, B, Hg, Wg, g2=None, mod=None, Cout=256, slope=0.2, pixel_major=False,
-                        passes=3):
+                        passes=3, act=0, ascale=None, rk_w=None, rk_v=None):
+    rk_n = 0 if rk_v is None else rk_v.shape[1]
     with torch.cuda.device_of(g):
         call("hg_conv1x1_blocked_bwd", ptr(g), ptr(g2), ptr(aux), ptr(mod), ptr(wimg_t), ptr(out), ptr(sums), Cout,
-             float(slope), int(bool(pixel_major)), B, Hg, Wg, passes, stream())
+             float(slope), int(bool(pixel_major)), act, ptr(ascale), ptr(rk_w), ptr(rk_v), rk_n, B, Hg, Wg, passes, stream())
     return out
+
+
+def act_conv1x1_blocked(x, mod, wimg, bias, out, *, B, Hg, Wg, x2=None, act=1, passes=3):
+    """out = W [act(x*g1+g0); act(x2*g1+g0)] + bias over tile-blocked points / pixels (act 1 = sine)."""
+    with torch.cuda.device_of(x):
+        call("hg_act_conv1x1_blocked", ptr(x), ptr(x2), ptr(mod), act, ptr(wimg), ptr(bias), ptr(out), B, Hg, Wg, passes, stream())
+    return out
+
+
+def act_wgrad_blocked(dout, x, x_bstride, mod, *, B, Hg, Wg, act, pscale=None, Cx=256, passes=3):
+    dev = dout.device
+    ws = _WGRAD_WS.get(dev)
+    if ws is None:
+        ws = _WGRAD_WS[dev] = torch.empty(int(lib().hg_spade_bwd_wgrad_workspace_bytes()) // 4, dtype=torch.float32, device=dev)
+    dw = torch.empty(256, Cx, dtype=torch.float32, device=dev)
+    db = torch.empty(256, dtype=torch.float32, device=dev)
+    with torch.cuda.device_of(dout):
+        call("hg_act_wgrad_blocked", ptr(dout), ptr(pscale), ptr(x), int(x_bstride), Cx, ptr(mod), act, ptr(dw), ptr(db), ptr(ws),
+             B, 256, Hg, Wg, passes, stream())
+    return dw, db
+
+
+def render_heads(out3, linc, mod3, w_sigma, w_rgb, heads_b, *, B, N):
+    sig = torch.empty(B, N, dtype=torch.float32, device=out3.device)
+    rgbp = torch.empty(B, 3, N, dtype=torch.float32, device=out3.device)
+    with torch.cuda.device_of(out3):
+        call("hg_render_heads", ptr(out3), ptr(linc), ptr(mod3), ptr(w_sigma), ptr(w_rgb), ptr(heads_b), ptr(sig), ptr(rgbp), B, N,
+             stream())
+    return sig, rgbp
+
+
+def render_heads_bwd(out3, linc, mod3, dsig, drgbp, *, B, N):
+    acc = torch.zeros(4 * 256 + 4, dtype=torch.float64, device=out3.device)
+    with torch.cuda.device_of(out3):
+        call("hg_render_heads_bwd", ptr(out3), ptr(linc), ptr(mod3), ptr(dsig), ptr(drgbp), ptr(acc), B, N, stream())
+    return acc
+
+
+def render_composite(sig, z, noise, rgbp, feat, *, B, R, S, noise_std, white_back, softplus):
+    ray_out = torch.empty(B, R, 260, dtype=torch.float32, device=sig.device)
+    w = torch.empty(B, R * S, dtype=torch.float32, device=sig.device)
+    with torch.cuda.device_of(sig):
+        call("hg_render_composite", ptr(sig), ptr(z), ptr(noise), ptr(rgbp), ptr(feat), ptr(ray_out), ptr(w), B, R, S,
+             float(noise_std), int(bool(white_back)), int(bool(softplus)), stream())
+    return ray_out, w
+
+
+def render_composite_bwd(sig, z, noise, rgbp, feat, dray, *, B, R, S, noise_std, white_back, softplus):
+    dfeat = torch.empty_like(feat)
+    drgbp = torch.empty_like(rgbp)
+    dsig = torch.empty_like(sig)
+    with torch.cuda.device_of(sig):
+        call("hg_render_composite_bwd", ptr(sig), ptr(z), ptr(noise), ptr(rgbp), ptr(feat), ptr(dray), ptr(dfeat), ptr(drgbp),
+             ptr(dsig), B, R, S, float(noise_std), int(bool(white_back)), int(bool(softplus)), stream())
+    return dfeat, drgbp, dsig
 
 
 def spade_a1(p_lr, p_stride, p_bias, a1, *, B, Hg, Wg, Rh, Rw):

@@ -80,6 +80,10 @@ struct SpadeArgs {
   float slope;           // operand LeakyReLU slope (1 = identity); backward epilogue: slope of the mask (0.2 / 0 = ReLU)
   int cout;              // output channels written by the epilogue: 256 or 128 (the MMA always runs N = 256)
   int out_pm;            // backward epilogue: write pixel-major [B,HW,cout] instead of tile-blocked
+  int act;               // 0: LeakyReLU(slope) (SPADE), 1: sine (FiLM-SIREN layers of the renderer: y = sin(x*g1 + g0))
+  const float* ascale;   // backward operand: per-(b,c) scale [B,C] applied to the incoming gradient, or null
+  const float* rk_v;     // backward epilogue: rank-k term  acc += sum_j rgb_w[j][c] * rk_v[b][j][pixel]  (k = rk_n <= 3)
+  int rk_n;
 };
 
 struct SynSmem {
@@ -92,6 +96,7 @@ struct SynSmem {
   float* tab_bias; // [C]
   float* tab_rgbw; // [3*C]
   float* tab_bgb;  // [512]
+  float* tab_as;   // [C]  backward operand scale
   float* st_sum;   // [C]
   float* st_sq;    // [C]
   uint64_t* bars;
@@ -111,6 +116,7 @@ __device__ __forceinline__ SynSmem carve(uint8_t* raw) {
   m.tab_bias = f; f += kC;
   m.tab_rgbw = f; f += 3 * kC;
   m.tab_bgb = f; f += 512;
+  m.tab_as = f; f += kC;
   m.st_sum = f; f += kC;
   m.st_sq = f; f += kC;
   m.bars = reinterpret_cast<uint64_t*>(f);
@@ -118,7 +124,7 @@ __device__ __forceinline__ SynSmem carve(uint8_t* raw) {
   return m;
 }
 constexpr uint32_t kSynSmemBytes = 2 * kASlots * kAChunk + kSynStages * kBStage + kXSlots * kXSlice +
-                                   (kC * 8 + 512) * 4 + 40 * 8 + 16 + 1024;
+                                   (kC * 9 + 512) * 4 + 40 * 8 + 16 + 1024;
 static_assert(kSynSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots
@@ -128,6 +134,17 @@ enum { A_FULL = 0 /*2*/, A_EMPTY = 2 /*2*/, B_FULL = 4 /*2*/, B_EMPTY = 6 /*2*/,
 __device__ __forceinline__ void rows_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+
+// sin / cos for |t| up to a few thousand: two-term Cody-Waite reduction by 2*pi, then the SFU (abs error ~2^-21);
+// the same evaluation as the fused renderer (csrc/render.cu), so that forward and backward agree.
+__device__ __forceinline__ float reduce_2pi(float t) {
+  const float y = t * 0.15915494309189535f;
+  const float k = (y + 12582912.f) - 12582912.f;
+  float r = fmaf(-k, 6.2831854820251465f, t);
+  return fmaf(-k, -1.7484555314695172e-07f, r);
+}
+__device__ __forceinline__ float sin_red(float t) { return __sinf(reduce_2pi(t)); }
+__device__ __forceinline__ float cos_red(float t) { return __cosf(reduce_2pi(t)); }
 
 // 32 lanes x 32 values: after the call lane j holds sum over lanes of v[j].
 __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
@@ -425,6 +442,9 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
   };
   const float mslope = a.slope;
   const int ncg = a.cout >> 5;
+  const bool sine = a.act == 1;
+  uint32_t trk = smem_u32(m.tab_rgbw);     // rank-k weights (loaded by init_common through a.rgb_w)
+  opaque(trk);
   for (int it = 0; it < tm.count; ++it) {
     int b, ti;
     tm.get(it, b, ti);
@@ -445,6 +465,9 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
     const bool valid = ti * 128 + row < a.HW;
     const long plane = a.out_pm ? (static_cast<long>(b) * a.HW + ti * 128 + row) * a.cout
                                 : (static_cast<long>(b) * tm.T + ti) * a.cout * 128 + row;
+    float rv[3] = {0.f, 0.f, 0.f};
+    if (a.rk_v && valid)
+      for (int j = 0; j < a.rk_n; ++j) rv[j] = a.rk_v[(static_cast<long>(b) * a.rk_n + j) * a.HW + ti * 128 + row];
     mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
     tc_fence_after();
 #pragma unroll 1
@@ -474,7 +497,15 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
         for (int jj = 0; jj < 8; ++jj) {
           const int j = g * 8 + jj;
           const float pre = fmaf(xs_[j], t1[jj], t0[jj]);
-          const float d = __uint_as_float(raw[j]) * (pre > 0.f ? 1.f : mslope);
+          float acc = __uint_as_float(raw[j]);
+          if (a.rk_v) {
+            acc = fmaf(rv[0], lds_f32(trk + (c0 + j) * 4), acc);
+            if (a.rk_n > 1) {
+              acc = fmaf(rv[1], lds_f32(trk + (kC + c0 + j) * 4), acc);
+              acc = fmaf(rv[2], lds_f32(trk + (2 * kC + c0 + j) * 4), acc);
+            }
+          }
+          const float d = acc * (sine ? cos_red(pre) : (pre > 0.f ? 1.f : mslope));
           if (valid && !a.out_pm) a.out[plane + (c0 + j) * 128] = d;
           v[j] = valid ? d : 0.f;
           w[j] = v[j] * xs_[j];
@@ -525,20 +556,25 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
     for (int it = 0; it < tm.count; ++it) {
       int b, ti;
       tm.get(it, b, ti);
-      if (!kBwd && b != cur_b) {  // refresh the per-sample modulation table
+      if (b != cur_b && (!kBwd || a.ascale)) {  // refresh the per-sample tables of the operand team
         rows_barrier();
-        for (int i = threadIdx.x; i < kC; i += 256) {   // no table = identity (plain 1x1 convolution)
-          m.tab_g1[i] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 0) * kC + i] : 1.f;
-          m.tab_g0[i] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 1) * kC + i] : 0.f;
+        for (int i = threadIdx.x; i < kC; i += 256) {
+          if (kBwd) {
+            m.tab_as[i] = a.ascale[static_cast<long>(b) * kC + i];
+          } else {   // no table = identity (plain 1x1 convolution)
+            m.tab_g1[i] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 0) * kC + i] : 1.f;
+            m.tab_g0[i] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 1) * kC + i] : 0.f;
+          }
         }
         rows_barrier();
         cur_b = b;
       }
       const bool valid = ti * 128 + row < a.HW;
-      uint32_t tg1 = smem_u32(m.tab_g1), tg0 = smem_u32(m.tab_g0);
+      uint32_t tg1 = smem_u32(kBwd ? m.tab_as : m.tab_g1), tg0 = smem_u32(m.tab_g0);
       opaque(tg1);   // the tables may just have been refreshed: no table load may move above this point
       opaque(tg0);
       const float slope = a.slope;
+      const bool sine = a.act == 1, scaled = kBwd && a.ascale != nullptr;
 #pragma unroll 1
       for (int kc = 0; kc < a.nkc; ++kc, ++acnt) {
         const int c0 = (kc * 64 + h * 32) & (kC - 1);
@@ -549,14 +585,20 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float y[8], t1[8], t0[8];
-          if (!kBwd) {
-            lds8(tg1 + (c0 + g * 8) * 4, t1);
-            lds8(tg0 + (c0 + g * 8) * 4, t0);
-          }
+          if (!kBwd || scaled) lds8(tg1 + (c0 + g * 8) * 4, t1);
+          if (!kBwd) lds8(tg0 + (c0 + g * 8) * 4, t0);
+          if (kBwd) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float v = fmaf(cur[g * 8 + j], t1[j], t0[j]);
-            y[j] = kBwd ? cur[g * 8 + j] : (v > 0.f ? v : slope * v);
+            for (int j = 0; j < 8; ++j) y[j] = scaled ? cur[g * 8 + j] * t1[j] : cur[g * 8 + j];
+          } else if (sine) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = sin_red(fmaf(cur[g * 8 + j], t1[j], t0[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v = fmaf(cur[g * 8 + j], t1[j], t0[j]);
+              y[j] = v > 0.f ? v : slope * v;
+            }
           }
           if (!valid) {   // only the last, partial tile of an image
 #pragma unroll
@@ -962,7 +1004,7 @@ int hg_spade_bwd_dgrad(const float* dout, const float* x, long x_bstride, const 
 int hg_conv1x1_blocked(const float* x, int Cin, const void* wimg, const float* bias, float* out, int B, int Hg, int Wg,
                        int passes, void* stream) {
   HG_REQUIRE(x && wimg && bias && out, "hg_conv1x1_blocked: null pointer");
-  HG_REQUIRE(Cin == 128 || Cin == 256, "hg_conv1x1_blocked: Cin must be 128 or 256 (got %d)", Cin);
+  HG_REQUIRE(Cin == 64 || Cin == 128 || Cin == 256, "hg_conv1x1_blocked: Cin must be 64, 128 or 256 (got %d)", Cin);
   HG_REQUIRE(passes == 1 || passes == 3, "hg_conv1x1_blocked: passes must be 1 or 3");
   HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_conv1x1_blocked: bad shape");
   const long T = (Hg * Wg + 127) / 128;
@@ -978,9 +1020,34 @@ int hg_conv1x1_blocked(const float* x, int Cin, const void* wimg, const float* b
   return launch_blocked_gemm(a, passes, false, static_cast<cudaStream_t>(stream), "hg_conv1x1_blocked");
 }
 
+int hg_act_conv1x1_blocked(const float* x, const float* x2, const float* mod, int act, const void* wimg, const float* bias,
+                           float* out, int B, int Hg, int Wg, int passes, void* stream) {
+  HG_REQUIRE(x && mod && wimg && bias && out, "hg_act_conv1x1_blocked: null pointer");
+  HG_REQUIRE(act == 0 || act == 1, "hg_act_conv1x1_blocked: act must be 0 (LeakyReLU 0.2) or 1 (sine)");
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_act_conv1x1_blocked: passes must be 1 or 3");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_act_conv1x1_blocked: bad shape");
+  const long T = (Hg * Wg + 127) / 128;
+  hg::SpadeArgs a{};
+  a.x = x;
+  a.x_bstride = T * hg::kC * 128;
+  a.x2 = x2;
+  a.mod = mod;
+  a.wimg = static_cast<const uint8_t*>(wimg);
+  a.bias = bias;
+  a.skip_bstride = T * hg::kC * 128;
+  a.out = out;
+  a.B = B; a.HW = Hg * Wg; a.Hg = Hg; a.Wg = Wg;
+  a.nkc = x2 ? 8 : 4; a.xC = hg::kC; a.slope = 0.2f; a.cout = hg::kC; a.act = act;
+  return launch_blocked_gemm(a, passes, false, static_cast<cudaStream_t>(stream), "hg_act_conv1x1_blocked");
+}
+
 int hg_conv1x1_blocked_bwd(const float* g, const float* g2, const float* aux, const float* mod, const void* wimg_t,
-                           float* out, double* sums, int Cout, float slope, int pixel_major, int B, int Hg, int Wg,
-                           int passes, void* stream) {
+                           float* out, double* sums, int Cout, float slope, int pixel_major, int act, const float* ascale,
+                           const float* rk_w, const float* rk_v, int rk_n, int B, int Hg, int Wg, int passes,
+                           void* stream) {
+  HG_REQUIRE(act == 0 || act == 1, "hg_conv1x1_blocked_bwd: act must be 0 (LeakyReLU/ReLU mask) or 1 (cosine)");
+  HG_REQUIRE(!ascale || !g2, "hg_conv1x1_blocked_bwd: the operand scale is built for K = 256");
+  HG_REQUIRE(!rk_v || (rk_w && rk_n >= 1 && rk_n <= 3 && Cout == 256), "hg_conv1x1_blocked_bwd: bad rank-k term");
   HG_REQUIRE(g && aux && wimg_t && out && sums, "hg_conv1x1_blocked_bwd: null pointer");
   HG_REQUIRE(Cout == 128 || Cout == 256, "hg_conv1x1_blocked_bwd: Cout must be 128 or 256 (got %d)", Cout);
   HG_REQUIRE(!pixel_major || Cout == 128, "hg_conv1x1_blocked_bwd: the pixel-major output is built for Cout == 128");
@@ -1000,6 +1067,7 @@ int hg_conv1x1_blocked_bwd(const float* g, const float* g2, const float* aux, co
   a.stats = sums;
   a.B = B; a.HW = Hg * Wg; a.Hg = Hg; a.Wg = Wg;
   a.nkc = g2 ? 8 : 4; a.xC = hg::kC; a.slope = slope; a.cout = Cout; a.out_pm = pixel_major;
+  a.act = act; a.ascale = ascale; a.rgb_w = rk_v ? rk_w : nullptr; a.rk_v = rk_v; a.rk_n = rk_n;
   return launch_blocked_gemm(a, passes, true, static_cast<cudaStream_t>(stream), "hg_conv1x1_blocked_bwd");
 }
 

@@ -27,7 +27,7 @@ namespace hg {
 constexpr int kWC = 256;
 constexpr int kWgThreads = 288;                 // warps 0-7: operand rows, warp 8: MMA issue
 constexpr uint32_t kWgImg = 256 * 128;          // [256 rows x 64 px] bf16 = 32 KB
-constexpr uint32_t kWgSmemBytes = 4 * kWgImg + 2 * kWC * 4 + 8 * 8 + 16 + 1024;
+constexpr uint32_t kWgSmemBytes = 4 * kWgImg + 3 * kWC * 4 + 8 * 8 + 16 + 1024;
 
 struct WgradArgs {
   const float* dout;     // [B,T,C,128]
@@ -38,9 +38,21 @@ struct WgradArgs {
   float* part_b;         // [grid, C]
   int B, HW;
   int nq;                // rows (channels) of the second operand x: 256, or 128 (gamma/beta weight gradients)
+  int act;               // y = 0: lrelu_0.2(x*g1+g0), 1: sin(x*g1+g0), 2: x (identity)
+  const float* pscale;   // [B,C] per-(b,row) scale of dout, or null
 };
 
 enum { WG_FULL = 0, WG_EMPTY = 1, WG_DONE = 2 };
+
+// the renderer's sine (csrc/render.cu `sin_reduced`): Cody-Waite reduction by 2*pi + SFU
+__device__ __forceinline__ float wg_red(float t) {
+  const float y = t * 0.15915494309189535f;
+  const float k = (y + 12582912.f) - 12582912.f;
+  float r = fmaf(-k, 6.2831854820251465f, t);
+  return fmaf(-k, -1.7484555314695172e-07f, r);
+}
+__device__ __forceinline__ float wg_sin(float t) { return __sinf(wg_red(t)); }
+__device__ __forceinline__ float wg_cos(float t) { return __cosf(wg_red(t)); }
 
 template <int kPasses>
 __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a) {
@@ -52,7 +64,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
   uint8_t* b_lo = s + 3 * kWgImg;
   float* tab_g1 = reinterpret_cast<float*>(s + 4 * kWgImg);
   float* tab_g0 = tab_g1 + kWC;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tab_g0 + kWC);
+  float* tab_ps = tab_g0 + kWC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tab_ps + kWC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -87,6 +100,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
         asm volatile("bar.sync 1, 256;" ::: "memory");
         tab_g1[threadIdx.x] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 0) * kWC + threadIdx.x] : 1.f;   // no table: y = lrelu(x)
         tab_g0[threadIdx.x] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 1) * kWC + threadIdx.x] : 0.f;
+        tab_ps[threadIdx.x] = a.pscale ? a.pscale[static_cast<long>(b) * kWC + threadIdx.x] : 1.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_b = b;
       }
@@ -113,6 +127,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = j < nvalid ? y[j] : 0.f;
           }
+          if (a.pscale) {
+            const float ps = tab_ps[st * 32 + rsub];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] *= ps;
+          }
           bsum[st] += ((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7]));
           store_a8<kPasses == 3>(a_hi, a_lo, st * 32 + rsub, sub * 8, y);
         }
@@ -136,7 +155,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float pre = fmaf(y[j], g1, g0);
-            y[j] = j < nvalid ? (pre > 0.f ? pre : 0.2f * pre) : 0.f;
+            const float v = a.act == 1 ? wg_sin(pre) : (a.act == 2 ? pre : (pre > 0.f ? pre : 0.2f * pre));
+            y[j] = j < nvalid ? v : 0.f;
           }
           store_a8<kPasses == 3>(b_hi, b_lo, row, sub * 8, y);
         }
@@ -526,6 +546,9 @@ extern "C" {
 
 int hg_wgrad_blocked(const float* dout, const float* x, long x_bstride, int Cx, const float* mod, float* dw, float* dbias,
                      void* workspace, int B, int C, int Hg, int Wg, int passes, void* stream);
+int hg_act_wgrad_blocked(const float* dout, const float* pscale, const float* x, long x_bstride, int Cx, const float* mod,
+                         int act, float* dw, float* dbias, void* workspace, int B, int C, int Hg, int Wg, int passes,
+                         void* stream);
 
 size_t hg_spade_bwd_wgrad_workspace_bytes(void) {
   return static_cast<size_t>(hg::num_sms()) * (hg::kWC * hg::kWC + hg::kWC) * sizeof(float);
@@ -538,6 +561,13 @@ int hg_spade_bwd_wgrad(const float* dout, const float* x, long x_bstride, const 
 
 int hg_wgrad_blocked(const float* dout, const float* x, long x_bstride, int Cx, const float* mod, float* dw, float* dbias,
                      void* workspace, int B, int C, int Hg, int Wg, int passes, void* stream) {
+  return hg_act_wgrad_blocked(dout, nullptr, x, x_bstride, Cx, mod, 0, dw, dbias, workspace, B, C, Hg, Wg, passes, stream);
+}
+
+int hg_act_wgrad_blocked(const float* dout, const float* pscale, const float* x, long x_bstride, int Cx, const float* mod,
+                         int act, float* dw, float* dbias, void* workspace, int B, int C, int Hg, int Wg, int passes,
+                         void* stream) {
+  HG_REQUIRE(act >= 0 && act <= 2, "hg_act_wgrad_blocked: act must be 0 (LeakyReLU 0.2), 1 (sine) or 2 (identity)");
   HG_REQUIRE(C == hg::kWC, "hg_wgrad_blocked: only %d gradient channels are supported (got %d)", hg::kWC, C);
   HG_REQUIRE(Cx == 128 || Cx == 256, "hg_wgrad_blocked: the second operand must have 128 or 256 channels (got %d)", Cx);
   HG_REQUIRE(dout && x && dw && workspace, "hg_wgrad_blocked: null pointer");
@@ -550,7 +580,7 @@ int hg_wgrad_blocked(const float* dout, const float* x, long x_bstride, int Cx, 
   const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
   float* part_w = static_cast<float*>(workspace);
   float* part_b = part_w + static_cast<size_t>(hg::num_sms()) * hg::kWC * hg::kWC;
-  hg::WgradArgs a{dout, x, x_bstride, mod, part_w, part_b, B, Hg * Wg, Cx};
+  hg::WgradArgs a{dout, x, x_bstride, mod, part_w, part_b, B, Hg * Wg, Cx, act, pscale};
   auto st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (passes == 3) {

@@ -137,7 +137,7 @@ size_t hg_spade_bwd_wgrad_workspace_bytes(void);
 int hg_spade_bwd_wgrad(const float* dout, const float* x, long x_bstride, const float* mod, float* dw, float* dbias,
                        void* workspace, int B, int C, int Hg, int Wg, int passes, void* stream);
 /* ---- generic pieces of the backward schedule over tile-blocked activations [B,T,C,128] (csrc/synth.cu, synth_bwd.cu) ----
- * hg_conv1x1_blocked:      out[B,T,256,128] = W[256 x Cin] x + bias, Cin in {128,256} (wimg = hg_pack_weight of W).
+ * hg_conv1x1_blocked:      out[B,T,256,128] = W[256 x Cin] x + bias, Cin in {64,128,256} (wimg = hg_pack_weight of W).
  * hg_conv1x1_blocked_bwd:  out = (Wt [g; g2]) * mask(aux*g1+g0), mask = 1 where positive else `slope` (0.2 LeakyReLU,
  *                          0 ReLU); g, g2 (NULL = absent) [B,T,256,128]; aux, out, sums carry Cout in {128,256} channels;
  *                          mod [B,2,Cout] or NULL (g1 = 1, g0 = 0); sums [B,2,Cout] fp64 += (sum out, sum out*aux);
@@ -151,9 +151,38 @@ int hg_spade_bwd_wgrad(const float* dout, const float* x, long x_bstride, const 
  *                          da1 [B,HW,128] (pixel-major); dp rows have stride dp_stride floats. */
 int hg_conv1x1_blocked(const float* x, int Cin, const void* wimg, const float* bias, float* out, int B, int Hg, int Wg,
                        int passes, void* stream);
+/* act (0 LeakyReLU/ReLU, 1 sine/cosine) selects the mask; ascale [B,256] scales g per (sample, channel) before the product
+ * (K = 256 only); rk_* adds  sum_j rk_w[j][c]*rk_v[b][j][pixel]  (rk_w [3,256], rk_v [B,rk_n,HW], rk_n in 1..3) to the
+ * product before the mask -- the sigma / rgb heads of the renderer (modulated.py:62-73) feed back that way. */
 int hg_conv1x1_blocked_bwd(const float* g, const float* g2, const float* aux, const float* mod, const void* wimg_t,
-                           float* out, double* sums, int Cout, float slope, int pixel_major, int B, int Hg, int Wg,
-                           int passes, void* stream);
+                           float* out, double* sums, int Cout, float slope, int pixel_major, int act, const float* ascale,
+                           const float* rk_w, const float* rk_v, int rk_n, int B, int Hg, int Wg, int passes,
+                           void* stream);
+/* out[B,T,256,128] = W [act(x*g1+g0); act(x2*g1+g0)] + bias with act = LeakyReLU 0.2 (0) or sine (1); mod [B,2,256];
+ * x2 NULL = K 256.  One FiLM-SIREN layer of COORDCONCATSIREN (modulated.py:41-75) over tile-blocked points. */
+int hg_act_conv1x1_blocked(const float* x, const float* x2, const float* mod, int act, const void* wimg, const float* bias,
+                           float* out, int B, int Hg, int Wg, int passes, void* stream);
+/* hg_wgrad_blocked with y = act(x*g1+g0), act 0 LeakyReLU 0.2 / 1 sine / 2 identity, and dout scaled per (sample, row) by
+ * pscale [B,256] (NULL = 1). */
+int hg_act_wgrad_blocked(const float* dout, const float* pscale, const float* x, long x_bstride, int Cx, const float* mod,
+                         int act, float* dw, float* dbias, void* workspace, int B, int C, int Hg, int Wg, int passes,
+                         void* stream);
+/* ---- renderer, training mode (csrc/render_train.cu): heads and volume integration over tile-blocked points ----
+ * hg_render_heads:      sig[B,N] = w_sigma . sin(f*out3+phi) + b0; rgbp[B,3,N] = W_rgb . sin(f*linc+phi) + b1..3
+ *                       (mod3 [B,2,256] = f, phi of the last FiLM slice; modulated.py:62-73).
+ * hg_render_heads_bwd:  acc[4*256+4] fp64 += (d w_sigma, d W_rgb[0..2], d b[0..3]).
+ * hg_render_composite(_bwd): vr.ray_integration (volume_rendering.py:12-56) and its gradient; ray_out / dray [B,R,260] =
+ *                       feat(256) | rgb(3) | depth; last_back = False only; S in {8,16,32,64,128}. */
+int hg_render_heads(const float* out3, const float* linc, const float* mod3, const float* w_sigma, const float* w_rgb,
+                    const float* heads_b, float* sig, float* rgbp, int B, int N, void* stream);
+int hg_render_heads_bwd(const float* out3, const float* linc, const float* mod3, const float* dsig, const float* drgbp,
+                        double* acc, int B, int N, void* stream);
+int hg_render_composite(const float* sig, const float* z, const float* noise, const float* rgbp, const float* feat,
+                        float* ray_out, float* weights, int B, int R, int S, float noise_std, int white_back,
+                        int clamp_softplus, void* stream);
+int hg_render_composite_bwd(const float* sig, const float* z, const float* noise, const float* rgbp, const float* feat,
+                            const float* dray, float* dfeat, float* drgbp, float* dsig, int B, int R, int S,
+                            float noise_std, int white_back, int clamp_softplus, void* stream);
 int hg_wgrad_blocked(const float* dout, const float* x, long x_bstride, int Cx, const float* mod, float* dw, float* dbias,
                      void* workspace, int B, int C, int Hg, int Wg, int passes, void* stream);
 int hg_spade_a1(const float* p_lr, long p_stride, const float* p_bias, float* a1, int B, int Hg, int Wg, int Rh, int Rw,
