@@ -12,8 +12,8 @@ reference's ~150 ATen launches:
     hg_spade_conv x18 SPADE half-blocks with BatchNorm / modulation / ToRGB fused around tcgen05 GEMMs
 
 There is no CPU or eager-PyTorch fallback: without a CUDA device and lib3dhg_sm100a.so the
-forward raises RuntimeError.  Backward kernels are not part of this round: calling forward with
-autograd enabled on parameters that require grad raises (see DESIGN.md "Scope").
+forward raises RuntimeError.  With autograd enabled on parameters that require grad, `forward` runs the
+training kernels (modules/render_train.py, modules/synthesis_train.py) and its outputs are differentiable.
 """
 from __future__ import annotations
 
@@ -302,11 +302,10 @@ class Map3DGenerator(nn.Module):
     def _params(self):
         return OrderedDict(list(self.named_parameters()) + list(self.named_buffers()))
 
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def _guard(self, kwargs):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError(
-                "hg3d: the backward kernels of the sm_100a path are not built yet; call the generator under "
-                "torch.no_grad() (as the discriminator step does, phase_trainer.py:358)")
         for key, bad in (("disable_render", True), ("disable_synthesis", True), ("2d_label_input", True),
                          ("2d_latent_input", True), ("hierarchical_sample", True)):
             if kwargs.get(key, False) == bad:
@@ -331,6 +330,13 @@ class Map3DGenerator(nn.Module):
         cond = {k: conditions[k] for k in ("skeletons_xyz", "vertices", "tpose_vertices", "fk_matrices", "lbs_weights",
                                            "cam2world_matrices", "intrinsics", "scales")}
         u, noise = rng.draw_render_noise(B, Rh * Rw, S, dev, cfg.get("sample_dist", None))
+        if self._wants_grad():
+            # training step of the generator: layer-by-layer renderer + taped synthesis network (render_train.py,
+            # synthesis_train.py); the fused inference kernels below keep nothing for a backward pass
+            from . import render_train
+            if not self.training:
+                raise RuntimeError("hg3d: gradients through the generator are built for train() mode (batch statistics)")
+            return render_train.GeneratorCore.apply(freq, phase, styles.reshape(B, -1), self, cond, cfg, u, noise, passes)
         r = render_ops.render_forward(P, freq, phase, cond, cfg, u, noise, passes=passes)
         ray = r["ray_out"]                                                   # [B,R,260]
         rgb = synthesis_ops.synthesis_forward(P, ray, styles.reshape(B, -1), cfg, training=self.training, passes=passes)
@@ -385,8 +391,16 @@ class Map3DGenerator(nn.Module):
 
     def forward(self, latent, conditions, render_height, render_width, latent_indices=None, **kwargs):
         """-> {"rgbs": [B,3,Hg,Wg], "rgbs_render": [B,3,Rh,Rw]}  (map3d_generator.py:208-280).
-        `hg_cuda_graph=True` (or HG3D_CUDA_GRAPH=1) replays the forward as a CUDA graph."""
+        `hg_cuda_graph=True` (or HG3D_CUDA_GRAPH=1) replays the forward as a CUDA graph.
+        With autograd enabled and parameters that require grad (the generator step of the trainer) the training
+        kernels run instead (render_train.GeneratorCore): outputs carry a grad_fn, `loss.backward()` fills `.grad`."""
         self._guard(kwargs)
+        if self._wants_grad():
+            cfg = self._cfg_for(kwargs, render_height, render_width)
+            if latent_indices is not None:
+                latent = self.latent_pool(latent_indices)
+            rgb, rgb_render, _ = self._forward_eager(latent, conditions, cfg, _precision_passes(kwargs))
+            return {"rgbs": rgb, "rgbs_render": rgb_render}
         with torch.no_grad():
             cfg = self._cfg_for(kwargs, render_height, render_width)
             if latent_indices is not None:

@@ -193,3 +193,68 @@ def mlp_backward(tape, dray):
             grads_.append(gr)
     torch.autograd.backward(outs_, grads_)
     return tape["fq"].grad, tape["ph"].grad
+
+
+@torch.no_grad()
+def geo_records(cond, cfg, u):
+    """Ray sampling + jitter + camera transform + exact nearest vertex + 31-d features (no gradient, as in the
+    reference: map3d_generator.py:196-205) -> (rec [B,N,36], z_vals [B,N]); same launches as render_ops.render_forward."""
+    dev = cond["vertices"].device
+    B = cond["vertices"].shape[0]
+    Rw, Rh, S = cfg["render_width"], cfg["render_height"], cfg["num_steps"]
+    f32 = dict(dtype=torch.float32, device=dev)
+    xs = torch.linspace(-Rw / Rh, Rw / Rh, Rw, **f32)
+    ys = torch.linspace(-1, 1, Rh, **f32)
+    zs = torch.linspace(cfg["ray_start"], cfg["ray_end"], S, **f32)
+    vik = abi.vertex_ik(cond["fk_matrices"], cond["lbs_weights"])
+    geo = abi.geo_features(cond["vertices"], cond["tpose_vertices"], cond["skeletons_xyz"], vik,
+                           input_scaler=2.0 / cfg["side_length"], legacy_mode=cfg.get("legacy_mode", False),
+                           xs=xs, ys=ys, zs=zs, focals=cond["intrinsics"][:, 0, 0], scales=cond["scales"],
+                           cam2world=cond["cam2world_matrices"], jitter=u.reshape(B, Rw * Rh * S) if u is not None else None)
+    return geo["rec"], geo["z_vals"]
+
+
+class GeneratorCore(torch.autograd.Function):
+    """(freq, phase, fixed style) -> (rgbs, rgbs_render, depth) with the renderer and the synthesis network on the
+    sm_100a kernels.  Backward returns the gradients of the three inputs (which continue into the mapping networks
+    through ordinary autograd) and ACCUMULATES the `.grad` of every renderer / synthesis parameter of `module` as a
+    side effect -- `loss.backward()` + an optimiser step work as usual; `torch.autograd.grad(loss, params)` does not
+    see those parameters.  Under data parallelism average the `.grad`s explicitly after backward (the reference's
+    DDP hooks never fire for them)."""
+
+    @staticmethod
+    def forward(ctx, freq, phase, styles, module, cond, cfg, u, noise, passes):
+        from . import synthesis_train
+        P = module._params()
+        B = freq.shape[0]
+        Rh, Rw = cfg["render_height"], cfg["render_width"]
+        if cfg.get("hierarchical_sample", False) or not cfg.get("lock_view_dependence", False):
+            raise RuntimeError("hg3d: the training renderer is built for hierarchical_sample=False, lock_view_dependence=True")
+        rec, z_vals = geo_records(cond, cfg, u)
+        with torch.enable_grad():
+            ray, rtape = mlp_forward_train(P, freq, phase, rec, z_vals, noise, cfg, geo_dim=cfg["geo_feature_dim"],
+                                           passes=passes)
+            rgb, stape = synthesis_train.synthesis_forward_train(P, ray, styles.reshape(B, -1), cfg, passes=passes)
+        ctx.tapes = (P, rtape, stape, cfg, passes)
+        rgb_render = (ray[..., 256:259] * 2 - 1).reshape(B, Rh, Rw, 3).permute(0, 3, 1, 2).contiguous()
+        depth = ray[..., 259:260].contiguous()
+        ctx.mark_non_differentiable(depth)
+        return rgb, rgb_render, depth
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_rgb_render, d_depth):
+        from . import synthesis_train
+        P, rtape, stape, cfg, passes = ctx.tapes
+        B = stape.B
+        Rh, Rw = cfg["render_height"], cfg["render_width"]
+        with torch.enable_grad():
+            dfs, dfeat = synthesis_train.synthesis_backward(P, stape, d_rgb, passes=passes)
+        dray = torch.zeros(B, Rh * Rw, 260, dtype=torch.float32, device=d_rgb.device)
+        if dfeat is not None:
+            dray[..., :256] = dfeat
+        if d_rgb_render is not None:
+            dray[..., 256:259] = 2.0 * d_rgb_render.permute(0, 2, 3, 1).reshape(B, Rh * Rw, 3)
+        with torch.enable_grad():
+            dfreq, dphase = mlp_backward(rtape, dray)
+        ctx.tapes = None
+        return dfreq, dphase, dfs.reshape(B, -1), None, None, None, None, None, None

@@ -90,13 +90,17 @@ def test_forward_fails_loudly_without_gpu(pkg, port):
         bias_act.bias_act(torch.randn(4, 8), torch.zeros(8), act="lrelu")
 
 
-def test_backward_is_refused_not_faked(pkg):
+def test_training_forward_has_no_cpu_path_either(pkg):
+    """With autograd enabled the generator takes the training kernels; on a CPU tensor that must raise, not fall back."""
     gen = importlib.import_module("3dhumangan_b200.modules.generator")
     cfg = pkg.configs.baseline_config("tiny")
     G = gen.Map3DGenerator(**cfg)
     G.set_device("cpu")
-    with pytest.raises(RuntimeError, match="backward"):
+    with pytest.raises(RuntimeError, match="CUDA|sm_100a|no CPU path"):
         G(torch.randn(1, cfg["latent_dim"]), pkg.synthetic.make_conditions(1), **cfg)
+    D = importlib.import_module("3dhumangan_b200.modules.discriminator").UNetDiscriminator(**cfg)
+    with pytest.raises(RuntimeError, match="backward"):          # the discriminator's backward kernels are not built yet
+        D(torch.randn(1, 3, 64, 64, requires_grad=True), None, 1.0)
 
 
 def test_dropin_import_paths():
