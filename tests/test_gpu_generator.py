@@ -140,20 +140,21 @@ def test_generator_backward_matches_oracle_autograd(port, monkeypatch):
     z = torch.randn(B, cfg["latent_dim"], generator=torch.Generator().manual_seed(23))
     wgt = torch.randn(B, 3, 16, 16, generator=torch.Generator().manual_seed(24))
     wgt_r = torch.randn(B, 3, 4, 4, generator=torch.Generator().manual_seed(25))
+    rng = importlib.import_module("3dhumangan_b200.rng")
     torch.manual_seed(3)
-    u, noise = pkg.rng.draw_render_noise(B, 16, 32, "cpu", cfg["sample_dist"])
-    torch.manual_seed(3)
+    u, noise = rng.draw_render_noise(B, 16, 32, "cpu", cfg["sample_dist"])
+    monkeypatch.setattr(rng, "draw_render_noise", lambda *a, **k: (u.cuda(), noise.cuda()))     # same draws on both sides
     out = G(z.cuda(), {k: v.cuda() for k, v in cond.items()}, **cfg)
     assert out["rgbs"].requires_grad and out["rgbs_render"].requires_grad
     loss = (out["rgbs"] * wgt.cuda()).sum() + (out["rgbs_render"] * wgt_r.cuda()).sum()
     loss.backward()
     torch.cuda.synchronize()
 
-    pc = {n: (v.clone().double().requires_grad_(True) if v.is_floating_point() else v.clone()) for n, v in params.items()}
-    condd = {k: (v.double() if v.is_floating_point() else v) for k, v in cond.items()}
-    ref = port.generator_forward(pc, z.double(), condd, cfg, u.double(), noise.double(), training=True)
-    assert (out["rgbs"].detach().cpu().double() - ref["rgbs"].detach()).abs().max() / ref["rgbs"].abs().max() < 1e-3
-    ((ref["rgbs"] * wgt.double()).sum() + (ref["rgbs_render"] * wgt_r.double()).sum()).backward()
+    # fp32 oracle: the reference's mapping network casts to float32 explicitly (mapping_networks.py:35)
+    pc = {n: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for n, v in params.items()}
+    ref = port.generator_forward(pc, z, cond, cfg, u, noise, training=True)
+    assert (out["rgbs"].detach().cpu() - ref["rgbs"].detach()).abs().max() / ref["rgbs"].abs().max() < 1e-3
+    ((ref["rgbs"] * wgt).sum() + (ref["rgbs_render"] * wgt_r).sum()).backward()
     named = dict(G.named_parameters())
     checked = 0
     worst = {}
