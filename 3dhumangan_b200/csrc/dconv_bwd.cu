@@ -1,0 +1,253 @@
+// Weight gradient of the discriminator's 3x3 / 1x1 convolutions (autograd through nn.Conv2d in
+// lib/discriminators/unet_discriminators.py:21-38), one launch per filter tap and per 256-channel chunk:
+//     dW[co, ci, ky, kx] = sum_{b,h,w} dy[b, co, h, w] * x[b, ci, h + ky - pad, w + kx - pad]
+// Same machine as the SPADE weight gradient (csrc/synth_bwd.cu): K = pixels, both operands are K-major as stored
+// (NCHW planes are contiguous along W), the operand warps convert rows of 64 pixels into bf16 hi/lo SW128 images --
+// the x rows read through the tap's shift with zero padding at the image border -- and the [256 x Cin] fp32
+// accumulator stays in TMEM for the CTA's lifetime; per-CTA partials are reduced in fp64 in a fixed order.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace hg {
+
+constexpr int kDwThreads = 288;
+constexpr uint32_t kDwImg = 256 * 128;
+constexpr uint32_t kDwSmemBytes = 4 * kDwImg + 8 * 8 + 16 + 1024;
+
+struct ConvWgradArgs {
+  const float* dy;       // [B,Cout,H,W]
+  const float* x;        // [B,Cin,H,W]
+  float* part_w;         // [grid,256,nq]
+  float* part_b;         // [grid,256]
+  int B, H, W, Cout, Cin;
+  int co0, nco;          // rows of dy handled by this launch (nco <= 256)
+  int ci0, nci, nq;      // rows of x (nci valid, nq = nci rounded up to 32, <= 256)
+  int oy, ox;            // tap shift: x is read at (h + oy, w + ox)
+};
+
+enum { DW_FULL = 0, DW_EMPTY = 1, DW_DONE = 2 };
+
+template <int kPasses>
+__global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_hi = s;
+  uint8_t* a_lo = s + kDwImg;
+  uint8_t* b_hi = s + 2 * kDwImg;
+  uint8_t* b_lo = s + 3 * kDwImg;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s + 4 * kDwImg);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bars + DW_FULL, 8);
+    mbar_init(bars + DW_EMPTY, 1);
+    mbar_init(bars + DW_DONE, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int HW = a.H * a.W, T = (HW + 127) / 128;
+  const int total = a.B * T;
+  const int count = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int nmh = a.nco > 128 ? 2 : 1;          // M halves that carry rows
+  const int nst_a = (a.nco + 31) >> 5, nst_b = a.nq >> 5;
+
+  if (warp < 8) {
+    const int sub = threadIdx.x & 7, rsub = threadIdx.x >> 3;
+    float bsum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+    uint32_t chunk = 0;
+    for (int it = 0; it < count; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / T, ti = tile - b * T;
+      const float* dbase = a.dy + (static_cast<long>(b) * a.Cout + a.co0) * HW;
+      const float* xbase = a.x + (static_cast<long>(b) * a.Cin + a.ci0) * HW;
+#pragma unroll 1
+      for (int kc = 0; kc < 2; ++kc, ++chunk) {
+        const int g0 = ti * 128 + kc * 64 + sub * 8;        // first pixel of this thread's 8
+        const int nvalid = HW - g0;
+        float4 va[16];
+#pragma unroll
+        for (int st = 0; st < 8; ++st) {
+          const int row = st * 32 + rsub;
+          if (st < nst_a && row < a.nco && nvalid >= 8) {
+            const float4* src = reinterpret_cast<const float4*>(dbase + static_cast<long>(row) * HW + g0);
+            va[2 * st] = __ldcs(src);
+            va[2 * st + 1] = __ldcs(src + 1);
+          } else {
+            va[2 * st] = va[2 * st + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (st < nst_a && row < a.nco && nvalid > 0) {      // ragged end of the image
+              const float* src = dbase + static_cast<long>(row) * HW + g0;
+              float t[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) t[j] = j < nvalid ? src[j] : 0.f;
+              va[2 * st] = make_float4(t[0], t[1], t[2], t[3]);
+              va[2 * st + 1] = make_float4(t[4], t[5], t[6], t[7]);
+            }
+          }
+        }
+        mbar_wait_sleep(bars + DW_EMPTY, (chunk & 1) ^ 1);
+#pragma unroll
+        for (int st = 0; st < 8; ++st) {
+          if (st >= nmh * 4) break;
+          const float y[8] = {va[2 * st].x, va[2 * st].y, va[2 * st].z, va[2 * st].w,
+                              va[2 * st + 1].x, va[2 * st + 1].y, va[2 * st + 1].z, va[2 * st + 1].w};
+          bsum[st] += ((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7]));
+          store_a8<kPasses == 3>(a_hi, a_lo, st * 32 + rsub, sub * 8, y);
+        }
+        // ---- x rows through the tap shift (zero padding outside the image)
+        int hh[8], ww[8];
+        bool ok[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int g = g0 + j;
+          const int h = g / a.W, w = g - h * a.W;
+          hh[j] = h + a.oy;
+          ww[j] = w + a.ox;
+          ok[j] = j < nvalid && hh[j] >= 0 && hh[j] < a.H && ww[j] >= 0 && ww[j] < a.W;
+        }
+        const int shift = a.oy * a.W + a.ox;
+#pragma unroll 2
+        for (int st = 0; st < 8; ++st) {
+          if (st >= nst_b) break;
+          const int row = st * 32 + rsub;
+          float y[8];
+          if (row < a.nci) {
+            const float* src = xbase + static_cast<long>(row) * HW + g0 + shift;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = ok[j] ? __ldg(src + j) : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = 0.f;
+          }
+          store_a8<kPasses == 3>(b_hi, b_lo, row, sub * 8, y);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + DW_FULL);
+      }
+    }
+#pragma unroll
+    for (int st = 0; st < 8; ++st) {
+      float v = bsum[st];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (sub == 0) a.part_b[static_cast<long>(blockIdx.x) * 256 + st * 32 + rsub] = v;
+    }
+  } else if (lane == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, a.nq);
+    uint32_t chunk = 0;
+    for (int it = 0; it < count; ++it)
+      for (int kc = 0; kc < 2; ++kc, ++chunk) {
+        mbar_wait_sleep(bars + DW_FULL, chunk & 1);
+        tc_fence_after();
+        for (int mh = 0; mh < nmh; ++mh) {
+          const uint32_t d = tmem + mh * 256;
+          const uint32_t ah = smem_u32(a_hi) + mh * (kDwImg / 2), al = smem_u32(a_lo) + mh * (kDwImg / 2);
+          umma_k64(d, ah, smem_u32(b_hi), idesc, chunk > 0);
+          if (kPasses == 3) {
+            umma_k64(d, al, smem_u32(b_hi), idesc, true);
+            umma_k64(d, ah, smem_u32(b_lo), idesc, true);
+          }
+        }
+        umma_commit(bars + DW_EMPTY);
+      }
+    umma_commit(bars + DW_DONE);
+  }
+  if (warp < 4) {
+    float* dst = a.part_w + static_cast<long>(blockIdx.x) * 256 * a.nq;
+    if (count > 0) {
+      mbar_wait_sleep(bars + DW_DONE, 0);
+      tc_fence_after();
+      for (int mh = 0; mh < 2; ++mh) {
+        const int co = mh * 128 + warp * 32 + lane;
+        for (int cg = 0; cg < (a.nq >> 5); ++cg) {
+          uint32_t raw[32];
+          if (mh < nmh) {
+            tmem_ld32(tmem + mh * 256 + (static_cast<uint32_t>(warp * 32) << 16) + cg * 32, raw);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = 0u;
+          }
+          float4* o = reinterpret_cast<float4*>(dst + static_cast<long>(co) * a.nq + cg * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                               __uint_as_float(raw[4 * j + 3]));
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < 256 * a.nq; i += 128) dst[i] = 0.f;
+    }
+  }
+  if (count == 0 && warp >= 4 && warp < 8) {
+    for (int i = threadIdx.x - 128; i < 256; i += 128) a.part_b[static_cast<long>(blockIdx.x) * 256 + i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<512>(tmem);
+}
+
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int nparts,
+                                         int nw, float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nw) {
+    double acc = 0.0;
+    for (int p = 0; p < nparts; ++p) acc += static_cast<double>(part_w[static_cast<long>(p) * nw + i]);
+    dw[i] = static_cast<float>(acc);
+  }
+  if (db && i < 256) {
+    double acc = 0.0;
+    for (int p = 0; p < nparts; ++p) acc += static_cast<double>(part_b[static_cast<long>(p) * 256 + i]);
+    db[i] = static_cast<float>(acc);
+  }
+}
+
+}  // namespace hg
+
+extern "C" {
+
+size_t hg_spade_bwd_wgrad_workspace_bytes(void);
+
+int hg_conv2d_wgrad_tap(const float* dy, const float* x, float* dw, float* dbias, void* workspace, int B, int H, int W,
+                        int Cout, int Cin, int co0, int nco, int ci0, int nci, int oy, int ox, int passes, void* stream) {
+  HG_REQUIRE(dy && x && dw && workspace, "hg_conv2d_wgrad_tap: null pointer");
+  HG_REQUIRE(B > 0 && H > 0 && W > 0 && (H * W) % 4 == 0, "hg_conv2d_wgrad_tap: bad image shape (H*W must be a multiple of 4)");
+  HG_REQUIRE(nco >= 1 && nco <= 256 && co0 >= 0 && co0 + nco <= Cout, "hg_conv2d_wgrad_tap: bad output-channel chunk");
+  HG_REQUIRE(nci >= 1 && nci <= 256 && ci0 >= 0 && ci0 + nci <= Cin, "hg_conv2d_wgrad_tap: bad input-channel chunk");
+  HG_REQUIRE(oy >= -1 && oy <= 1 && ox >= -1 && ox <= 1, "hg_conv2d_wgrad_tap: tap shift out of range");
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_conv2d_wgrad_tap: passes must be 1 or 3");
+  HG_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
+             "hg_conv2d_wgrad_tap: dy / workspace must be 16-byte aligned");
+  const int nq = (nci + 31) / 32 * 32;
+  const int T = (H * W + 127) / 128;
+  const int tiles = B * T;
+  const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
+  float* part_w = static_cast<float*>(workspace);
+  float* part_b = part_w + static_cast<size_t>(hg::num_sms()) * 256 * 256;
+  hg::ConvWgradArgs a{dy, x, part_w, part_b, B, H, W, Cout, Cin, co0, nco, ci0, nci, nq, oy, ox};
+  auto st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (passes == 3) {
+    e = cudaFuncSetAttribute(hg::conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kDwSmemBytes);
+    if (e == cudaSuccess) hg::conv_wgrad_kernel<3><<<grid, hg::kDwThreads, hg::kDwSmemBytes, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(hg::conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kDwSmemBytes);
+    if (e == cudaSuccess) hg::conv_wgrad_kernel<1><<<grid, hg::kDwThreads, hg::kDwSmemBytes, st>>>(a);
+  }
+  if (e != cudaSuccess) { hg::set_error("hg_conv2d_wgrad_tap: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; }
+  int rc = hg::check_launch("hg_conv2d_wgrad_tap");
+  if (rc) return rc;
+  // dw [256, nq] (rows >= nco and columns >= nci are zero), dbias [256]
+  hg::conv_wgrad_reduce_kernel<<<(256 * nq + 255) / 256, 256, 0, st>>>(part_w, part_b, grid, 256 * nq, dw, dbias);
+  return hg::check_launch("hg_conv2d_wgrad_tap(reduce)");
+}
+
+}  // extern "C"

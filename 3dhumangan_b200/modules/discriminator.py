@@ -76,9 +76,11 @@ class UNetDiscriminator(nn.Module):
         """-> {"prediction": [B,1,H,W], "latents": [B,L], "segments": [B,label_dim,H,W]} (:125-160).
         `conditions`, `alpha` and other kwargs are accepted and ignored, as in the reference."""
         from . import discriminator_ops
-        if torch.is_grad_enabled() and (images.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise RuntimeError("hg3d: the backward kernels of the sm_100a path are not built yet; call the "
-                               "discriminator under torch.no_grad()")
         from .generator import _precision_passes
+        if torch.is_grad_enabled() and (images.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # discriminator / generator step of the trainer: the autograd graph over the sm_100a primitives
+            from . import discriminator_train
+            return discriminator_train.discriminator_forward_train(self, images, passes=_precision_passes(kwargs),
+                                                                   masks=kwargs.get("hg_record_masks"))
         passes = _precision_passes(kwargs)
         return discriminator_ops.discriminator_forward(self, images, passes=passes)

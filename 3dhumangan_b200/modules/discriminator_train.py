@@ -1,0 +1,152 @@
+"""Training-mode U-Net discriminator: autograd graph over the sm_100a primitives.
+
+The inference path (`discriminator_ops.discriminator_forward`) folds LeakyReLU / up-sample / concat / residual into
+the convolution kernel.  For training the same network is an ordinary autograd graph whose nodes are this library's
+ops, so that first-order gradients w.r.t. images (generator step) and parameters (discriminator step) come out of
+`loss.backward()`:
+
+    convolution      `Conv2dSame`  forward `hg_conv2d`, data gradient `hg_conv2d` with the rotated / transposed filter,
+                                   weight gradient `hg_conv2d_wgrad_tap` (tcgen05, one launch per tap)
+    LeakyReLU        `ops.bias_act` (hg_bias_act / hg_bias_act_grad)
+    avg-pool / nearest up-sample   `ops.upfirdn2d` with a 2x2 box filter (its backward is another upfirdn pass)
+    spectral norm    torch autograd on W / sigma (one power iteration per training forward, buffers in place)
+    residual add, channel concat, the full-extent `latent_layer`: torch (`+`, `cat`, one library GEMM)
+
+Mirrors UNetDiscriminator.forward / ResBlock.forward (lib/discriminators/unet_discriminators.py:47-72, 125-160).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .. import abi
+from ..ops import bias_act as _ba
+from ..ops import upfirdn2d as _uf
+
+
+def _pack(w):
+    """[Cout,Cin,k,k] -> packed operand image of hg_conv2d (tap-major K)."""
+    Cout, Cin, kh, kw = w.shape
+    wm = w.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin).contiguous().float()
+    Nb = min(256, (Cout + 15) // 16 * 16)
+    return abi.pack_weight(wm, Nb=Nb)
+
+
+def _conv_raw(x, w, bias, passes):
+    """Stride-1 'same' convolution through hg_conv2d; output channels in chunks of 512 (two N blocks per launch)."""
+    B, Cin, H, W = x.shape
+    Cout, k = w.shape[0], w.shape[2]
+    outs = []
+    for c0 in range(0, Cout, 512):
+        wc = w[c0:c0 + 512]
+        img, Nb = _pack(wc)
+        outs.append(abi.conv2d(x, img, wc.shape[0], Nb, ksize=k, H=H, W=W, bias=None if bias is None else bias[c0:c0 + 512].contiguous(),
+                               passes=passes))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, 1)
+
+
+class Conv2dSame(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, passes):
+        x = x.float().contiguous()
+        ctx.save_for_backward(x, w)
+        ctx.passes, ctx.has_bias = passes, bias is not None
+        return _conv_raw(x, w.detach().float(), None if bias is None else bias.detach().float(), passes)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # correlation with the 180-degree rotated filter, input and output channels exchanged
+            wt = w.detach().float().flip(2, 3).transpose(0, 1).contiguous()
+            dx = _conv_raw(dy, wt, None, ctx.passes)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = abi.conv2d_wgrad(dy, x, w.shape[2], passes=ctx.passes)
+            if not ctx.has_bias:
+                db = None
+        return dx, dw, db, None
+
+
+def _lrelu(x, rec=None):
+    if rec is not None:
+        rec.append(x.detach() > 0)
+    return _ba.bias_act(x, None, act="lrelu", alpha=0.2, gain=1.0)
+
+
+def _pool(x):
+    f = torch.full((2, 2), 0.25, device=x.device)
+    return _uf.upfirdn2d(x, f, down=2)
+
+
+def _up(x):
+    f = torch.ones(2, 2, device=x.device)
+    return _uf.upfirdn2d(x, f, up=2, padding=[1, 0, 1, 0])
+
+
+def _sn_weight(P, name, training, enabled, eps=1e-12):
+    if not enabled:
+        return P[name + ".weight"]
+    w = P[name + ".weight_orig"]
+    u, v = P[name + ".weight_u"], P[name + ".weight_v"]
+    wm = w.reshape(w.shape[0], -1)
+    with torch.no_grad():
+        if training:
+            v.copy_(F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps))
+            u.copy_(F.normalize(torch.mv(wm, v), dim=0, eps=eps))
+    sigma = torch.dot(u.detach().clone(), torch.mv(wm, v.detach().clone()))
+    return w / sigma
+
+
+def discriminator_forward_train(module, images, passes=3, masks=None):
+    """Differentiable forward.  `masks`: optional list that receives the LeakyReLU masks in application order (tests)."""
+    abi.require_device()
+    P = dict(list(module.named_parameters()) + list(module.named_buffers()))
+    training = module.training
+    sn = not module._cfg.get("disable_spectral_norm", False)
+    nb = module.num_blocks
+    B = images.shape[0]
+
+    def conv(name, x, spectral=True):
+        return Conv2dSame.apply(x, _sn_weight(P, name, training, sn and spectral), P[name + ".bias"], passes)
+
+    x = images.float()
+    skips = []
+    for i in range(nb):
+        blk = f"body_down.{i}"
+        learned = (blk + ".conv_s.bias") in P
+        if i == 0:                                   # first block: pool, then the 1x1 shortcut (:58-63)
+            s = _pool(x)
+            if learned:
+                s = conv(blk + ".conv_s", s)
+            dx = conv(blk + ".conv1", x)
+        else:
+            s = conv(blk + ".conv_s", x) if learned else x
+            s = _pool(s)
+            dx = conv(blk + ".conv1.1", _lrelu(x, masks))
+        dx = conv(blk + ".conv2.1", _lrelu(dx, masks))
+        x = s + _pool(dx)
+        skips.append(x)
+    if min(x.shape[2:4]) > 1:
+        w = P["latent_layer.weight"]
+        latents = F.linear(x.reshape(B, -1), w.reshape(w.shape[0], -1), P["latent_layer.bias"])
+    else:
+        latents = torch.zeros(B, module.latent_dim, dtype=x.dtype, device=x.device)
+    for i in range(nb):
+        blk = f"body_up.{i}"
+        xin = x if i == 0 else torch.cat((skips[-i - 1], x), 1)
+        learned = (blk + ".conv_s.bias") in P
+        s = _up(xin)
+        if learned:
+            s = conv(blk + ".conv_s", s)
+        dx = conv(blk + ".conv1.2", _up(_lrelu(xin, masks)))
+        dx = conv(blk + ".conv2.1", _lrelu(dx, masks))
+        x = s + dx
+    pred = conv("layer_up_last", x, spectral=False)
+    seg = conv("output_layer", x, spectral=False)
+    sd = module.semantic_dim
+    out = {"prediction": pred, "latents": latents, "segments": seg[:, sd:]}
+    if sd > 0:
+        out["semantics"] = seg[:, :sd]
+    return out

@@ -193,6 +193,13 @@ int hg_spade_pixel_mod_bwd(const float* dpre, const float* x, long x_bstride, co
                            double* sums, int B, int C, int Hg, int Wg, void* stream);
 int hg_bilinear_adjoint(const float* da1, float* dp, long dp_stride, int B, int Hg, int Wg, int Rh, int Rw, void* stream);
 
+/* One tap of the weight gradient of a stride-1 "same" convolution over NCHW planes (autograd through nn.Conv2d,
+ * unet_discriminators.py:21-38):  dw[r, c] = sum_{b,h,w} dy[b, co0+r, h, w] * x[b, ci0+c, h+oy, w+ox]  (zero outside the
+ * image) for r < nco <= 256, c < nci <= 256; dw is [256, ceil32(nci)] (unused rows / columns zero), dbias [256] =
+ * sum dy (NULL = skip).  A 3x3 filter is 9 calls (oy, ox in -1..1), larger channel counts are chunked by the caller.
+ * workspace: hg_spade_bwd_wgrad_workspace_bytes(). */
+int hg_conv2d_wgrad_tap(const float* dy, const float* x, float* dw, float* dbias, void* workspace, int B, int H, int W,
+                        int Cout, int Cin, int co0, int nco, int ci0, int nci, int oy, int ox, int passes, void* stream);
 /* Backward of hg_synth_input: dx [B,T,C,128] (gradient w.r.t. the batch-shared x0, per sample) -> dw [C,2], db [C]. */
 int hg_synth_input_bwd(const float* dx, const float* w, const float* bias, const float* ic, const float* jc, int B, int C,
                        int Hg, int Wg, float* dw, float* db, void* stream);

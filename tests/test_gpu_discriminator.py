@@ -63,3 +63,66 @@ def test_pool_add_and_dense(pkg):
     w = torch.randn(37, 3000, generator=g).cuda()
     bias = torch.randn(37, generator=g).cuda()
     assert torch.allclose(abi.dense(x, w, bias), x @ w.t() + bias, rtol=1e-4, atol=1e-3)
+
+
+def test_conv_wgrad_and_dgrad_primitives():
+    """Conv2dSame (hg_conv2d forward / data gradient, hg_conv2d_wgrad_tap) against torch autograd in fp64."""
+    import torch.nn.functional as TF
+    dt = importlib.import_module("3dhumangan_b200.modules.discriminator_train")
+    g = torch.Generator().manual_seed(31)
+    for (B, Cin, Cout, H, W, k) in [(2, 64, 128, 16, 16, 3), (2, 3, 64, 16, 24, 3), (1, 320, 27, 8, 8, 1), (2, 128, 320, 8, 8, 3)]:
+        if Cin % 64 != 0 and k * k * Cin > 64:
+            continue
+        x0 = torch.randn(B, Cin, H, W, generator=g)
+        w0 = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+        b0 = torch.randn(Cout, generator=g)
+        gy = torch.randn(B, Cout, H, W, generator=g)
+        xr, wr, br = (t.double().requires_grad_(True) for t in (x0, w0, b0))
+        yr = TF.conv2d(xr, wr, br, padding=k // 2)
+        yr.backward(gy.double())
+        xg, wg, bg = (t.cuda().requires_grad_(True) for t in (x0, w0, b0))
+        yg = dt.Conv2dSame.apply(xg, wg, bg, 3)
+        yg.backward(gy.cuda())
+        torch.cuda.synchronize()
+        for name, a, b in (("y", yg.detach(), yr.detach()), ("dx", xg.grad, xr.grad), ("dw", wg.grad, wr.grad), ("db", bg.grad, br.grad)):
+            e = (a.cpu().double() - b).norm() / b.norm()
+            assert e < 3e-5, (B, Cin, Cout, H, W, k, name, float(e))
+
+
+def test_training_graph_matches_inference_and_oracle_gradients(port, monkeypatch):
+    """UNetDiscriminator under autograd: same outputs as the fused inference path; gradients w.r.t. the image (generator
+    step) and every parameter (discriminator step) against fp64 autograd through the restated reference, evaluated with
+    the LeakyReLU masks of our forward (the gradient is discontinuous in them, see tests/test_gpu_synthesis_bwd.py)."""
+    import torch.nn.functional as TF
+    cfg, params, img, gold = discriminator_case("d_tiny")
+    D = _build(cfg, params)
+    with torch.no_grad():
+        ref_out = D(img.cuda(), None, alpha=1.0, **cfg)
+    D2 = _build(cfg, params)
+    masks = []
+    xg = img.cuda().requires_grad_(True)
+    out = D2(xg, None, alpha=1.0, hg_record_masks=masks, **cfg)
+    for k in ("prediction", "segments", "latents"):
+        assert rel_l2(out[k].detach().cpu(), ref_out[k].cpu()) < 1e-4, k
+    g = torch.Generator().manual_seed(41)
+    ws = {k: torch.randn(out[k].shape, generator=g) for k in ("prediction", "segments", "latents")}
+    sum((out[k] * ws[k].cuda()).sum() for k in ws).backward()
+    torch.cuda.synchronize()
+
+    pc = {n: (v.clone().double().requires_grad_(True) if v.is_floating_point() else v.clone()) for n, v in params.items()}
+    xc = img.clone().double().requires_grad_(True)
+    it = iter([torch.where(m.cpu(), 1.0, 0.2).double() for m in masks])
+    with monkeypatch.context() as mp:
+        mp.setattr(port.F, "leaky_relu", lambda v, slope: v * next(it))
+        ro = port.discriminator_forward(pc, xc, cfg, training=True)
+    sum((ro[k] * ws[k].double()).sum() for k in ws).backward()
+    assert rel_l2(xg.grad.cpu().double(), xc.grad) < 5e-4
+    named = dict(D2.named_parameters())
+    bad = {}
+    for n, p in named.items():
+        if pc[n].grad is None:
+            continue
+        e = rel_l2(p.grad.cpu().double(), pc[n].grad)
+        if e > 5e-4:
+            bad[n] = e
+    assert not bad, sorted(bad.items(), key=lambda t: -t[1])[:8]
