@@ -27,7 +27,8 @@ from ..ops import upfirdn2d as _uf
 def _pack(w):
     """[Cout,Cin,k,k] -> packed operand image of hg_conv2d (tap-major K)."""
     Cout, Cin, kh, kw = w.shape
-    wm = w.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin).contiguous().float()
+    wm = torch.empty(Cout, kh * kw * Cin, dtype=torch.float32, device=w.device)      # explicit strides (K, 1) even for K == 1
+    wm.copy_(w.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin))
     Nb = min(256, (Cout + 15) // 16 * 16)
     return abi.pack_weight(wm, Nb=Nb)
 

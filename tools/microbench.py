@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--train-batch", type=int, default=4)
     args = ap.parse_args()
     pkg = importlib.import_module("3dhumangan_b200")
     abi = importlib.import_module("3dhumangan_b200.abi")
@@ -144,6 +145,42 @@ def main():
     abi.TIMING = None
     out["synthesis_train_fp32x3"] = {"forward_ms": ms_f, "forward_backward_ms": ms_fb, "images_per_s_fwd_bwd": B / ms_fb * 1e3,
                                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                                     "kernels_ms": {k: [round(v[0], 3), v[1]] for k, v in sorted(per.items(), key=lambda t: -t[1][0])}}
+    # ---- one G+D training iteration (C3 shape, R1 weight 0 as in the 512 curricula), per-entry-point breakdown
+    del P, feat, fs, drgb, G
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    disc = importlib.import_module("3dhumangan_b200.modules.discriminator")
+    cfg = pkg.configs.baseline_config("C2")
+    cfg.update(gen_height=S, gen_width=S, nerf_noise=0.5)
+    torch.manual_seed(0)
+    G = gen.Map3DGenerator(**cfg).to(dev).train()
+    G.set_device(dev)
+    D = disc.UNetDiscriminator(**cfg).to(dev).train()
+    og, od = ts.make_optimizers(G, D, cfg)
+    Bt = args.train_batch
+    cond = {k: v.to(dev) for k, v in pkg.synthetic.make_conditions(Bt, seed=1).items()}
+    batch = dict(z_d=torch.randn(Bt, cfg["latent_dim"], device=dev), z_g=torch.randn(Bt, cfg["latent_dim"], device=dev), cond=cond,
+                 images=torch.randn(Bt, 3, S, S, device=dev).clamp_(-1, 1), labels=torch.randint(1, cfg["label_dim"], (Bt, S, S), device=dev))
+
+    def iteration():
+        return ts.train_iteration(G, D, og, od, batch, cfg)
+
+    ms_it = timed(iteration, 2, warmup=1)
+    abi.TIMING = []
+    torch.cuda.synchronize()
+    iteration()
+    torch.cuda.synchronize()
+    per = {}
+    for name, s_, e_ in abi.TIMING:
+        d = per.setdefault(name, [0.0, 0])
+        d[0] += s_.elapsed_time(e_)
+        d[1] += 1
+    abi.TIMING = None
+    out["train_iteration_fp32x3"] = {"batch": Bt, "ms": ms_it, "images_per_s": Bt / ms_it * 1e3,
+                                     "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                                     "library_kernel_ms": sum(v[0] for v in per.values()),
                                      "kernels_ms": {k: [round(v[0], 3), v[1]] for k, v in sorted(per.items(), key=lambda t: -t[1][0])}}
     print(json.dumps(out, indent=1))
 
