@@ -35,7 +35,7 @@ def segmentation_loss(segments, gt, label_dim, prior_weights=None):
 def make_optimizers(G, D, cfg):
     """Adam with the curriculum's betas / learning rates (phase_trainer.py:57-76; the per-group multipliers of the
     generator are the trainer's business and do not change the cost of a step)."""
-    betas = tuple(cfg.get("betas", (0, 0.9)))
+    betas = tuple(float(b) for b in cfg.get("betas", (0, 0.9)))
     og = torch.optim.Adam(G.parameters(), lr=cfg.get("gen_lr", 5e-5), betas=betas)
     od = torch.optim.Adam(D.parameters(), lr=cfg.get("disc_lr", 2e-4), betas=betas)
     return og, od
