@@ -41,6 +41,25 @@ def make_optimizers(G, D, cfg):
     return og, od
 
 
+def average_gradients(module, group=None):
+    """Data parallelism: the kernels' parameter gradients are written by hand (`.grad` side effects of the autograd
+    functions), so DistributedDataParallel's reducer hooks never see them; average them explicitly, one flat
+    NCCL all-reduce per call (19.6 MB for G, 105.8 MB for D)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
 def discriminator_step(G, D, opt_d, z, cond, real_images, real_labels, cfg):
     opt_d.zero_grad(set_to_none=True)
     with torch.no_grad():
@@ -52,6 +71,7 @@ def discriminator_step(G, D, opt_d, z, cond, real_images, real_labels, cfg):
     loss = (segmentation_loss(out_real["segments"], real_labels, L)
             + segmentation_loss(out_fake["segments"], torch.zeros_like(real_labels), L)) * cfg["segmentation_lambda"]
     loss.backward()
+    average_gradients(D)
     torch.nn.utils.clip_grad_norm_(D.parameters(), cfg["grad_clip"])
     opt_d.step()
     return loss.detach()
@@ -70,6 +90,7 @@ def generator_step(G, D, opt_g, z, cond, labels, cfg):
     finally:
         for p, f in zip(D.parameters(), flags):
             p.requires_grad_(f)
+    average_gradients(G)
     torch.nn.utils.clip_grad_norm_(G.parameters(), cfg["grad_clip"])
     opt_g.step()
     return loss.detach()

@@ -352,6 +352,111 @@ def run_gpu(args, pkg):
     _leave(world, G)
 
 
+def run_train(args, pkg):
+    """--workload C3: one G+D training iteration (discriminator step, generator step) per step, BASELINE.json's second
+    metric.  Weak scaling over ranks (own batch per rank, gradients averaged over NCCL, SyncBatchNorm statistics
+    all-reduced inside the generator)."""
+    import torch.distributed as dist
+    abi = importlib.import_module("3dhumangan_b200.abi")
+    gen = importlib.import_module("3dhumangan_b200.modules.generator")
+    disc = importlib.import_module("3dhumangan_b200.modules.discriminator")
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    abi.require_device()
+    cfg = workload_cfg(pkg, "C2")
+    cfg["nerf_noise"] = 0.5                      # SURVEY.md §8d: C3 trains with sigma noise
+    B = args.batch
+    torch.manual_seed(0)
+    G = gen.Map3DGenerator(**cfg).to(dev).train()
+    G.set_device(dev)
+    D = disc.UNetDiscriminator(**cfg).to(dev).train()
+    og, od = ts.make_optimizers(G, D, cfg)
+    kw = dict(cfg, hg_precision=args.precision)
+    Hg, Wg = cfg["gen_height"], cfg["gen_width"]
+    gcpu = torch.Generator().manual_seed(5 + rank)
+    host = dict(z_d=torch.randn(B, cfg["latent_dim"], generator=gcpu), z_g=torch.randn(B, cfg["latent_dim"], generator=gcpu),
+                images=torch.randn(B, 3, Hg, Wg, generator=gcpu).clamp_(-1, 1),
+                labels=torch.randint(1, cfg["label_dim"], (B, Hg, Wg), generator=gcpu))
+    host = {k: v.pin_memory() for k, v in host.items()}
+    cond_h = {k: v.pin_memory() for k, v in pkg.synthetic.make_conditions(B, seed=1 + rank).items()}
+    h2d = sum(v.numel() * v.element_size() for v in list(host.values()) + list(cond_h.values()))
+    resident = {k: v.to(dev) for k, v in host.items()}
+    resident["cond"] = {k: v.to(dev) for k, v in cond_h.items()}
+    loss_h = torch.empty(2).pin_memory()
+
+    def step_resident():
+        return ts.train_iteration(G, D, og, od, resident, kw)
+
+    def step_e2e():
+        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        batch["cond"] = {k: v.to(dev, non_blocking=True) for k, v in cond_h.items()}
+        d, g = ts.train_iteration(G, D, og, od, batch, kw)
+        loss_h.copy_(torch.stack([d, g]), non_blocking=True)
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    abi.LAUNCHES = 0
+    ms_total = timed(step_resident, args.steps)
+    launches = abi.LAUNCHES
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, args.steps)
+    abi.TIMING = []
+    torch.cuda.synchronize()
+    step_resident()
+    torch.cuda.synchronize()
+    per = {}
+    for name, s_, e_ in abi.TIMING:
+        d = per.setdefault(name, [0.0, 0])
+        d[0] += s_.elapsed_time(e_)
+        d[1] += 1
+    abi.TIMING = None
+    if rank != 0:
+        _leave(world, G)
+        return
+    imgs = B * world * args.steps
+    line = {
+        "metric": "images_per_sec_GD_train_step_512x512", "value": imgs / (ms_total / 1e3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.precision == "fp32x3" else "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"C3: one discriminator step + one generator step (segmentation loss, R1 weight 0 as in configs/map3d.py:98-191), "
+                               f"batch {B}/GPU, 512x512, render 96x96, 32 samples/ray, hidden 256, Adam, grad clip 1, random init, synthetic data",
+                   "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single GPU",
+                   "l2": "activations >> 126 MB L2: no flush needed", "precision": args.precision, "launch": "eager"},
+        "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None,
+        "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+        "kernels": {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])},
+    }
+    print(json.dumps(line), flush=True)
+    _leave(world, G)
+
+
 def _leave(world, G):
     """End a multi-rank run without tearing NCCL down: destroying a communicator whose kernels are still referenced
     by live CUDA graphs blocks, so drop the graphs, drain the device and leave the process directly."""
@@ -370,7 +475,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C2", "C2native", "C5", "tiny"])
+    ap.add_argument("--workload", default="C2", choices=["C2", "C2native", "C5", "tiny", "C3"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--precision", default=os.environ.get("HG3D_PRECISION", "fp32x3"), choices=["fp32x3", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -378,7 +483,13 @@ def main():
     args = ap.parse_args()
     pkg = importlib.import_module("3dhumangan_b200")
     if args.impl == "reference":
+        if args.workload == "C3":
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times the generator forward (C2); a CPU training "
+                                                                     "iteration at 512x512 does not fit a bounded sample"}))
+            return
         run_reference(args, pkg)
+    elif args.workload == "C3":
+        run_train(args, pkg)
     else:
         run_gpu(args, pkg)
 

@@ -67,3 +67,32 @@ def test_bench_reference_arm_under_torchrun_two_ranks():
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "images/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["higher_is_better"] is True and d["metric"] == "images_per_sec_G_fwd_512x512"
+
+
+def _avg_worker(rank, world, port_, q):
+    import importlib, os, torch, torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    m = torch.nn.Linear(3, 2)
+    for i, p in enumerate(m.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    ts.average_gradients(m)
+    q.put((rank, [float(p.grad.flatten()[0]) for p in m.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_average_gradients_gloo():
+    """The explicit gradient averaging that stands in for DDP's reducer hooks (train_step.average_gradients)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port_ = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_avg_worker, args=(r, 2, port_, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0] == res[1] == [1.5, 3.0]
