@@ -54,10 +54,12 @@ SIGNATURES = {
     "hg_spade_pixel_pre": (c_int, [c_void_p, c_long, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "hg_spade_pixel_mod_bwd": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "hg_bilinear_adjoint": (c_int, [c_void_p, c_void_p, c_long] + [c_int] * 5 + [c_void_p]),
-    "hg_conv2d_wgrad_tap": (c_int, [c_void_p] * 5 + [c_int] * 12 + [c_void_p]),
+    "hg_conv2d_wgrad_workspace_bytes": (c_size_t, []),
+    "hg_conv2d_wgrad_taps": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p, c_void_p, c_int, c_void_p]),
     "hg_synth_input_bwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p]),
     "hg_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_bias_act_grad": (c_int, [c_void_p] * 6 + [c_long, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    "hg_resample2x": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_void_p]),
     "hg_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 14 + [c_float, c_void_p]),
     "hg_conv2d": (c_int, [c_void_p, c_int, c_void_p, c_int] + [c_int] * 6 + [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
                               c_void_p, c_int, c_void_p]),
@@ -415,36 +417,57 @@ def conv2d(x1, wimg, Cout, Nb, *, ksize, H, W, x2=None, up2=False, pre_lrelu=Fal
     return out
 
 
+_CONV_WS = {}
+
+
 def conv2d_wgrad(dy, x, ksize, passes=3):
-    """dW [Cout,Cin,k,k], dbias [Cout] of a stride-1 'same' convolution (csrc/dconv_bwd.cu): one launch per tap and per
-    (256 output, 256 input)-channel chunk."""
+    """dW [Cout,Cin,k,k], dbias [Cout] of a stride-1 'same' convolution (csrc/dconv_bwd.cu): one launch per
+    (256 output, 256 input)-channel chunk and per group of taps that fits the 512 TMEM columns."""
+    import ctypes
     B, Cout, H, W = dy.shape
     Cin = x.shape[1]
     dev = dy.device
-    ws = _WGRAD_WS.get(dev)
+    ws = _CONV_WS.get(dev)
     if ws is None:
-        ws = _WGRAD_WS[dev] = torch.empty(int(lib().hg_spade_bwd_wgrad_workspace_bytes()) // 4, dtype=torch.float32, device=dev)
+        ws = _CONV_WS[dev] = torch.empty(int(lib().hg_conv2d_wgrad_workspace_bytes()) // 4, dtype=torch.float32, device=dev)
     dW = torch.empty(Cout, Cin, ksize, ksize, dtype=torch.float32, device=dev)
     db = torch.empty(Cout, dtype=torch.float32, device=dev)
     pad = ksize // 2
+    taps = [(ky, kx) for ky in range(ksize) for kx in range(ksize)]
     dy, x = dy.contiguous(), x.contiguous()
     for co0 in range(0, Cout, 256):
         nco = min(256, Cout - co0)
+        nmh = 2 if nco > 128 else 1
         for ci0 in range(0, Cin, 256):
             nci = min(256, Cin - ci0)
             nq = (nci + 31) // 32 * 32
-            for ky in range(ksize):
-                for kx in range(ksize):
-                    dw = torch.empty(256, nq, dtype=torch.float32, device=dev)
-                    first = ci0 == 0 and ky == 0 and kx == 0
-                    dbt = torch.empty(256, dtype=torch.float32, device=dev) if first else None
-                    with torch.cuda.device_of(dy):
-                        call("hg_conv2d_wgrad_tap", ptr(dy), ptr(x), ptr(dw), ptr(dbt), ptr(ws), B, H, W, Cout, Cin, co0, nco,
-                             ci0, nci, ky - pad, kx - pad, passes, stream())
-                    dW[co0:co0 + nco, ci0:ci0 + nci, ky, kx] = dw[:nco, :nci]
-                    if first:
-                        db[co0:co0 + nco] = dbt[:nco]
+            per = max(1, 512 // (nmh * nq))
+            for t0 in range(0, len(taps), per):
+                grp = taps[t0:t0 + per]
+                n = len(grp)
+                oy = (ctypes.c_int * n)(*[ky - pad for ky, _ in grp])
+                ox = (ctypes.c_int * n)(*[kx - pad for _, kx in grp])
+                dw = torch.empty(n, 256, nq, dtype=torch.float32, device=dev)
+                first = ci0 == 0 and t0 == 0
+                dbt = torch.empty(256, dtype=torch.float32, device=dev) if first else None
+                with torch.cuda.device_of(dy):
+                    call("hg_conv2d_wgrad_taps", ptr(dy), ptr(x), ptr(dw), ptr(dbt), ptr(ws), B, H, W, Cout, Cin, co0, nco,
+                         ci0, nci, n, ctypes.cast(oy, c_void_p), ctypes.cast(ox, c_void_p), passes, stream())
+                for i, (ky, kx) in enumerate(grp):
+                    dW[co0:co0 + nco, ci0:ci0 + nci, ky, kx] = dw[i, :nco, :nci]
+                if first:
+                    db[co0:co0 + nco] = dbt[:nco]
     return dW, db
+
+
+def resample2x(x, up, scale):
+    """[B,C,H,W] -> 2x2 pooled (up=False: scale * block sum) or nearest up-sampled (up=True: scale * x)."""
+    B, C, H, W = x.shape
+    y = torch.empty(B, C, H * 2, W * 2, dtype=torch.float32, device=x.device) if up else \
+        torch.empty(B, C, H // 2, W // 2, dtype=torch.float32, device=x.device)
+    with torch.cuda.device_of(x):
+        call("hg_resample2x", ptr(x), ptr(y), B * C, H, W, int(bool(up)), float(scale), stream())
+    return y
 
 
 def pool_add(a, pool_a, b=None, pool_b=False):

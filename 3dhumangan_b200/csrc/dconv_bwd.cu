@@ -1,5 +1,6 @@
 // Weight gradient of the discriminator's 3x3 / 1x1 convolutions (autograd through nn.Conv2d in
-// lib/discriminators/unet_discriminators.py:21-38), one launch per filter tap and per 256-channel chunk:
+// lib/discriminators/unet_discriminators.py:21-38), one launch per GROUP of filter taps and per 256-channel chunk
+// (as many taps as fit the 512 TMEM columns: ntaps * M-halves * ceil32(Cin chunk) <= 512, so dy is read once per group):
 //     dW[co, ci, ky, kx] = sum_{b,h,w} dy[b, co, h, w] * x[b, ci, h + ky - pad, w + kx - pad]
 // Same machine as the SPADE weight gradient (csrc/synth_bwd.cu): K = pixels, both operands are K-major as stored
 // (NCHW planes are contiguous along W), the operand warps convert rows of 64 pixels into bf16 hi/lo SW128 images --
@@ -22,10 +23,11 @@ struct ConvWgradArgs {
   int B, H, W, Cout, Cin;
   int co0, nco;          // rows of dy handled by this launch (nco <= 256)
   int ci0, nci, nq;      // rows of x (nci valid, nq = nci rounded up to 32, <= 256)
-  int oy, ox;            // tap shift: x is read at (h + oy, w + ox)
+  int ntaps;             // taps of this launch; tap t reads x at (h + oy[t], w + ox[t])
+  int oy[9], ox[9];
 };
 
-enum { DW_FULL = 0, DW_EMPTY = 1, DW_DONE = 2 };
+enum { DW_AFULL = 0, DW_AEMPTY = 1, DW_BFULL = 2, DW_BEMPTY = 3, DW_DONE = 4 };
 
 template <int kPasses>
 __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs a) {
@@ -39,8 +41,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(bars + DW_FULL, 8);
-    mbar_init(bars + DW_EMPTY, 1);
+    mbar_init(bars + DW_AFULL, 8);
+    mbar_init(bars + DW_AEMPTY, 1);
+    mbar_init(bars + DW_BFULL, 8);
+    mbar_init(bars + DW_BEMPTY, 1);
     mbar_init(bars + DW_DONE, 1);
     fence_mbar_init();
   }
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
     float bsum[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
-    uint32_t chunk = 0;
+    uint32_t chunk = 0, bcnt = 0;
     for (int it = 0; it < count; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int b = tile / T, ti = tile - b * T;
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
             }
           }
         }
-        mbar_wait_sleep(bars + DW_EMPTY, (chunk & 1) ^ 1);
+        mbar_wait_sleep(bars + DW_AEMPTY, (chunk & 1) ^ 1);
 #pragma unroll
         for (int st = 0; st < 8; ++st) {
           if (st >= nmh * 4) break;
@@ -100,36 +104,45 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
           bsum[st] += ((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7]));
           store_a8<kPasses == 3>(a_hi, a_lo, st * 32 + rsub, sub * 8, y);
         }
-        // ---- x rows through the tap shift (zero padding outside the image)
-        int hh[8], ww[8];
-        bool ok[8];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + DW_AFULL);
+        // ---- x rows through each tap's shift (zero padding outside the image); re-reads hit L1/L2
+        int ph[8], pw[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int g = g0 + j;
-          const int h = g / a.W, w = g - h * a.W;
-          hh[j] = h + a.oy;
-          ww[j] = w + a.ox;
-          ok[j] = j < nvalid && hh[j] >= 0 && hh[j] < a.H && ww[j] >= 0 && ww[j] < a.W;
+          ph[j] = g / a.W;
+          pw[j] = g - ph[j] * a.W;
         }
-        const int shift = a.oy * a.W + a.ox;
+#pragma unroll 1
+        for (int t = 0; t < a.ntaps; ++t, ++bcnt) {
+          const int oy = a.oy[t], ox = a.ox[t];
+          bool ok[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ok[j] = j < nvalid && ph[j] + oy >= 0 && ph[j] + oy < a.H && pw[j] + ox >= 0 && pw[j] + ox < a.W;
+          const int shift = oy * a.W + ox;
+          mbar_wait_sleep(bars + DW_BEMPTY, (bcnt & 1) ^ 1);
 #pragma unroll 2
-        for (int st = 0; st < 8; ++st) {
-          if (st >= nst_b) break;
-          const int row = st * 32 + rsub;
-          float y[8];
-          if (row < a.nci) {
-            const float* src = xbase + static_cast<long>(row) * HW + g0 + shift;
+          for (int st = 0; st < 8; ++st) {
+            if (st >= nst_b) break;
+            const int row = st * 32 + rsub;
+            float y[8];
+            if (row < a.nci) {
+              const float* src = xbase + static_cast<long>(row) * HW + g0 + shift;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = ok[j] ? __ldg(src + j) : 0.f;
-          } else {
+              for (int j = 0; j < 8; ++j) y[j] = ok[j] ? __ldg(src + j) : 0.f;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = 0.f;
+              for (int j = 0; j < 8; ++j) y[j] = 0.f;
+            }
+            store_a8<kPasses == 3>(b_hi, b_lo, row, sub * 8, y);
           }
-          store_a8<kPasses == 3>(b_hi, b_lo, row, sub * 8, y);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars + DW_BFULL);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + DW_FULL);
       }
     }
 #pragma unroll
@@ -142,49 +155,56 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
     }
   } else if (lane == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, a.nq);
-    uint32_t chunk = 0;
+    uint32_t chunk = 0, bcnt = 0;
     for (int it = 0; it < count; ++it)
       for (int kc = 0; kc < 2; ++kc, ++chunk) {
-        mbar_wait_sleep(bars + DW_FULL, chunk & 1);
-        tc_fence_after();
-        for (int mh = 0; mh < nmh; ++mh) {
-          const uint32_t d = tmem + mh * 256;
-          const uint32_t ah = smem_u32(a_hi) + mh * (kDwImg / 2), al = smem_u32(a_lo) + mh * (kDwImg / 2);
-          umma_k64(d, ah, smem_u32(b_hi), idesc, chunk > 0);
-          if (kPasses == 3) {
-            umma_k64(d, al, smem_u32(b_hi), idesc, true);
-            umma_k64(d, ah, smem_u32(b_lo), idesc, true);
+        mbar_wait_sleep(bars + DW_AFULL, chunk & 1);
+        for (int t = 0; t < a.ntaps; ++t, ++bcnt) {
+          mbar_wait_sleep(bars + DW_BFULL, bcnt & 1);
+          tc_fence_after();
+          for (int mh = 0; mh < nmh; ++mh) {
+            const uint32_t d = tmem + (t * nmh + mh) * a.nq;
+            const uint32_t ah = smem_u32(a_hi) + mh * (kDwImg / 2), al = smem_u32(a_lo) + mh * (kDwImg / 2);
+            umma_k64(d, ah, smem_u32(b_hi), idesc, chunk > 0);
+            if (kPasses == 3) {
+              umma_k64(d, al, smem_u32(b_hi), idesc, true);
+              umma_k64(d, ah, smem_u32(b_lo), idesc, true);
+            }
           }
+          umma_commit(bars + DW_BEMPTY);
         }
-        umma_commit(bars + DW_EMPTY);
+        umma_commit(bars + DW_AEMPTY);
       }
     umma_commit(bars + DW_DONE);
   }
   if (warp < 4) {
-    float* dst = a.part_w + static_cast<long>(blockIdx.x) * 256 * a.nq;
+    float* dst0 = a.part_w + static_cast<long>(blockIdx.x) * a.ntaps * 256 * a.nq;
     if (count > 0) {
       mbar_wait_sleep(bars + DW_DONE, 0);
       tc_fence_after();
-      for (int mh = 0; mh < 2; ++mh) {
-        const int co = mh * 128 + warp * 32 + lane;
-        for (int cg = 0; cg < (a.nq >> 5); ++cg) {
-          uint32_t raw[32];
-          if (mh < nmh) {
-            tmem_ld32(tmem + mh * 256 + (static_cast<uint32_t>(warp * 32) << 16) + cg * 32, raw);
-            tmem_ld_wait();
-          } else {
+      for (int t = 0; t < a.ntaps; ++t) {
+        float* dst = dst0 + static_cast<long>(t) * 256 * a.nq;
+        for (int mh = 0; mh < 2; ++mh) {
+          const int co = mh * 128 + warp * 32 + lane;
+          for (int cg = 0; cg < (a.nq >> 5); ++cg) {
+            uint32_t raw[32];
+            if (mh < nmh) {
+              tmem_ld32(tmem + (t * nmh + mh) * a.nq + (static_cast<uint32_t>(warp * 32) << 16) + cg * 32, raw);
+              tmem_ld_wait();
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) raw[j] = 0u;
+              for (int j = 0; j < 32; ++j) raw[j] = 0u;
+            }
+            float4* o = reinterpret_cast<float4*>(dst + static_cast<long>(co) * a.nq + cg * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                                 __uint_as_float(raw[4 * j + 3]));
           }
-          float4* o = reinterpret_cast<float4*>(dst + static_cast<long>(co) * a.nq + cg * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
-                               __uint_as_float(raw[4 * j + 3]));
         }
       }
     } else {
-      for (int i = threadIdx.x; i < 256 * a.nq; i += 128) dst[i] = 0.f;
+      for (int i = threadIdx.x; i < a.ntaps * 256 * a.nq; i += 128) dst0[i] = 0.f;
     }
   }
   if (count == 0 && warp >= 4 && warp < 8) {
@@ -214,25 +234,39 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ part_w, const
 
 extern "C" {
 
-size_t hg_spade_bwd_wgrad_workspace_bytes(void);
+// worst case per CTA: ntaps * 256 * nq floats with ntaps * nq <= 512 (one M half), plus the bias partial
+size_t hg_conv2d_wgrad_workspace_bytes(void) {
+  return static_cast<size_t>(hg::num_sms()) * (512 * 256 + 256) * sizeof(float);
+}
 
-int hg_conv2d_wgrad_tap(const float* dy, const float* x, float* dw, float* dbias, void* workspace, int B, int H, int W,
-                        int Cout, int Cin, int co0, int nco, int ci0, int nci, int oy, int ox, int passes, void* stream) {
-  HG_REQUIRE(dy && x && dw && workspace, "hg_conv2d_wgrad_tap: null pointer");
-  HG_REQUIRE(B > 0 && H > 0 && W > 0 && (H * W) % 4 == 0, "hg_conv2d_wgrad_tap: bad image shape (H*W must be a multiple of 4)");
-  HG_REQUIRE(nco >= 1 && nco <= 256 && co0 >= 0 && co0 + nco <= Cout, "hg_conv2d_wgrad_tap: bad output-channel chunk");
-  HG_REQUIRE(nci >= 1 && nci <= 256 && ci0 >= 0 && ci0 + nci <= Cin, "hg_conv2d_wgrad_tap: bad input-channel chunk");
-  HG_REQUIRE(oy >= -1 && oy <= 1 && ox >= -1 && ox <= 1, "hg_conv2d_wgrad_tap: tap shift out of range");
-  HG_REQUIRE(passes == 1 || passes == 3, "hg_conv2d_wgrad_tap: passes must be 1 or 3");
+int hg_conv2d_wgrad_taps(const float* dy, const float* x, float* dw, float* dbias, void* workspace, int B, int H, int W,
+                         int Cout, int Cin, int co0, int nco, int ci0, int nci, int ntaps, const int* oy, const int* ox,
+                         int passes, void* stream) {
+  HG_REQUIRE(dy && x && dw && workspace && oy && ox, "hg_conv2d_wgrad_taps: null pointer");
+  HG_REQUIRE(B > 0 && H > 0 && W > 0 && (H * W) % 4 == 0, "hg_conv2d_wgrad_taps: bad image shape (H*W must be a multiple of 4)");
+  HG_REQUIRE(nco >= 1 && nco <= 256 && co0 >= 0 && co0 + nco <= Cout, "hg_conv2d_wgrad_taps: bad output-channel chunk");
+  HG_REQUIRE(nci >= 1 && nci <= 256 && ci0 >= 0 && ci0 + nci <= Cin, "hg_conv2d_wgrad_taps: bad input-channel chunk");
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_conv2d_wgrad_taps: passes must be 1 or 3");
   HG_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
-             "hg_conv2d_wgrad_tap: dy / workspace must be 16-byte aligned");
+             "hg_conv2d_wgrad_taps: dy / workspace must be 16-byte aligned");
   const int nq = (nci + 31) / 32 * 32;
+  const int nmh = nco > 128 ? 2 : 1;
+  HG_REQUIRE(ntaps >= 1 && ntaps <= 9 && ntaps * nmh * nq <= 512,
+             "hg_conv2d_wgrad_taps: %d taps x %d M-halves x %d columns do not fit the 512 TMEM columns", ntaps, nmh, nq);
+  hg::ConvWgradArgs a{};
+  for (int t = 0; t < ntaps; ++t) {
+    HG_REQUIRE(oy[t] >= -1 && oy[t] <= 1 && ox[t] >= -1 && ox[t] <= 1, "hg_conv2d_wgrad_taps: tap shift out of range");
+    a.oy[t] = oy[t];
+    a.ox[t] = ox[t];
+  }
   const int T = (H * W + 127) / 128;
   const int tiles = B * T;
   const int grid = tiles < hg::num_sms() ? tiles : hg::num_sms();
   float* part_w = static_cast<float*>(workspace);
-  float* part_b = part_w + static_cast<size_t>(hg::num_sms()) * 256 * 256;
-  hg::ConvWgradArgs a{dy, x, part_w, part_b, B, H, W, Cout, Cin, co0, nco, ci0, nci, nq, oy, ox};
+  float* part_b = part_w + static_cast<size_t>(hg::num_sms()) * 512 * 256;
+  a.dy = dy; a.x = x; a.part_w = part_w; a.part_b = part_b;
+  a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.Cin = Cin;
+  a.co0 = co0; a.nco = nco; a.ci0 = ci0; a.nci = nci; a.nq = nq; a.ntaps = ntaps;
   auto st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (passes == 3) {
@@ -242,12 +276,13 @@ int hg_conv2d_wgrad_tap(const float* dy, const float* x, float* dw, float* dbias
     e = cudaFuncSetAttribute(hg::conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kDwSmemBytes);
     if (e == cudaSuccess) hg::conv_wgrad_kernel<1><<<grid, hg::kDwThreads, hg::kDwSmemBytes, st>>>(a);
   }
-  if (e != cudaSuccess) { hg::set_error("hg_conv2d_wgrad_tap: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; }
-  int rc = hg::check_launch("hg_conv2d_wgrad_tap");
+  if (e != cudaSuccess) { hg::set_error("hg_conv2d_wgrad_taps: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; }
+  int rc = hg::check_launch("hg_conv2d_wgrad_taps");
   if (rc) return rc;
-  // dw [256, nq] (rows >= nco and columns >= nci are zero), dbias [256]
-  hg::conv_wgrad_reduce_kernel<<<(256 * nq + 255) / 256, 256, 0, st>>>(part_w, part_b, grid, 256 * nq, dw, dbias);
-  return hg::check_launch("hg_conv2d_wgrad_tap(reduce)");
+  // dw [ntaps, 256, nq] (rows >= nco and columns >= nci are zero), dbias [256]
+  const int nw = ntaps * 256 * nq;
+  hg::conv_wgrad_reduce_kernel<<<(nw + 255) / 256, 256, 0, st>>>(part_w, part_b, grid, nw, dw, dbias);
+  return hg::check_launch("hg_conv2d_wgrad_taps(reduce)");
 }
 
 }  // extern "C"

@@ -189,6 +189,43 @@ __global__ void __launch_bounds__(128) upfirdn2d_kernel(const float* __restrict_
   }
 }
 
+
+// 2x2 average pooling / nearest-neighbour 2x up-sampling with a scale factor (each is the other's adjoint up to the
+// scale: d avgpool = 0.25 * up(dy), d up = 4 * avgpool(dy)).  The discriminator's ResBlocks use them between
+// convolutions (unet_discriminators.py:30,60-70); pure streaming, one float2 / float4 per lane.
+__global__ void __launch_bounds__(256) pool2x_kernel(const float* __restrict__ x, float* __restrict__ y, long planes,
+                                                     int oH, int oW, float scale) {
+  const int ow2 = oW >> 1;                              // output float2 per row (oW even)
+  const long total = planes * oH * ow2;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int cx = static_cast<int>(i % ow2);
+    const long r = i / ow2;                             // plane * oH + oy
+    const long plane = r / oH;
+    const int oy = static_cast<int>(r - plane * oH);
+    const float* src = x + (plane * (2 * oH) + 2 * oy) * (2L * oW) + 4 * cx;
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(src + 2 * oW));
+    __stcs(reinterpret_cast<float2*>(y + r * oW) + cx, make_float2(((a.x + a.y) + (b.x + b.y)) * scale, ((a.z + a.w) + (b.z + b.w)) * scale));
+  }
+}
+
+__global__ void __launch_bounds__(256) up2x_kernel(const float* __restrict__ x, float* __restrict__ y, long planes, int iH,
+                                                   int iW, float scale) {
+  const int iw2 = iW >> 1;
+  const long total = planes * iH * iw2;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int cx = static_cast<int>(i % iw2);
+    const long r = i / iw2;                             // plane * iH + iy
+    const long plane = r / iH;
+    const int iy = static_cast<int>(r - plane * iH);
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(x + r * iW) + cx);
+    const float4 o = make_float4(v.x * scale, v.x * scale, v.y * scale, v.y * scale);
+    float* dst = y + (plane * (2 * iH) + 2 * iy) * (2L * iW) + 4 * cx;
+    __stcs(reinterpret_cast<float4*>(dst), o);
+    __stcs(reinterpret_cast<float4*>(dst + 2 * iW), o);
+  }
+}
+
 }  // namespace hg
 
 extern "C" {
@@ -264,6 +301,26 @@ int hg_upfirdn2d(const float* x, const float* f, float* y, int NC, int inH, int 
   hg::upfirdn2d_kernel<<<grid, 128, fH * fW * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       x, f, y, NC, inH, inW, outH, outW, fH, fW, upx, upy, downx, downy, padx0, pady0, flip_filter, gain);
   return hg::check_launch("hg_upfirdn2d");
+}
+
+int hg_resample2x(const float* x, float* y, long planes, int inH, int inW, int up, float scale, void* stream) {
+  HG_REQUIRE(x && y && planes > 0 && inH > 0 && inW > 0, "hg_resample2x: bad arguments");
+  HG_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "hg_resample2x: tensors must be 16-byte aligned");
+  auto st = static_cast<cudaStream_t>(stream);
+  long total;
+  if (up) {
+    HG_REQUIRE(inW % 2 == 0, "hg_resample2x: up-sampling needs an even input width (got %d)", inW);
+    total = planes * inH * (inW / 2);
+  } else {
+    HG_REQUIRE(inH % 2 == 0 && inW % 4 == 0, "hg_resample2x: pooling needs even height and a width that is a multiple of 4 (got %dx%d)", inH, inW);
+    total = planes * (inH / 2) * (inW / 4);
+  }
+  long blocks = (total + 255) / 256;
+  const long cap = static_cast<long>(hg::num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  if (up) hg::up2x_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, y, planes, inH, inW, scale);
+  else hg::pool2x_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, y, planes, inH / 2, inW / 2, scale);
+  return hg::check_launch("hg_resample2x");
 }
 
 }  // extern "C"

@@ -6,7 +6,7 @@ ops, so that first-order gradients w.r.t. images (generator step) and parameters
 `loss.backward()`:
 
     convolution      `Conv2dSame`  forward `hg_conv2d`, data gradient `hg_conv2d` with the rotated / transposed filter,
-                                   weight gradient `hg_conv2d_wgrad_tap` (tcgen05, one launch per tap)
+                                   weight gradient `hg_conv2d_wgrad_taps` (tcgen05, one launch per tap)
     LeakyReLU        `ops.bias_act` (hg_bias_act / hg_bias_act_grad)
     avg-pool / nearest up-sample   `ops.upfirdn2d` with a 2x2 box filter (its backward is another upfirdn pass)
     spectral norm    torch autograd on W / sigma (one power iteration per training forward, buffers in place)
@@ -76,14 +76,32 @@ def _lrelu(x, rec=None):
     return _ba.bias_act(x, None, act="lrelu", alpha=0.2, gain=1.0)
 
 
+class _Resample2x(torch.autograd.Function):
+    """avg_pool2d(x, 2) (up=False) / nearest 2x up-sample (up=True) on `hg_resample2x`; each is the other's adjoint up to
+    a factor, so the backward is the other direction of the same kernel (and differentiable again)."""
+
+    @staticmethod
+    def forward(ctx, x, up, scale):
+        ctx.up, ctx.scale = up, scale
+        return abi.resample2x(x.float().contiguous(), up, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        # y = s * U x  =>  dx = s * U^T dy with U^T = block sum;   y = s * P x (block sum)  =>  dx = s * P^T dy = s * nearest(dy)
+        return _Resample2x.apply(dy, not ctx.up, ctx.scale), None, None
+
+
 def _pool(x):
-    f = torch.full((2, 2), 0.25, device=x.device)
-    return _uf.upfirdn2d(x, f, down=2)
+    W = x.shape[3]
+    if x.shape[2] % 2 or W % 4:          # odd sizes / tiny maps: the general resampler (a 2x2 box through upfirdn2d)
+        return _uf.upfirdn2d(x, torch.full((2, 2), 0.25, device=x.device), down=2)
+    return _Resample2x.apply(x, False, 0.25)
 
 
 def _up(x):
-    f = torch.ones(2, 2, device=x.device)
-    return _uf.upfirdn2d(x, f, up=2, padding=[1, 0, 1, 0])
+    if x.shape[3] % 2:
+        return _uf.upfirdn2d(x, torch.ones(2, 2, device=x.device), up=2, padding=[1, 0, 1, 0])
+    return _Resample2x.apply(x, True, 1.0)
 
 
 def _sn_weight(P, name, training, enabled, eps=1e-12):

@@ -193,13 +193,17 @@ int hg_spade_pixel_mod_bwd(const float* dpre, const float* x, long x_bstride, co
                            double* sums, int B, int C, int Hg, int Wg, void* stream);
 int hg_bilinear_adjoint(const float* da1, float* dp, long dp_stride, int B, int Hg, int Wg, int Rh, int Rw, void* stream);
 
-/* One tap of the weight gradient of a stride-1 "same" convolution over NCHW planes (autograd through nn.Conv2d,
- * unet_discriminators.py:21-38):  dw[r, c] = sum_{b,h,w} dy[b, co0+r, h, w] * x[b, ci0+c, h+oy, w+ox]  (zero outside the
- * image) for r < nco <= 256, c < nci <= 256; dw is [256, ceil32(nci)] (unused rows / columns zero), dbias [256] =
- * sum dy (NULL = skip).  A 3x3 filter is 9 calls (oy, ox in -1..1), larger channel counts are chunked by the caller.
- * workspace: hg_spade_bwd_wgrad_workspace_bytes(). */
-int hg_conv2d_wgrad_tap(const float* dy, const float* x, float* dw, float* dbias, void* workspace, int B, int H, int W,
-                        int Cout, int Cin, int co0, int nco, int ci0, int nci, int oy, int ox, int passes, void* stream);
+/* Weight gradient of a stride-1 "same" convolution over NCHW planes (autograd through nn.Conv2d,
+ * unet_discriminators.py:21-38), `ntaps` filter taps per launch:
+ *   dw[t, r, c] = sum_{b,h,w} dy[b, co0+r, h, w] * x[b, ci0+c, h+oy[t], w+ox[t]]   (zero outside the image)
+ * for r < nco <= 256, c < nci <= 256; dw is [ntaps, 256, ceil32(nci)] (unused rows / columns zero), dbias [256] = sum dy
+ * (NULL = skip).  ntaps * (nco > 128 ? 2 : 1) * ceil32(nci) <= 512 (TMEM columns); oy / ox are HOST arrays of shifts in
+ * -1..1; larger filters / channel counts are chunked by the caller (abi.conv2d_wgrad).
+ * workspace: hg_conv2d_wgrad_workspace_bytes() bytes of device memory. */
+size_t hg_conv2d_wgrad_workspace_bytes(void);
+int hg_conv2d_wgrad_taps(const float* dy, const float* x, float* dw, float* dbias, void* workspace, int B, int H, int W,
+                         int Cout, int Cin, int co0, int nco, int ci0, int nci, int ntaps, const int* oy, const int* ox,
+                         int passes, void* stream);
 /* Backward of hg_synth_input: dx [B,T,C,128] (gradient w.r.t. the batch-shared x0, per sample) -> dw [C,2], db [C]. */
 int hg_synth_input_bwd(const float* dx, const float* w, const float* bias, const float* ic, const float* jc, int B, int C,
                        int Hg, int Wg, float* dw, float* db, void* stream);
@@ -238,6 +242,11 @@ int hg_bias_act(const float* x, const float* b, float* y, long n, int stepB, int
 int hg_bias_act_grad(const float* g, const float* b, const float* xref, const float* yref, const float* dy, float* out,
                      long n, int stepB, int sizeB, int order, int act, float alpha, float gain, float clamp,
                      void* stream);
+
+/* 2x2 average pooling (up = 0: y[planes,H/2,W/2] = scale * sum of the 2x2 block) or nearest 2x up-sampling (up = 1:
+ * y[planes,2H,2W] = scale * x) -- F.avg_pool2d(x, 2) is scale 0.25, nn.Upsample(scale_factor=2) scale 1
+ * (unet_discriminators.py:30,60-70); each is the other's adjoint up to the scale. */
+int hg_resample2x(const float* x, float* y, long planes, int inH, int inW, int up, float scale, void* stream);
 
 /* Zero-insert up-sample, pad/crop, 2-D FIR, decimate   replaces upfirdn2d.cpp:16 / upfirdn2d.cu:29-375.
  * x [NC,inH,inW] -> y [NC,outH,outW]; f [fH,fW]; the filter is flipped unless flip_filter (conv2d is a correlation). */
