@@ -39,6 +39,26 @@ UNIT = "images/s"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout to the ONE JSON line: libraries write banners to file descriptor 1 (NCCL prints its version there at
+    NCCL_DEBUG=WARN/VERSION), so fd 1 is pointed at stderr for the rest of the process and the JSON line goes to a private
+    duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -118,7 +138,7 @@ def run_reference(args, pkg):
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def describe(cfg, name, batch):
@@ -348,7 +368,7 @@ def run_gpu(args, pkg):
         "cpu_baseline": cpu,
         "kernels": breakdown,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     _leave(world, G)
 
 
@@ -453,7 +473,7 @@ def run_train(args, pkg):
         "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
         "kernels": {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     _leave(world, G)
 
 
@@ -481,11 +501,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    claim_stdout()
     pkg = importlib.import_module("3dhumangan_b200")
     if args.impl == "reference":
         if args.workload == "C3":
-            print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times the generator forward (C2); a CPU training "
-                                                                     "iteration at 512x512 does not fit a bounded sample"}))
+            emit({"impl": "reference", "unavailable": "the CPU arm times the generator forward (C2); a CPU training "
+                                                       "iteration at 512x512 does not fit a bounded sample"})
             return
         run_reference(args, pkg)
     elif args.workload == "C3":
