@@ -64,12 +64,14 @@ def discriminator_step(G, D, opt_d, z, cond, real_images, real_labels, cfg):
     opt_d.zero_grad(set_to_none=True)
     with torch.no_grad():
         fake = G(z, cond, **cfg)["rgbs"]
-    real = real_images.detach().requires_grad_(True)            # the reference sets requires_grad for R1 (:388)
-    out_real = D(real, cond, alpha=1.0, **cfg)
-    out_fake = D(fake, cond, alpha=1.0, **cfg)
+    # The reference runs the discriminator twice (real, generated: phase_trainer.py:390,402).  It has no batch
+    # statistics, so one pass over the concatenated batch computes exactly the same outputs and gradients with half
+    # the launches (the low-resolution layers are launch-bound).
+    B = real_images.shape[0]
+    out = D(torch.cat([real_images.detach(), fake], 0), cond, alpha=1.0, **cfg)
     L = cfg["label_dim"]
-    loss = (segmentation_loss(out_real["segments"], real_labels, L)
-            + segmentation_loss(out_fake["segments"], torch.zeros_like(real_labels), L)) * cfg["segmentation_lambda"]
+    loss = (segmentation_loss(out["segments"][:B], real_labels, L)
+            + segmentation_loss(out["segments"][B:], torch.zeros_like(real_labels), L)) * cfg["segmentation_lambda"]
     loss.backward()
     average_gradients(D)
     torch.nn.utils.clip_grad_norm_(D.parameters(), cfg["grad_clip"])
