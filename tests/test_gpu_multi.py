@@ -69,3 +69,60 @@ def test_data_parallel_equals_single_gpu(tmp_path):
     assert r["e_running_var"] < 1e-4, r
     assert r["e_ranks"] < 1e-6, r
     assert r["e_gold"] < 1e-3, r
+
+
+def _grad_worker(rank, world, port_no, out_path):
+    """Generator gradients under data parallelism: each rank back-propagates the loss of its own sample (SyncBatchNorm
+    statistics and their gradients all-reduced inside forward / backward), gradients averaged with
+    `train_step.average_gradients`; must equal the single-GPU gradients of the mean loss over the whole batch."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from golden_util import generator_case, rel_l2
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    gen = importlib.import_module("3dhumangan_b200.modules.generator")
+    rng = importlib.import_module("3dhumangan_b200.rng")
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    cfg, params, cond, z, (u, noise), gold = generator_case("g_tiny_dense")     # B = 2
+    dev = torch.device("cuda", rank)
+    wgt = torch.randn(2, 3, cfg["gen_height"], cfg["gen_width"], generator=torch.Generator().manual_seed(3))
+
+    def run(sl, nb):
+        G = gen.Map3DGenerator(**cfg).to(dev)
+        G.load_state_dict(params)
+        G.set_device(dev)
+        G.train()
+        rng.draw_render_noise = lambda *a, **k: (u[sl].to(dev), noise[sl].to(dev))
+        out = G(z[sl].to(dev), {k: v[sl].to(dev) for k, v in cond.items()}, **cfg)
+        ((out["rgbs"] * wgt[sl].to(dev)).sum() / nb).backward()
+        return G
+
+    G = run(slice(rank, rank + 1), 1)
+    ts.average_gradients(G)
+    torch.cuda.synchronize()
+    dp = {n: p.grad.cpu() for n, p in G.named_parameters() if p.grad is not None}
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        G1 = run(slice(0, 2), 2)
+        errs = {}
+        for n, p in G1.named_parameters():
+            if p.grad is None or float(p.grad.norm()) == 0:
+                continue
+            errs[n] = rel_l2(dp[n], p.grad.cpu())
+        torch.save(errs, out_path)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_gradients_equal_single_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "grads.pt")
+    mp.spawn(_grad_worker, args=(2, 29900 + os.getpid() % 90, out), nprocs=2, join=True)
+    errs = torch.load(out)
+    assert len(errs) > 100
+    vals = sorted(errs.values())
+    # identical arithmetic up to summation order; LeakyReLU-mask flips (tests/test_gpu_synthesis_bwd.py) bound the tail
+    assert vals[len(vals) // 2] < 1e-3, vals[len(vals) // 2]
+    assert vals[-1] < 5e-2, sorted(errs.items(), key=lambda t: -t[1])[:5]
