@@ -7,7 +7,7 @@
 // tiles of 128 consecutive pixels): the 128 KB a CTA reads / writes per tile are CONTIGUOUS, and every
 // 32-channel slice of a tile is one contiguous 16 KB block (one cp.async.bulk).
 //
-// Per CTA (480 threads), persistent over tiles of 128 pixels of one image:
+// Per CTA (512 threads), persistent over tiles of 128 pixels of one image:
 //   warps 0-7   operand team: build the bf16 hi/lo A operand of the NEXT tile in a 2-slot ring of
 //               [128 x 64] K-major SW128 chunks (BN scale/shift, SPADE modulation, LeakyReLU fused)
 //   warps 8-11  epilogue team: drain the fp32 accumulator of the PREVIOUS tile from TMEM (warp 8+q owns lanes
@@ -31,6 +31,13 @@
 //                 materialised.  TMEM plan per tile t (R = half t&1, R' = the other, still being drained):
 //                 G1(gamma|beta, channels 0-127) -> R, G1(channels 128-255) -> R' once the epilogue of t-1 is
 //                 done, y chunks 0,1 <- R, conv accumulator -> R, y chunks 2,3 <- R'.
+//
+// The const-style kernel doubles as the library's blocked 1x1-convolution engine (runtime fields at the end of SpadeArgs):
+// K of 64..512 input channels from one or two sources, LeakyReLU / sine / identity operand transform, and -- template
+// flag kBwd -- the data-gradient form: the operand is the incoming gradient (optionally scaled per sample and channel),
+// the weight image is W^T and the epilogue multiplies by the activation derivative rebuilt from the forward input that
+// arrives through the residual ring, adds a rank-k term (the renderer's sigma / rgb heads) and accumulates the
+// per-(sample, channel) sums the BatchNorm / FiLM gradients need (DESIGN.md "Backward").
 //
 // Ring protocol note: every consumer warp of a staging ring waits for and releases EVERY slice in order
 // (only the owning column half reads it).  With per-half arrivals a slot of an odd-sized ring alternates
