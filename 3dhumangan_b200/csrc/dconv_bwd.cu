@@ -123,21 +123,26 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
           for (int j = 0; j < 8; ++j)
             ok[j] = j < nvalid && ph[j] + oy >= 0 && ph[j] + oy < a.H && pw[j] + ox >= 0 && pw[j] + ox < a.W;
           const int shift = oy * a.W + ox;
-          mbar_wait_sleep(bars + DW_BEMPTY, (bcnt & 1) ^ 1);
-#pragma unroll 2
+          // all loads of this tap first (registers only), so that they overlap the MMAs of the previous tap;
+          // the shared image is touched only after the EMPTY wait
+          float yq[8][8];
+#pragma unroll
           for (int st = 0; st < 8; ++st) {
-            if (st >= nst_b) break;
             const int row = st * 32 + rsub;
-            float y[8];
-            if (row < a.nci) {
+            if (st < nst_b && row < a.nci) {
               const float* src = xbase + static_cast<long>(row) * HW + g0 + shift;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) y[j] = ok[j] ? __ldg(src + j) : 0.f;
+              for (int j = 0; j < 8; ++j) yq[st][j] = ok[j] ? __ldg(src + j) : 0.f;
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) y[j] = 0.f;
+              for (int j = 0; j < 8; ++j) yq[st][j] = 0.f;
             }
-            store_a8<kPasses == 3>(b_hi, b_lo, row, sub * 8, y);
+          }
+          mbar_wait_sleep(bars + DW_BEMPTY, (bcnt & 1) ^ 1);
+#pragma unroll
+          for (int st = 0; st < 8; ++st) {
+            if (st >= nst_b) break;
+            store_a8<kPasses == 3>(b_hi, b_lo, st * 32 + rsub, sub * 8, yq[st]);
           }
           fence_proxy_async_smem();
           __syncwarp();
