@@ -144,3 +144,18 @@ def test_synthetic_conditions_are_consistent(pkg):
     assert (v - cond["vertices"]).abs().max() < 1e-4
     again = pkg.synthetic.make_conditions(2, seed=3)
     assert all(torch.equal(cond[k], again[k]) for k in cond)
+
+
+def test_segmentation_loss_matches_reference_trainer():
+    """train_step.segmentation_loss against values of the reference's own method (tests/golden/make_golden_loss.py)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_loss
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "seg_loss.npz"))
+    for i, (seg, gt, L) in enumerate(make_golden_loss.cases()):
+        s = seg.clone().requires_grad_(True)
+        loss = ts.segmentation_loss(s, gt, L)
+        loss.backward()
+        assert abs(float(loss) - gold["loss"][i]) < 1e-5 * max(1.0, abs(gold["loss"][i])), i
+        assert abs(float(s.grad.double().norm()) - gold["grad_norm"][i]) < 1e-5 * gold["grad_norm"][i], i
