@@ -108,8 +108,10 @@ def _grad_worker(rank, world, port_no, out_path):
     if rank == 0:
         G1 = run(slice(0, 2), 2)
         errs = {}
+        scale = max(float(p.grad.norm()) for p in G1.parameters() if p.grad is not None)
         for n, p in G1.named_parameters():
-            if p.grad is None or float(p.grad.norm()) == 0:
+            # analytic zeros (a conv bias in front of a BatchNorm) are rounding noise on both sides: skip them
+            if p.grad is None or float(p.grad.norm()) < 1e-5 * scale:
                 continue
             errs[n] = rel_l2(dp[n], p.grad.cpu())
         torch.save(errs, out_path)
