@@ -13,63 +13,62 @@ import torch
 import torch.nn as nn
 
 
-def _sn(conv, disable):
-    return conv if disable else nn.utils.spectral_norm(conv)
+def _conv(cin, cout, k, spectral):
+    layer = nn.Conv2d(cin, cout, k, stride=1, padding=k // 2)
+    return nn.utils.spectral_norm(layer) if spectral else layer
 
 
 class ResBlock(nn.Module):
-    """unet_discriminators.py:7-72 (parameter holder; index positions inside the Sequentials match
-    the reference so that keys read `conv1.1.*` / `conv1.2.*` / `conv2.1.*`)."""
+    """Parameter holder of one residual block (unet_discriminators.py:7-72).  The positions inside the Sequentials
+    fix the state_dict keys: `conv1.1.*` (down), `conv1.2.*` (up), `conv1.*` (first block), `conv2.1.*`."""
 
     def __init__(self, fin, fout, up_or_down, first=False, **kwargs):
         super().__init__()
-        self.up_or_down, self.first = up_or_down, first
-        self.learned_shortcut = fin != fout
-        dis = kwargs.get("disable_spectral_norm", False)
-        if first:
-            self.conv1 = _sn(nn.Conv2d(fin, fout, 3, 1, 1), dis)
-        elif up_or_down > 0:
-            self.conv1 = nn.Sequential(nn.LeakyReLU(0.2, False), nn.Upsample(scale_factor=2), _sn(nn.Conv2d(fin, fout, 3, 1, 1), dis))
-        else:
-            self.conv1 = nn.Sequential(nn.LeakyReLU(0.2, False), _sn(nn.Conv2d(fin, fout, 3, 1, 1), dis))
-        self.conv2 = nn.Sequential(nn.LeakyReLU(0.2, False), _sn(nn.Conv2d(fout, fout, 3, 1, 1), dis))
+        spectral = not kwargs.get("disable_spectral_norm", False)
+        self.up_or_down, self.first, self.learned_shortcut = up_or_down, first, fin != fout
+        head = _conv(fin, fout, 3, spectral)
+        if not first:
+            pre = [nn.LeakyReLU(0.2, False)] + ([nn.Upsample(scale_factor=2)] if up_or_down > 0 else [])
+            head = nn.Sequential(*pre, head)
+        self.conv1 = head
+        self.conv2 = nn.Sequential(nn.LeakyReLU(0.2, False), _conv(fout, fout, 3, spectral))
         if self.learned_shortcut:
-            self.conv_s = _sn(nn.Conv2d(fin, fout, 1, 1, 0), dis)
+            self.conv_s = _conv(fin, fout, 1, spectral)
+
+
+def _channel_plan(cin, nb):
+    """(down, up) lists of (in, out) channels: the up path consumes [skip | x] concatenations (:96-113)."""
+    width = [cin, 128, 128, 256, 256, 512, 512, 512, 512]
+    down = [(width[i], width[i + 1]) for i in range(nb)]
+    up = [(width[nb], width[nb - 1])]
+    up += [(2 * width[nb - i], width[nb - i - 1]) for i in range(1, nb - 1)]
+    up += [(2 * width[1], 64)]
+    return width, down, up
 
 
 class UNetDiscriminator(nn.Module):
     def __init__(self, **kwargs):
         super().__init__()
-        self.epoch = 0
-        self.step = 0
-        self.semantic_dim = kwargs.get("semantic_dim", 0)
-        self.label_dim = kwargs.get("label_dim", 0)
-        self.latent_dim = kwargs["latent_dim"]
+        self.epoch, self.step = 0, 0
+        self.semantic_dim, self.label_dim = kwargs.get("semantic_dim", 0), kwargs.get("label_dim", 0)
         self.output_dim = self.semantic_dim + self.label_dim
-        self.num_blocks = min(kwargs.get("discriminator_blocks", 6),
-                              int(math.log2(max(kwargs["gen_height"], kwargs["gen_width"]))) - 1)
-        cin = 6 if kwargs.get("dual_discrimination", False) else 3
-        self.channels = [cin, 128, 128, 256, 256, 512, 512, 512, 512]
-        ch, nb = self.channels, self.num_blocks
-        self.body_up = nn.ModuleList([])
-        self.body_down = nn.ModuleList([])
-        for i in range(nb):
-            self.body_down.append(ResBlock(ch[i], ch[i + 1], -1, first=(i == 0), **kwargs))
-        self.body_up.append(ResBlock(ch[nb], ch[nb - 1], 1, **kwargs))
-        for i in range(1, nb - 1):
-            self.body_up.append(ResBlock(2 * ch[nb - i], ch[nb - i - 1], 1, **kwargs))
-        self.body_up.append(ResBlock(2 * ch[1], 64, 1, **kwargs))
-        self.layer_up_last = nn.Conv2d(64, 1, 1, 1, 0)
-        self.output_layer = nn.Conv2d(64, self.output_dim, 1, 1)
-        ds = 2 ** nb
-        self.latent_layer = nn.Conv2d(ch[nb], self.latent_dim, (kwargs["gen_height"] // ds, kwargs["gen_width"] // ds))
-        # `self.apply(kaiming_leaky_init)` (:121, :74-79): for spectral-normed convs the reference re-draws
-        # the derived `.weight` attribute, which the next forward overwrites -- `weight_orig` keeps the
-        # default Conv2d initialisation; only the three plain heads actually get the kaiming draw.
-        for m in (self.layer_up_last, self.output_layer, self.latent_layer):
-            nn.init.kaiming_normal_(m.weight, a=0.2, mode="fan_in", nonlinearity="leaky_relu")
+        self.latent_dim = kwargs["latent_dim"]
+        Hg, Wg = kwargs["gen_height"], kwargs["gen_width"]
+        self.num_blocks = nb = min(kwargs.get("discriminator_blocks", 6), int(math.log2(max(Hg, Wg))) - 1)
+        self.channels, down, up = _channel_plan(6 if kwargs.get("dual_discrimination", False) else 3, nb)
+        # registration order (up before down, then the heads) is the reference's state_dict order
+        self.body_up = nn.ModuleList(ResBlock(i, o, 1, **kwargs) for i, o in up)
+        self.body_down = nn.ModuleList(ResBlock(i, o, -1, first=(k == 0), **kwargs) for k, (i, o) in enumerate(down))
+        self.layer_up_last = nn.Conv2d(64, 1, 1)
+        self.output_layer = nn.Conv2d(64, self.output_dim, 1)
+        self.latent_layer = nn.Conv2d(self.channels[nb], self.latent_dim, (Hg >> nb, Wg >> nb))
+        # The reference calls `self.apply(kaiming_leaky_init)` (:121): on a spectral-normed conv that only re-draws the
+        # derived `.weight`, which the next forward recomputes from `weight_orig` -- so only the three plain heads
+        # really receive the kaiming draw.
+        for head in (self.layer_up_last, self.output_layer, self.latent_layer):
+            nn.init.kaiming_normal_(head.weight, a=0.2, mode="fan_in", nonlinearity="leaky_relu")
         with torch.no_grad():
-            self.output_layer.weight *= 0.25
+            self.output_layer.weight.mul_(0.25)
         self._cfg = {k: v for k, v in kwargs.items() if isinstance(k, str)}
 
     def forward(self, images, conditions, alpha, **kwargs):
