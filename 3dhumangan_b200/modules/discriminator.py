@@ -62,11 +62,15 @@ class UNetDiscriminator(nn.Module):
         self.layer_up_last = nn.Conv2d(64, 1, 1)
         self.output_layer = nn.Conv2d(64, self.output_dim, 1)
         self.latent_layer = nn.Conv2d(self.channels[nb], self.latent_dim, (Hg >> nb, Wg >> nb))
-        # The reference calls `self.apply(kaiming_leaky_init)` (:121): on a spectral-normed conv that only re-draws the
-        # derived `.weight`, which the next forward recomputes from `weight_orig` -- so only the three plain heads
-        # really receive the kaiming draw.
-        for head in (self.layer_up_last, self.output_layer, self.latent_layer):
-            nn.init.kaiming_normal_(head.weight, a=0.2, mode="fan_in", nonlinearity="leaky_relu")
+        # The reference calls `self.apply(kaiming_leaky_init)` (:121, :74-78).  On a spectral-normed conv `module.weight` is
+        # `weight_orig.data` at that point (torch.nn.utils.spectral_norm registers the plain attribute from the same
+        # storage), so the in-place kaiming draw re-initialises `weight_orig` of all 33 spectral-normed convolutions as
+        # well as the three plain heads: std = sqrt(2 / (1 + 0.2^2)) / sqrt(fan_in).
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                w = m.weight_orig if hasattr(m, "weight_orig") else m.weight
+                with torch.no_grad():
+                    nn.init.kaiming_normal_(w, a=0.2, mode="fan_in", nonlinearity="leaky_relu")
         with torch.no_grad():
             self.output_layer.weight.mul_(0.25)
         self._cfg = {k: v for k, v in kwargs.items() if isinstance(k, str)}

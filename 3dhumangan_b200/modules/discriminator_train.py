@@ -6,7 +6,8 @@ ops, so that first-order gradients w.r.t. images (generator step) and parameters
 `loss.backward()`:
 
     convolution      `Conv2dSame`  forward `hg_conv2d`, data gradient `hg_conv2d` with the rotated / transposed filter,
-                                   weight gradient `hg_conv2d_wgrad_taps` (tcgen05, one launch per tap)
+                                   weight gradient `ConvWgrad` = `hg_conv2d_wgrad_taps` (tcgen05); both backward nodes
+                                   are themselves differentiable (R1 double backward, phase_trainer.py:259-294)
     LeakyReLU        `ops.bias_act` (hg_bias_act / hg_bias_act_grad)
     avg-pool / nearest up-sample   `ops.upfirdn2d` with a 2x2 box filter (its backward is another upfirdn pass)
     spectral norm    torch autograd on W / sigma (one power iteration per training forward, buffers in place)
@@ -46,8 +47,19 @@ def _conv_raw(x, w, bias, passes):
     return outs[0] if len(outs) == 1 else torch.cat(outs, 1)
 
 
+def _rot(w):
+    """Filter of the data gradient: 180-degree rotation, input and output channels exchanged (differentiable in w)."""
+    return w.flip(2, 3).transpose(0, 1)
+
+
 class Conv2dSame(torch.autograd.Function):
+    """Stride-1 'same' convolution y = w * x + b.  Differentiable to ANY order: its backward is composed of `Conv2dSame`
+    (data gradient: the same kernel with the rotated filter) and `ConvWgrad` nodes, whose backwards are again those two --
+    which is what the reference trainer's R1 term needs (`torch.autograd.grad(..., create_graph=True)` through the
+    discriminator on the do_r1 phases, then `d_loss.backward()` through that graph: phase_trainer.py:259-294)."""
+
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, w, bias, passes):
         x = x.float().contiguous()
         ctx.save_for_backward(x, w)
@@ -55,19 +67,41 @@ class Conv2dSame(torch.autograd.Function):
         return _conv_raw(x, w.detach().float(), None if bias is None else bias.detach().float(), passes)
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        dy = dy.float().contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            # correlation with the 180-degree rotated filter, input and output channels exchanged
-            wt = w.detach().float().flip(2, 3).transpose(0, 1).contiguous()
-            dx = _conv_raw(dy, wt, None, ctx.passes)
+            dx = Conv2dSame.apply(dy, _rot(w), None, ctx.passes)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = abi.conv2d_wgrad(dy, x, w.shape[2], passes=ctx.passes)
+            dw, db = ConvWgrad.apply(dy, x, w.shape[2], ctx.passes)
             if not ctx.has_bias:
                 db = None
         return dx, dw, db, None
+
+
+class ConvWgrad(torch.autograd.Function):
+    """(dy [B,Co,H,W], x [B,Ci,H,W]) -> dw[co,ci,i,j] = sum_{b,p} dy[b,co,p] x[b,ci,p+(i,j)-k//2],  db[co] = sum dy.
+    Bilinear in (dy, x); its two gradients are convolutions again."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, dy, x, ksize, passes):
+        dy, x = dy.float().contiguous(), x.float().contiguous()
+        ctx.save_for_backward(dy, x)
+        ctx.passes = passes
+        return abi.conv2d_wgrad(dy, x, ksize, passes=passes)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, ddw, ddb):
+        dy, x = ctx.saved_tensors
+        g_dy = g_x = None
+        if ctx.needs_input_grad[0]:          # d/d dy[b,co,p] = sum_{ci,k} ddw[co,ci,k] x[b,ci,p+k] (+ ddb[co])
+            g_dy = Conv2dSame.apply(x, ddw, ddb, ctx.passes)
+        if ctx.needs_input_grad[1]:          # d/d x[b,ci,q] = sum_{co,k} ddw[co,ci,k] dy[b,co,q-k]
+            g_x = Conv2dSame.apply(dy, _rot(ddw), None, ctx.passes)
+        return g_dy, g_x, None, None
 
 
 def _lrelu(x, rec=None):

@@ -336,7 +336,9 @@ class Map3DGenerator(nn.Module):
             from . import render_train
             if not self.training:
                 raise RuntimeError("hg3d: gradients through the generator are built for train() mode (batch statistics)")
-            return render_train.GeneratorCore.apply(freq, phase, styles.reshape(B, -1), self, cond, cfg, u, noise, passes)
+            names, tensors = render_train.core_parameters(self)
+            return render_train.GeneratorCore.apply(self, cond, cfg, u, noise, passes, names, freq, phase,
+                                                    styles.reshape(B, -1), *tensors)
         r = render_ops.render_forward(P, freq, phase, cond, cfg, u, noise, passes=passes)
         ray = r["ray_out"]                                                   # [B,R,260]
         rgb = synthesis_ops.synthesis_forward(P, ray, styles.reshape(B, -1), cfg, training=self.training, passes=passes)
@@ -357,9 +359,12 @@ class Map3DGenerator(nn.Module):
         buffers are read / updated in place by the replay (running stats, spectral-norm u/v, RNG offsets)."""
         keys = ("skeletons_xyz", "vertices", "tpose_vertices", "fk_matrices", "lbs_weights", "cam2world_matrices",
                 "intrinsics", "scales")
+        # every plain config value is part of the key: scalars such as clamp_mode, ray_start/ray_end, side_length,
+        # sample_dist, legacy_mode are baked into the captured launches, and a curriculum step may change them
+        plain = tuple(sorted((k, repr(v)) for k, v in cfg.items()
+                             if isinstance(v, (bool, int, float, str, type(None), list, tuple)) and not k.startswith("hg_")))
         sig = (tuple(latent.shape), tuple(tuple(conditions[k].shape) for k in keys), self.training, passes,
-               cfg["render_height"], cfg["render_width"], cfg["num_steps"], cfg.get("map3d_mode"), cfg["nerf_noise"],
-               cfg.get("last_back", False), cfg.get("white_back", False), str(latent.device))
+               str(latent.device), plain)
         if not hasattr(self, "_graphs"):
             self._graphs = {}
         entry = self._graphs.get(sig)

@@ -97,11 +97,15 @@ def mlp_forward_train(P, freq, phase, rec, z_vals, noise, cfg, *, geo_dim=31, lo
     return ray_out, tape
 
 
-def mlp_backward(tape, dray):
+def mlp_backward(tape, dray, grads=None):
     """dray [B,R,260] (gradient w.r.t. feat | rgb | depth; the depth column is ignored, as no loss uses it).
-    Accumulates `.grad` of the neural-field parameters and returns (d freq, d phase) [B,4*256] each."""
+    Adds the gradients of the neural-field parameters to `grads` (name -> tensor; to `.grad` when grads is None) and
+    returns (d freq, d phase) [B,4*256] each."""
+    from .synthesis_train import grad_accumulator
     P, prefix = tape["P"], tape["prefix"]
     g = lambda n: P[prefix + n]
+    acc_ = grad_accumulator(P, grads)
+    acc = lambda n, grad: acc_(prefix + n, grad)
     B, N, kw = tape["B"], tape["N"], tape["kw"]
     dev = dray.device
     f32 = dict(dtype=torch.float32, device=dev)
@@ -111,18 +115,13 @@ def mlp_backward(tape, dray):
     packT = lambda w: abi.pack_weight(w.detach().float().t().contiguous(), Nb=256)[0]
     mods_d, mod30, outs = tape["mods_d"], tape["mod30"], tape["outs"]
 
-    def acc(p, grad):
-        if p.requires_grad:
-            grad = grad.to(p.dtype).reshape(p.shape)
-            p.grad = grad if p.grad is None else p.grad + grad
-
     dfeat, drgbp, dsig = abi.render_composite_bwd(tape["sig"], tape["z"], tape["noise"], tape["rgbp"], tape["feat"],
                                                   dray.float().contiguous(), **tape["comp"])
     hb = abi.render_heads_bwd(outs[3], tape["lin_c"], mods_d[3], dsig, drgbp, B=B, N=N)
-    acc(g("sigma_layer.weight"), hb[:H].float())
-    acc(g("color_layer_linear.weight"), hb[H:4 * H].float().reshape(3, H))
-    acc(g("sigma_layer.bias"), hb[4 * H:4 * H + 1].float())
-    acc(g("color_layer_linear.bias"), hb[4 * H + 1:].float())
+    acc("sigma_layer.weight", hb[:H].float())
+    acc("color_layer_linear.weight", hb[H:4 * H].float().reshape(3, H))
+    acc("sigma_layer.bias", hb[4 * H:4 * H + 1].float())
+    acc("color_layer_linear.bias", hb[4 * H + 1:].float())
 
     dmods = [torch.zeros(B, 2, H, **f32) for _ in range(4)]
     sums = lambda: torch.zeros(B, 2, H, dtype=torch.float64, device=dev)
@@ -139,8 +138,8 @@ def mlp_backward(tape, dray):
                                      rk_w=rk3, rk_v=drgbp, **kw)
     add_film(3, s)
     dw, db = abi.act_wgrad_blocked(dfeat, tape["lin_c"], full, mods_d[3], act=1, **kw)
-    acc(g("feature_layer_linear.weight"), dw)
-    acc(g("feature_layer_linear.bias"), db)
+    acc("feature_layer_linear.weight", dw)
+    acc("feature_layer_linear.bias", db)
     del dfeat
     # ---- colour layer: lin_c = Wcol' sin(f3 out3 + phi3) + bcol';  the sigma head feeds back through h4
     f3 = mods_d[3][:, 0].contiguous()
@@ -150,10 +149,9 @@ def mlp_backward(tape, dray):
                                    rk_w=rk1, rk_v=dsig.reshape(B, 1, N), **kw)
     add_film(3, s)
     dw, db = abi.act_wgrad_blocked(dpre_c, outs[3], full, mods_d[3], act=1, pscale=f3, **kw)
-    if wcol.requires_grad:
-        gw = torch.zeros_like(wcol)
-        gw[:, 3:] = dw
-        wcol.grad = gw if wcol.grad is None else wcol.grad + gw
+    gw = torch.zeros_like(wcol)
+    gw[:, 3:] = dw
+    acc("color_layer_sine.layer.weight", gw)
     small = [(tape["bcol"], db)]                                              # bias + direction columns via autograd
     del dpre_c
     # ---- network.3 .. network.1: out_i = W_i sin(f_{i-1} out_{i-1} + phi_{i-1}) + b_i
@@ -164,8 +162,8 @@ def mlp_backward(tape, dray):
         nxt = abi.conv1x1_blocked_bwd(dpre, outs[i - 1], packT(wi), new(), s, mod=mods_d[i - 1], act=1, ascale=fi, **kw)
         add_film(i - 1, s)
         dw, db = abi.act_wgrad_blocked(dpre, outs[i - 1], full, mods_d[i - 1], act=1, pscale=fi, **kw)
-        acc(wi, dw)
-        acc(g(f"network.{i}.layer.bias"), db)
+        acc(f"network.{i}.layer.weight", dw)
+        acc(f"network.{i}.layer.bias", db)
         dpre = nxt
     # ---- network.0 (K = 512: coordinate half, geometry half) and the two first layers
     f0 = mods_d[0][:, 0].contiguous()
@@ -180,19 +178,23 @@ def mlp_backward(tape, dray):
         gw0[:, half * H:(half + 1) * H] = dw
         # first layer: lin = W x + b with the sine's factor 30 folded into the incoming gradient
         dwf, dbf = abi.act_wgrad_blocked(dlin, tape["rec_b"], T * 128 * 128, None, act=2, pscale=thirty, Cx=128, **kw)
-        acc(g(first + "weight"), dwf[:, cols])
-        acc(g(first + "bias"), dbf)
+        acc(first + "weight", dwf[:, cols])
+        acc(first + "bias", dbf)
         del dlin
-    acc(w0, gw0)
-    acc(g("network.0.layer.bias"), db0)
+    acc("network.0.layer.weight", gw0)
+    acc("network.0.layer.bias", db0)
     # ---- FiLM tables, colour bias / direction columns: tiny autograd graphs
     outs_, grads_ = list(tape["mods"]), list(dmods)
     for t, gr in small:
         if t.requires_grad:
             outs_.append(t)
             grads_.append(gr)
-    torch.autograd.backward(outs_, grads_)
-    return tape["fq"].grad, tape["ph"].grad
+    leaves = [n for n in ("color_layer_sine.layer.bias", "color_layer_sine.layer.weight") if g(n).requires_grad]
+    res = torch.autograd.grad(outs_, [tape["fq"], tape["ph"]] + [g(n) for n in leaves], grads_, allow_unused=True)
+    for n, r in zip(leaves, res[2:]):
+        if r is not None:
+            acc(n, r)
+    return res[0], res[1]
 
 
 @torch.no_grad()
@@ -214,47 +216,75 @@ def geo_records(cond, cfg, u):
     return geo["rec"], geo["z_vals"]
 
 
+CORE_PREFIXES = ("neural_field.", "synthesis_network.", "synthesis_input.")
+
+
+def core_parameters(module):
+    """(names, tensors): the renderer / synthesis parameters that enter `GeneratorCore` as autograd inputs."""
+    names, tensors = [], []
+    for n, p in module.named_parameters():
+        if n.startswith(CORE_PREFIXES):
+            names.append(n)
+            tensors.append(p)
+    return names, tensors
+
+
 class GeneratorCore(torch.autograd.Function):
-    """(freq, phase, fixed style) -> (rgbs, rgbs_render, depth) with the renderer and the synthesis network on the
-    sm_100a kernels.  Backward returns the gradients of the three inputs (which continue into the mapping networks
-    through ordinary autograd) and ACCUMULATES the `.grad` of every renderer / synthesis parameter of `module` as a
-    side effect -- `loss.backward()` + an optimiser step work as usual; `torch.autograd.grad(loss, params)` does not
-    see those parameters.  Under data parallelism average the `.grad`s explicitly after backward (the reference's
-    DDP hooks never fire for them)."""
+    """(freq, phase, fixed style, *renderer and synthesis parameters) -> (rgbs, rgbs_render, depth) on the sm_100a kernels.
+
+    EVERY parameter the kernels read is an input of this node and its gradient is RETURNED by `backward`, so the
+    reference trainer's machinery sees them like any other autograd node's: `DistributedDataParallel` reducer hooks fire
+    (base_trainer.py:102-104, find_unused_parameters=True walks the graph to them), `torch.autograd.grad(loss, params)`
+    works, `GradScaler.unscale_` finds fp32 `.grad`s.  Under `torch.autocast` the inputs are taken as fp32 (the kernels
+    compute in fp32 / bf16x3 whatever the ambient autocast dtype; phase_trainer.py:355,396,462 run the models under
+    fp16 autocast).  First-order only: the reference never differentiates the generator twice (R1 acts on real images)."""
 
     @staticmethod
-    def forward(ctx, freq, phase, styles, module, cond, cfg, u, noise, passes):
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, module, cond, cfg, u, noise, passes, names, freq, phase, styles, *tensors):
         from . import synthesis_train
         P = module._params()
+        for n, t in zip(names, tensors):           # the tensors autograd tracks (identical objects unless a caller wraps them)
+            P[n] = t
         B = freq.shape[0]
         Rh, Rw = cfg["render_height"], cfg["render_width"]
         if cfg.get("hierarchical_sample", False) or not cfg.get("lock_view_dependence", False):
             raise RuntimeError("hg3d: the training renderer is built for hierarchical_sample=False, lock_view_dependence=True")
+        if cfg.get("neural_field_blocks", 4) != 4:
+            raise RuntimeError("hg3d: the training renderer is built for neural_field_blocks == 4 (all shipped curricula)")
         rec, z_vals = geo_records(cond, cfg, u)
         with torch.enable_grad():
             ray, rtape = mlp_forward_train(P, freq, phase, rec, z_vals, noise, cfg, geo_dim=cfg["geo_feature_dim"],
                                            passes=passes)
             rgb, stape = synthesis_train.synthesis_forward_train(P, ray, styles.reshape(B, -1), cfg, passes=passes)
-        ctx.tapes = (P, rtape, stape, cfg, passes)
+        ctx.tapes = (P, rtape, stape, cfg, passes, names)
         rgb_render = (ray[..., 256:259] * 2 - 1).reshape(B, Rh, Rw, 3).permute(0, 3, 1, 2).contiguous()
         depth = ray[..., 259:260].contiguous()
         ctx.mark_non_differentiable(depth)
         return rgb, rgb_render, depth
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    @torch.autograd.function.once_differentiable
     def backward(ctx, d_rgb, d_rgb_render, d_depth):
         from . import synthesis_train
-        P, rtape, stape, cfg, passes = ctx.tapes
+        if ctx.tapes is None:
+            raise RuntimeError("hg3d: the generator's activation tape was released by a previous backward pass "
+                               "(one backward per forward; retain_graph=True keeps the graph, not the tape)")
+        P, rtape, stape, cfg, passes, names = ctx.tapes
         B = stape.B
         Rh, Rw = cfg["render_height"], cfg["render_width"]
+        grads = {}
         with torch.enable_grad():
-            dfs, dfeat = synthesis_train.synthesis_backward(P, stape, d_rgb, passes=passes)
+            dfs, dfeat = synthesis_train.synthesis_backward(P, stape, d_rgb, passes=passes, grads=grads)
         dray = torch.zeros(B, Rh * Rw, 260, dtype=torch.float32, device=d_rgb.device)
         if dfeat is not None:
             dray[..., :256] = dfeat
         if d_rgb_render is not None:
             dray[..., 256:259] = 2.0 * d_rgb_render.permute(0, 2, 3, 1).reshape(B, Rh * Rw, 3)
         with torch.enable_grad():
-            dfreq, dphase = mlp_backward(rtape, dray)
+            dfreq, dphase = mlp_backward(rtape, dray, grads=grads)
         ctx.tapes = None
-        return dfreq, dphase, dfs.reshape(B, -1), None, None, None, None, None, None
+        out = [grads.get(n) for n in names]
+        return (None, None, None, None, None, None, None, dfreq.detach(), dphase.detach(), dfs.detach().reshape(B, -1),
+                *[None if g is None else g.detach() for g in out])

@@ -199,9 +199,25 @@ def synthesis_forward_train(params, feat_lr, fixed_style, cfg, *, passes=3, pref
     return tape.rgb, tape
 
 
-def synthesis_backward(params, tape, drgb, *, passes=3):
-    """Accumulates `.grad` of every synthesis parameter in `params` (those that require grad) and returns
-    (d fixed_style [B,256], d feat_lr [B,Rh*Rw,256] or None when no half-block is pixel-style)."""
+def grad_accumulator(P, grads):
+    """-> acc(name, g): adds g to `grads[name]` (the gradients an autograd.Function RETURNS, so that DDP reducer hooks,
+    torch.autograd.grad and GradScaler see them), or -- with grads=None, kernel-level tests and tools -- to `P[name].grad`."""
+    def acc(name, g):
+        p = P[name]
+        if not p.requires_grad:
+            return
+        g = g.to(p.dtype).reshape(p.shape)
+        if grads is None:
+            p.grad = g if p.grad is None else p.grad + g
+        else:
+            grads[name] = g if name not in grads else grads[name] + g
+    return acc
+
+
+def synthesis_backward(params, tape, drgb, *, passes=3, grads=None):
+    """Gradients of every synthesis parameter in `params` (those that require grad) into `grads` (name -> tensor; `.grad`
+    when grads is None) and returns (d fixed_style [B,256], d feat_lr [B,Rh*Rw,256] or None when no half-block is
+    pixel-style)."""
     P = params
     cfg, B = tape.cfg, tape.B
     Hg, Wg = cfg["gen_height"], cfg["gen_width"]
@@ -214,9 +230,7 @@ def synthesis_backward(params, tape, drgb, *, passes=3):
     n = len(H)
     full = T * C * 128
 
-    def acc(p, g):
-        if p.requires_grad:
-            p.grad = g.to(p.dtype).reshape(p.shape) if p.grad is None else p.grad + g.to(p.dtype).reshape(p.shape)
+    acc = grad_accumulator(P, grads)
 
     # every ToRGB bias sees the full drgb
     drgb_sum = drgb.sum((0, 2))
@@ -239,8 +253,8 @@ def synthesis_backward(params, tape, drgb, *, passes=3):
             kw.update(dpre=nxt[0], g1=nxt[1], ak=nxt[2])
         abi.spade_bwd_combine(d, B=B, Hg=Hg, Wg=Wg, x=rec["out"], x_bstride=full, dskip=dskip, **kw)
         if dwrgb is not None:
-            acc(P[rec["rgb"] + "weight"], dwrgb.float())
-            acc(P[rec["rgb"] + "bias"], drgb_sum)
+            acc(rec["rgb"] + "weight", dwrgb.float())
+            acc(rec["rgb"] + "bias", drgb_sum)
         dout[h] = d
         dout.pop(h + 3, None)
         # ---- this half-block
@@ -280,10 +294,10 @@ def synthesis_backward(params, tape, drgb, *, passes=3):
             dwg, dbg = abi.spade_bwd_wgrad(dgam, a1, T * 128 * 128, None, Cx=128, B=B, Hg=Hg, Wg=Wg, passes=passes)
             dwb, dbb = abi.spade_bwd_wgrad(dpre, a1, T * 128 * 128, None, Cx=128, B=B, Hg=Hg, Wg=Wg, passes=passes)
             sp_ = rec["spade"]
-            acc(P[sp_ + "mlp_gamma.weight"], dwg)
-            acc(P[sp_ + "mlp_gamma.bias"], dbg)
-            acc(P[sp_ + "mlp_beta.weight"], dwb)
-            acc(P[sp_ + "mlp_beta.bias"], dbb)
+            acc(sp_ + "mlp_gamma.weight", dwg)
+            acc(sp_ + "mlp_gamma.bias", dbg)
+            acc(sp_ + "mlp_beta.weight", dwb)
+            acc(sp_ + "mlp_beta.bias", dbb)
             if "dp" not in tape.p:
                 tape.p["dp"] = torch.zeros_like(p_lr)
             dp = tape.p["dp"]
@@ -291,7 +305,7 @@ def synthesis_backward(params, tape, drgb, *, passes=3):
             if rec["p_bias"].requires_grad:
                 small_out.append(rec["p_bias"])
                 small_grad.append(s7[:, 0].float())
-            acc(P[rec["conv"] + "bias"], db)
+            acc(rec["conv"] + "bias", db)
             small_out.append(rec["w_sn"])
             small_grad.append(dw)
             dmod = torch.stack([s3[0], s3[1]]).float()                        # d sc = sum dxn*x, d sh = sum dxn
@@ -301,7 +315,7 @@ def synthesis_backward(params, tape, drgb, *, passes=3):
         else:
             abi.spade_bwd_dgrad(d, rec["x"], rec["x_bstride"], rec["mod_d"], wimg_t, dpre, sums, B=B, Hg=Hg, Wg=Wg, passes=passes)
             dw, db = abi.spade_bwd_wgrad(d, rec["x"], rec["x_bstride"], rec["mod_d"], B=B, Hg=Hg, Wg=Wg, passes=passes)
-            acc(P[rec["conv"] + "bias"], db)
+            acc(rec["conv"] + "bias", db)
             small_out.append(rec["w_sn"])
             small_grad.append(dw)
             dmod = torch.stack([sums[:, 1], sums[:, 0]], dim=1).float()       # d g1 = sum dpre*x, d g0 = sum dpre
@@ -319,14 +333,18 @@ def synthesis_backward(params, tape, drgb, *, passes=3):
     abi.spade_bwd_combine(dx0, B=B, Hg=Hg, Wg=Wg, x=H[0]["x"], x_bstride=0, dpre=nxt[0], g1=nxt[1], ak=nxt[2])
     ip = tape.input["prefix"]
     dw_in, db_in = abi.synth_input_bwd(dx0, tape.input["w"], P[ip + "network.0.bias"].detach(), tape.input["ic"], tape.input["jc"], B)
-    acc(P[ip + "network.0.weight"], dw_in)
-    acc(P[ip + "network.0.bias"], db_in)
+    acc(ip + "network.0.weight", dw_in)
+    acc(ip + "network.0.bias", db_in)
     # ---- all [C]- and [B,C]-sized chains in one autograd pass (accumulates into the Parameters' .grad)
     fs = tape.fixed_style
     leaves = [t for t in small_out if t.requires_grad]
-    grads = [g for t, g in zip(small_out, small_grad) if t.requires_grad]
-    inputs = [p for p in P.values() if isinstance(p, torch.Tensor) and p.requires_grad and p.is_leaf] + [fs]
-    torch.autograd.backward(leaves, grads, inputs=inputs)
+    small = [g for t, g in zip(small_out, small_grad) if t.requires_grad]
+    names = [n for n, p in P.items() if isinstance(p, torch.Tensor) and p.requires_grad and p.is_leaf]
+    res = torch.autograd.grad(leaves, [P[n] for n in names] + [fs], small, allow_unused=True)
+    for n, r in zip(names, res[:-1]):
+        if r is not None:
+            acc(n, r)
+    dfs = res[-1] if res[-1] is not None else torch.zeros_like(fs)
     # ---- render-resolution projection P_lr = X . W_shared^T: feature-map and weight gradients
     dfeat = None
     if tape.px and "dp" in tape.p:
@@ -344,5 +362,5 @@ def synthesis_backward(params, tape, drgb, *, passes=3):
         torch.backends.cuda.matmul.allow_tf32 = prev
         for rec in H:
             if rec["pixel"]:
-                acc(P[rec["spade"] + "mlp_shared.0.weight"], dWs[rec["i"] * 128:(rec["i"] + 1) * 128])
-    return fs.grad, dfeat
+                acc(rec["spade"] + "mlp_shared.0.weight", dWs[rec["i"] * 128:(rec["i"] + 1) * 128])
+    return dfs, dfeat

@@ -1,105 +1,316 @@
-"""One training iteration of the shipped 512-pixel curricula on the sm_100a kernels: discriminator step, then
-generator step (PhaseTrainer.train_discriminator / train_generator, lib/trainers/phase_trainer.py:297-344, with
-`_train_discriminator` :344-444 and `_train_generator` :446-560 for gan_lambda = 0, latent_lambda = 0,
-segmentation_lambda = 1, r1_lambda = 0 -- configs/map3d.py:98-191; with r1_lambda = 0 the R1 term is identically
-zero, so it is not evaluated).
+"""One training iteration of the reference's trainer over this library's modules: the host-side mirror of
+`PhaseTrainer.train_discriminator / train_generator` (lib/trainers/phase_trainer.py:297-344, `_train_discriminator`
+:344-444, `_train_generator` :446-560), `init_optimizer` (:57-76), `_calculate_segmentation_loss` (:203-256),
+`_calculate_r1_regularization` (:259-294), `BaseTrainer.init_model`'s DDP wrapping (base_trainer.py:102-104) and
+`ExponentialMovingAverage.update` (lib/components/ema.py:29-48).
 
-Everything between the inputs and the two losses runs on this library's kernels (generator: fused inference kernels
-in the discriminator step, training kernels in the generator step; discriminator: the autograd graph of
-modules/discriminator_train.py).  The loss itself (class-balanced cross entropy), gradient clipping and Adam are the
-trainer's own torch code -- SURVEY.md §8f row 1, outside the hot path.
+It exists for two reasons: (1) the reference's trainer cannot travel to the GPU box (it needs the dataset, the
+pytorch3d rasteriser and tensorboard), so THIS is what exercises the module surfaces exactly the way that trainer
+does -- `DistributedDataParallel(find_unused_parameters=True, broadcast_buffers=False)`, fp16 autocast +
+`GradScaler`, `disc_input_real.requires_grad = True`, `torch.autograd.grad(..., create_graph=True)` on the do_r1 phases,
+`backward(retain_graph=True)`, `unscale_` / `clip_grad_norm_` / `scaler.step`, EMA over `parameters()`; (2) it is the
+G+D step that `bench.py` times (BASELINE.json's second metric).
+
+Everything between the inputs and the two losses runs on the sm_100a kernels (generator: fused inference kernels under
+no_grad in the discriminator step, training kernels in the generator step; discriminator: the autograd graph of
+modules/discriminator_train.py).  Loss reduction, clipping, Adam and EMA are multi-tensor torch calls.
 """
 from __future__ import annotations
+
+import math
 
 import torch
 import torch.nn.functional as F
 
 
-def segmentation_loss(segments, gt, label_dim, prior_weights=None):
-    """`cross_entropy_balanced` of PhaseTrainer._calculate_segmentation_loss (phase_trainer.py:203-256)."""
+# ----------------------------------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------------------------------
+def segmentation_loss(segments, gt, label_dim, prior_weights=None, with_stats=False):
+    """`cross_entropy_balanced` of PhaseTrainer._calculate_segmentation_loss (phase_trainer.py:203-256): per-class weights
+    ~ 1 / occurrence (background excluded), normalised by the number of classes present."""
+    if gt.shape[1:] != segments.shape[2:]:
+        with torch.no_grad():
+            gt = F.interpolate(gt[:, None].float(), segments.shape[2:], mode="nearest")[:, 0].long()
     if not bool((gt > 0).any()):
-        return F.cross_entropy(segments, gt)
-    pw = torch.ones(label_dim, dtype=segments.dtype, device=segments.device) if prior_weights is None else prior_weights
-    pw = pw / pw.mean()
-    one_hot = F.one_hot(gt, num_classes=label_dim).permute(0, 3, 1, 2)
-    occ = one_hot.sum(dim=(0, 2, 3))
-    occ[0] = 0
-    n_occ = torch.count_nonzero(occ)
-    coef = torch.reciprocal(occ.to(segments.dtype)) * one_hot.numel() / (n_occ * one_hot.shape[1])
-    coef[0] = 0
-    coef[torch.isinf(coef)] = 0
-    coef = coef * pw
-    return (F.cross_entropy(segments, gt, reduction="none") * coef[gt]).mean()
+        loss = F.cross_entropy(segments, gt)
+    else:
+        pw = torch.ones(label_dim, dtype=segments.dtype, device=segments.device) if prior_weights is None else \
+            torch.as_tensor(prior_weights, dtype=segments.dtype, device=segments.device)
+        pw = pw / pw.mean()
+        occ = torch.bincount(gt.reshape(-1), minlength=label_dim)[:label_dim].clone()
+        occ[0] = 0
+        n_occ = torch.count_nonzero(occ)
+        coef = torch.reciprocal(occ.to(segments.dtype)) * (gt.numel() * label_dim) / (n_occ * label_dim)
+        coef[0] = 0
+        coef[torch.isinf(coef)] = 0
+        coef = coef * pw
+        loss = (F.cross_entropy(segments, gt, reduction="none") * coef[gt]).mean()
+    if not with_stats:
+        return loss
+    with torch.no_grad():
+        real_prob = (1 - torch.softmax(segments, dim=1)[:, 0]).mean()
+        acc = ((torch.argmax(segments[:, 1:], dim=1) + 1) == gt).float().mean()
+    return loss, acc, real_prob
 
 
-def make_optimizers(G, D, cfg):
-    """Adam with the curriculum's betas / learning rates (phase_trainer.py:57-76; the per-group multipliers of the
-    generator are the trainer's business and do not change the cost of a step)."""
-    betas = tuple(float(b) for b in cfg.get("betas", (0, 0.9)))
-    og = torch.optim.Adam(G.parameters(), lr=cfg.get("gen_lr", 5e-5), betas=betas)
-    od = torch.optim.Adam(D.parameters(), lr=cfg.get("disc_lr", 2e-4), betas=betas)
+def r1_penalty(disc_input_real, out_real, scaler, meta):
+    """phase_trainer.py:259-294: 0.5 * r1_lambda * E_b |d f / d x_b|^2 with f = sum(prediction) (gan_lambda > 0) or
+    sum(softmax(segments)) (segmentation only); differentiated again by `d_loss.backward()` (create_graph=True)."""
+    if meta["gan_lambda"] > 0:
+        target = out_real["prediction"].sum()
+    elif meta["segmentation_lambda"] > 0:
+        target = torch.softmax(out_real["segments"], dim=1).sum()
+    else:
+        raise RuntimeError("cannot do r1 regularization when segmentation_lambda == 0 and gan_lambda == 0")
+    grad_real = torch.autograd.grad(outputs=scaler.scale(target), inputs=disc_input_real, create_graph=True)[0]
+    grad_real = grad_real * (1.0 / scaler.get_scale())
+    pen = grad_real.reshape(grad_real.shape[0], -1).pow(2).sum(dim=1).mean()
+    pen = 0.5 * meta["r1_lambda"] * pen
+    if bool(torch.isnan(pen).any()):
+        return 0.0
+    return pen
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# optimisers, EMA
+# ----------------------------------------------------------------------------------------------------------------------
+def generator_param_groups(named_params, meta):
+    """The five Adam groups of PhaseTrainer.init_optimizer (phase_trainer.py:57-76), selected by the same name substrings
+    in the same precedence: neural_field_mapping_network, synthesis_mapping_network, latent_pool, neural_field, rest."""
+    named = list(named_params)
+    nf_map = {n: p for n, p in named if "neural_field_mapping_network" in n}
+    syn_map = {n: p for n, p in named if "synthesis_mapping_network" in n}
+    codes = {n: p for n, p in named if "latent_pool" in n}
+    field = {n: p for n, p in named if "neural_field" in n and n not in nf_map}
+    taken = {**codes, **field, **nf_map, **syn_map}
+    rest = {n: p for n, p in named if n not in taken}
+    lr = meta["gen_lr"]
+    return [
+        {"params": list(rest.values()), "name": "generator"},
+        {"params": list(codes.values()), "name": "appearance_codes", "lr": lr * meta["appearance_codes_lr_mul"]},
+        {"params": list(nf_map.values()), "name": "neural_field_mapping", "lr": lr * meta["mapping_net_lr_mul"]},
+        {"params": list(syn_map.values()), "name": "synthesis_mapping", "lr": lr},
+        {"params": list(field.values()), "name": "neural_field", "lr": lr * meta["neural_field_lr_mul"]},
+    ]
+
+
+def make_optimizers(G, D, meta):
+    """Adam for G (five groups with the curriculum's learning-rate multipliers) and D, as PhaseTrainer.init_optimizer."""
+    betas = tuple(float(b) for b in meta.get("betas", (0, 0.9)))
+    wd = meta.get("weight_decay", 0)
+    og = torch.optim.Adam(generator_param_groups(G.named_parameters(), meta), lr=meta["gen_lr"], betas=betas, weight_decay=wd)
+    od = torch.optim.Adam(D.parameters(), lr=meta["disc_lr"], betas=betas, weight_decay=wd)
     return og, od
 
 
-def average_gradients(module, group=None):
-    """Data parallelism: the kernels' parameter gradients are written by hand (`.grad` side effects of the autograd
-    functions), so DistributedDataParallel's reducer hooks never see them; average them explicitly, one flat
-    NCCL all-reduce per call (19.6 MB for G, 105.8 MB for D)."""
+class ParameterEMA:
+    """lib/components/ema.py:8-48: shadow copies of the parameters that require grad, decay = min(decay, (1+n)/(10+n)),
+    updated with one multi-tensor call per step."""
+
+    def __init__(self, parameters, decay=0.999, use_num_updates=True):
+        if not 0.0 <= decay <= 1.0:
+            raise ValueError("Decay must be between 0 and 1")
+        self.decay = decay
+        self.num_updates = 0 if use_num_updates else None
+        self.shadow_params = [p.clone().detach() for p in parameters if p.requires_grad]
+
+    @torch.no_grad()
+    def update(self, parameters):
+        decay = self.decay
+        if self.num_updates is not None:
+            self.num_updates += 1
+            decay = min(decay, (1 + self.num_updates) / (10 + self.num_updates))
+        params = [p.detach() for p in parameters if p.requires_grad]
+        torch._foreach_lerp_(self.shadow_params, params, 1.0 - decay)          # s -= (1 - decay) * (s - p)
+
+    @torch.no_grad()
+    def copy_to(self, parameters):
+        for s, p in zip(self.shadow_params, [p for p in parameters if p.requires_grad]):
+            p.data.copy_(s.data)
+
+
+def average_gradients(module, group=None, _cache={}):
+    """Optional fast path WITHOUT DistributedDataParallel: one flat NCCL all-reduce over every parameter that requires
+    grad (a missing gradient counts as zeros, so all ranks always reduce the same number of elements), through a cached
+    flat buffer.  The module surfaces work under real DDP (tests/test_gpu_multi.py); this is only for callers that want to
+    place the collective themselves."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
-    grads = [p.grad for p in module.parameters() if p.grad is not None]
-    if not grads:
+    params = [p for p in module.parameters() if p.requires_grad]
+    if not params:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    n = sum(p.numel() for p in params)
+    key = (id(module), n, params[0].device)
+    flat = _cache.get(key)
+    if flat is None:
+        flat = _cache[key] = torch.empty(n, dtype=torch.float32, device=params[0].device)
+    off = 0
+    for p in params:
+        seg = flat[off:off + p.numel()]
+        if p.grad is None:
+            seg.zero_()
+        else:
+            seg.copy_(p.grad.reshape(-1))
+        off += p.numel()
     dist.all_reduce(flat, group=group)
     flat /= dist.get_world_size(group)
     off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+    for p in params:
+        seg = flat[off:off + p.numel()].view_as(p)
+        if p.grad is None:
+            p.grad = seg.clone()
+        else:
+            p.grad.copy_(seg)
+        off += p.numel()
 
 
-def discriminator_step(G, D, opt_d, z, cond, real_images, real_labels, cfg):
-    opt_d.zero_grad(set_to_none=True)
-    with torch.no_grad():
-        fake = G(z, cond, **cfg)["rgbs"]
-    # The reference runs the discriminator twice (real, generated: phase_trainer.py:390,402).  It has no batch
-    # statistics, so one pass over the concatenated batch computes exactly the same outputs and gradients with half
-    # the launches (the low-resolution layers are launch-bound).
-    B = real_images.shape[0]
-    out = D(torch.cat([real_images.detach(), fake], 0), cond, alpha=1.0, **cfg)
-    L = cfg["label_dim"]
-    loss = (segmentation_loss(out["segments"][:B], real_labels, L)
-            + segmentation_loss(out["segments"][B:], torch.zeros_like(real_labels), L)) * cfg["segmentation_lambda"]
-    loss.backward()
-    average_gradients(D)
-    torch.nn.utils.clip_grad_norm_(D.parameters(), cfg["grad_clip"])
-    opt_d.step()
-    return loss.detach()
+# ----------------------------------------------------------------------------------------------------------------------
+# the iteration
+# ----------------------------------------------------------------------------------------------------------------------
+class Trainer:
+    """Drives (generator, discriminator) through the reference's two step functions.
+
+    `batch`: dict(images [B,3,H,W], labels [B,H,W] int64 (the real segmentation map), cond = the pose conditions,
+    optional z_d / z_g latents (drawn like `z_sampler` otherwise)).  `meta` is the merged curriculum dict that the
+    reference splats into every call."""
+
+    def __init__(self, G, D, meta, *, amp=None, ddp=None, amp_dtype=torch.float16, ema_decay=0.999):
+        import torch.distributed as dist
+        self.meta = dict(meta)
+        self.amp = bool(self.meta.get("use_mixed_precision", False)) if amp is None else bool(amp)
+        self.amp_dtype = amp_dtype
+        self.scaler = torch.amp.GradScaler("cuda", enabled=self.amp and amp_dtype == torch.float16)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.use_ddp = multi if ddp is None else bool(ddp)
+        if self.use_ddp:      # base_trainer.py:102-104
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            dev = next(G.parameters()).device
+            ids = [dev] if dist.get_backend() == "nccl" else None
+            self.generator_ddp = DDP(G, device_ids=ids, find_unused_parameters=True, broadcast_buffers=False)
+            self.discriminator_ddp = DDP(D, device_ids=ids, find_unused_parameters=True, broadcast_buffers=False)
+        else:
+            self.generator_ddp, self.discriminator_ddp = G, D
+        self.generator, self.discriminator = G, D
+        # groups are selected by name substrings, which survive DDP's "module." prefix (the reference builds them from
+        # `generator_ddp.named_parameters()`, phase_trainer.py:59)
+        self.optimizer_G, self.optimizer_D = make_optimizers(self.generator_ddp, self.discriminator_ddp, self.meta)
+        self.ema = ParameterEMA(G.parameters(), decay=ema_decay)
+        self.batch_split = int(self.meta.get("batch_split", 1))
+
+    # -- helpers
+    def _autocast(self):
+        return torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp)
+
+    def _phase(self):
+        phases = self.meta["phases"]
+        return phases[self.discriminator.step % len(phases)]
+
+    def _z(self, batch, key, B, device):
+        if key in batch:
+            return batch[key]
+        if self.meta.get("z_dist", "gaussian") == "gaussian":
+            return torch.randn(B, self.meta["latent_dim"], device=device)
+        return torch.rand(B, self.meta["latent_dim"], device=device) * 2 - 1
+
+    # -- phase_trainer.py:297-318 + :344-444
+    def train_discriminator(self, batch, alpha=1.0):
+        meta, phase = self.meta, self._phase()
+        self.optimizer_D.zero_grad()
+        real_images, labels, cond = batch["images"], batch["labels"], batch["cond"]
+        B = real_images.shape[0]
+        with self._autocast():
+            with torch.no_grad():
+                z = self._z(batch, "z_d", B, real_images.device)
+                split = B // self.batch_split
+                outs = []
+                for s in range(self.batch_split):
+                    sl = slice(s * split, (s + 1) * split)
+                    outs.append(self.generator_ddp(z[sl], {k: v[sl] for k, v in cond.items()}, latent_indices=None, **meta))
+                gen_outputs = {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+            disc_input_real = real_images.detach().clone() if real_images.requires_grad else real_images
+            disc_input_real.requires_grad = True
+            out_real = self.discriminator_ddp(disc_input_real, cond, alpha=alpha, mode="real", **meta)
+            pred_real = out_real["prediction"]
+        grad_penalty = 4 * r1_penalty(disc_input_real, out_real, self.scaler, meta) if phase["do_r1"] else 0.0
+        with self._autocast():
+            disc_input_gen = gen_outputs[phase["gen_modal"]]
+            out_gen = self.discriminator_ddp(disc_input_gen, cond, alpha=alpha, mode="gen", **meta)
+            pred_gen = out_gen["prediction"]
+            if meta["gan_lambda"] > 0:
+                gan_loss = meta["gan_lambda"] * (F.softplus(pred_gen).mean() + F.softplus(-pred_real).mean())
+            else:
+                gan_loss = pred_gen.sum() * 0 + pred_real.sum() * 0
+            if meta["segmentation_lambda"] > 0:
+                L = meta["label_dim"]
+                w = meta.get("segmentation_weights")
+                seg = (segmentation_loss(out_real["segments"], labels, L, w)
+                       + segmentation_loss(out_gen["segments"], torch.zeros_like(labels), L, w)) * meta["segmentation_lambda"]
+            else:
+                seg = (out_real["segments"].sum() + out_gen["segments"].sum()) * 0
+            latent_loss = (out_real["latents"].sum() + out_gen["latents"].sum()) * 0      # latent_lambda = 0 in every shipped curriculum
+            if meta.get("latent_lambda", 0) > 0:
+                raise RuntimeError("hg3d: latent_lambda > 0 is not used by any shipped curriculum and is not built")
+            d_loss = gan_loss + grad_penalty + seg + latent_loss
+        self.scaler.scale(d_loss).backward()
+        self.scaler.unscale_(self.optimizer_D)
+        torch.nn.utils.clip_grad_norm_(self.discriminator_ddp.parameters(), meta["grad_clip"])
+        self.scaler.step(self.optimizer_D)
+        return d_loss.detach()
+
+    # -- phase_trainer.py:321-341 + :446-560
+    def train_generator(self, batch, alpha=1.0):
+        meta, phase = self.meta, self._phase()
+        self.optimizer_G.zero_grad()
+        real_images, labels, cond = batch["images"], batch["labels"], batch["cond"]
+        B = real_images.shape[0]
+        z = self._z(batch, "z_g", B, real_images.device)
+        split = B // self.batch_split
+        total = 0.0
+        for s in range(self.batch_split):
+            sl = slice(s * split, (s + 1) * split)
+            with self._autocast():
+                sub = {k: v[sl] for k, v in cond.items()}
+                gen_outputs = self.generator_ddp(z[sl], sub, latent_indices=None, **meta)
+                out = self.discriminator_ddp(gen_outputs[phase["gen_modal"]], sub, alpha=alpha, mode="gen", **meta)
+                pred_gen = out["prediction"]
+                gan_lambda = meta["gan_lambda"] if phase["uncond"] else 0
+                gan_loss = gan_lambda * F.softplus(-pred_gen).mean() if gan_lambda > 0 else 0 * pred_gen.sum()
+                latent_loss = out["latents"].sum() * 0
+                if meta["segmentation_lambda"] > 0:
+                    seg = segmentation_loss(out["segments"], labels[sl], meta["label_dim"],
+                                            meta.get("segmentation_weights")) * meta["segmentation_lambda"]
+                else:
+                    seg = out["segments"].sum() * 0
+                g_loss = (gan_loss + latent_loss + seg) / self.batch_split
+                self.scaler.scale(g_loss).backward()
+            total = total + g_loss.detach()
+        self.scaler.unscale_(self.optimizer_G)
+        torch.nn.utils.clip_grad_norm_(self.generator_ddp.parameters(), meta["grad_clip"])
+        self.scaler.step(self.optimizer_G)
+        self.scaler.update()
+        self.ema.update(self.generator_ddp.parameters())
+        return total
+
+    def iteration(self, batch, alpha=1.0):
+        """base_trainer.py:366-446: discriminator step, generator step, step counters."""
+        d = self.train_discriminator(batch, alpha)
+        g = self.train_generator(batch, alpha)
+        self.discriminator.step += 1
+        self.generator.step += 1
+        return d, g
 
 
-def generator_step(G, D, opt_g, z, cond, labels, cfg):
-    opt_g.zero_grad(set_to_none=True)
-    flags = [p.requires_grad for p in D.parameters()]
-    for p in D.parameters():            # the discriminator is not updated here: skip its weight gradients
-        p.requires_grad_(False)
-    try:
-        fake = G(z, cond, **cfg)["rgbs"]
-        out = D(fake, cond, alpha=1.0, **cfg)
-        loss = segmentation_loss(out["segments"], labels, cfg["label_dim"]) * cfg["segmentation_lambda"]
-        loss.backward()
-    finally:
-        for p, f in zip(D.parameters(), flags):
-            p.requires_grad_(f)
-    average_gradients(G)
-    torch.nn.utils.clip_grad_norm_(G.parameters(), cfg["grad_clip"])
-    opt_g.step()
-    return loss.detach()
-
-
-def train_iteration(G, D, opt_g, opt_d, batch, cfg):
-    """batch: dict(z_d, z_g, cond, images, labels).  Returns (d_loss, g_loss)."""
-    d = discriminator_step(G, D, opt_d, batch["z_d"], batch["cond"], batch["images"], batch["labels"], cfg)
-    g = generator_step(G, D, opt_g, batch["z_g"], batch["cond"], batch["labels"], cfg)
-    return d, g
+# ----------------------------------------------------------------------------------------------------------------------
+# functional form (bench.py, tests): fp32, no AMP, R1 on its schedule
+# ----------------------------------------------------------------------------------------------------------------------
+def train_iteration(G, D, opt_g, opt_d, batch, cfg, trainer=None):
+    """batch: dict(z_d, z_g, cond, images, labels).  Returns (d_loss, g_loss).  Kept for callers that own their optimisers;
+    builds a `Trainer` around them once (cached on G)."""
+    t = trainer or getattr(G, "_hg_trainer", None)
+    if t is None or t.discriminator is not D:
+        t = Trainer(G, D, cfg, amp=False)
+        t.optimizer_G, t.optimizer_D = opt_g, opt_d
+        G._hg_trainer = t
+    return t.iteration(batch)

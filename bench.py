@@ -94,7 +94,7 @@ def cpu_sample(pkg, name, steps, warmup, sample_div=4):
     (gen and render resolutions divided by sample_div, same 32 samples per ray, same dims) and scales
     by the pixel ratio.  Returns (images_per_sec, cores, description)."""
     from oracle import port
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     cfg = workload_cfg(pkg, name)
     full_px = cfg["gen_height"] * cfg["gen_width"]
@@ -114,19 +114,43 @@ def cpu_sample(pkg, name, steps, warmup, sample_div=4):
             port.generator_forward(params, z, cond, cfg, u, noise, training=True)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    t = sum(times) / len(times)
+    times.sort()
+    t = times[len(times) // 2]                       # median pass
     desc = (f"oracle.port.generator_forward, 1 image on a {cfg['gen_height']}x{cfg['gen_width']} / render "
             f"{cfg['render_height']}x{cfg['render_width']}x{S} sub-grid ({frac:.4f} of the workload's pixels), "
-            f"{t:.2f} s per pass, scaled by pixel count; fp32, torch {torch.__version__}, {cores} threads")
+            f"median of {len(times)} passes {t:.2f} s (min {times[0]:.2f}, max {times[-1]:.2f}), scaled by pixel count; fp32, "
+            f"torch {torch.__version__}, {cores} threads = len(os.sched_getaffinity(0)) (os.cpu_count() = {os.cpu_count()})")
     return frac / t, cores, desc, t
+
+
+def host_cores():
+    """Cores this process may actually run on (cgroup / affinity aware): `os.cpu_count()` reports the machine's 128 even when
+    the container is given a fraction of them, and 128 torch threads on fewer cores made the round-1 CPU arm swing 19x."""
+    try:
+        n = max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):      # cgroup v2 / v1 CPU quota
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                quota, period = txt[0], float(txt[1])
+            else:
+                quota, period = txt[0], float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota not in ("max", "-1"):
+                n = max(1, min(n, int(float(quota) / period + 0.999)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
 
 
 def run_reference(args, pkg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
+    steps = max(3, min(args.steps, 5))
+    warm = 1
     ips, cores, desc, t = cpu_sample(pkg, args.workload, steps, warm)
     cfg = workload_cfg(pkg, args.workload)
     line = {
@@ -194,6 +218,43 @@ def kernel_costs(cfg, B):
     }
 
 
+def parity_gate(pkg, G, cfg, z, cond, kw, dev, tol=1e-3):
+    """One forward of the benchmarked batch through the module, compared with `oracle.port.generator_forward` run on the
+    same device in fp32 (TF32 off) on the same parameters, latents, poses and random draws.  Raises if the images differ by
+    more than `tol` (relative L2) or are not finite: a fast kernel with different results is not a result."""
+    from oracle import port                              # checker only (never on the timed path)
+    rng = importlib.import_module("3dhumangan_b200.rng")
+    B = z.shape[0]
+    R, S = cfg["render_height"] * cfg["render_width"], cfg["num_steps"]
+    g = torch.Generator(device=dev).manual_seed(1234)
+    u = torch.rand(B, R, S, 1, device=dev, generator=g)
+    noise = torch.randn(B, R, S, 1, device=dev, generator=g)
+    state = {k: v.detach().clone() for k, v in G.state_dict().items()}       # the forward advances buffers (BN, spectral u/v)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    orig = rng.draw_render_noise
+    rng.draw_render_noise = lambda *a, **k: (u, noise)
+    try:
+        with torch.no_grad():
+            out = G(z, cond, **kw)
+            ref = port.generator_forward(state, z, cond, cfg, u, noise, training=True)
+    finally:
+        rng.draw_render_noise = orig
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    res = {}
+    for key in ("rgbs", "rgbs_render"):
+        a, b = out[key].double(), ref[key].double()
+        if not bool(torch.isfinite(a).all()):
+            raise SystemExit(f"bench parity gate: {key} is not finite")
+        res[key] = float((a - b).norm() / b.norm())
+    del ref, state
+    torch.cuda.empty_cache()
+    if max(res.values()) > tol:
+        raise SystemExit(f"bench parity gate FAILED: relative L2 vs oracle {res} > {tol}")
+    return {"checker": "oracle.port.generator_forward on the same device, fp32, TF32 off", "batch": B, "tol": tol,
+            "rel_l2": res}
+
+
 def run_gpu(args, pkg):
     import torch.distributed as dist
     abi = importlib.import_module("3dhumangan_b200.abi")
@@ -206,10 +267,6 @@ def run_gpu(args, pkg):
             raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
-        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # the watchdog must not query events of a capturing stream
-        dist.init_process_group("nccl", device_id=dev)
     abi.require_device()
 
     cfg = workload_cfg(pkg, args.workload)
@@ -229,6 +286,16 @@ def run_gpu(args, pkg):
     d2h = out_h.numel() * 4
     cond_d = {k: v.to(dev) for k, v in cond_h.items()}
     z_d = z_h.to(dev)
+
+    # Parity gate BEFORE anything is timed: this rank's batch, at the benchmarked size, through the same module call,
+    # against the oracle executed on the device in true fp32 (before the process group exists: single-GPU BatchNorm
+    # statistics on both sides; the cross-rank statistics are covered by tests/test_gpu_multi.py).
+    parity = None if args.no_parity else parity_gate(pkg, G, cfg, z_d, cond_d, dict(kw, hg_cuda_graph=False), dev)
+
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # the watchdog must not query events of a capturing stream
+        dist.init_process_group("nccl", device_id=dev)
 
     def step_resident():
         with torch.no_grad():
@@ -285,6 +352,20 @@ def run_gpu(args, pkg):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+
+    # the TIMED path is the graph replay: same seed + same buffers => its pixels must equal the eager launch sequence that
+    # the parity gate compared with the oracle
+    graph_vs_eager = None
+    if not args.no_parity:
+        bufs = {k: v.detach().clone() for k, v in G.named_buffers()}
+        torch.cuda.manual_seed(4321)
+        a = step_resident().double().clone()
+        for k, v in G.named_buffers():
+            v.copy_(bufs[k])
+        torch.cuda.manual_seed(4321)
+        b = step_eager().double()
+        graph_vs_eager = float((a - b).norm() / b.norm())
+        del a, b, bufs
     if os.environ.get("HG3D_BENCH_DEBUG") and rank == 0:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         t0 = time.perf_counter()
@@ -344,7 +425,7 @@ def run_gpu(args, pkg):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        ips, cores, desc, _ = cpu_sample(pkg, args.workload, 1, 0)
+        ips, cores, desc, _ = cpu_sample(pkg, args.workload, 3, 1)
         cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
 
     line = {
@@ -362,6 +443,8 @@ def run_gpu(args, pkg):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "parity_checked": parity is not None and graph_vs_eager is not None and graph_vs_eager < 1e-3,
+        "parity": None if parity is None else dict(parity, graph_replay_vs_eager_rel_l2=graph_vs_eager),
         "eager_ms_per_step": ms_eager / args.steps,
         "clocks": clocks,
         "roofline": roof,
@@ -500,6 +583,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("HG3D_PRECISION", "fp32x3"), choices=["fp32x3", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate (profiling runs)")
     args = ap.parse_args()
     claim_stdout()
     pkg = importlib.import_module("3dhumangan_b200")

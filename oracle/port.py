@@ -106,13 +106,14 @@ def initial_rays(focals, scales, num_steps, render_width, render_height, ray_sta
     """lib/generators/volume_rendering.py:86-110.  Ray r = h*Rw + w."""
     B = focals.shape[0]
     W, H = render_width, render_height
-    xs = torch.linspace(-W / H, W / H, W)
-    ys = torch.linspace(-1, 1, H)
+    dev = focals.device                                   # device-aware: the GPU tests run this checker on the device
+    xs = torch.linspace(-W / H, W / H, W, device=dev)
+    ys = torch.linspace(-1, 1, H, device=dev)
     x = xs[None, :].expand(H, W).reshape(-1)
     y = ys[:, None].expand(H, W).reshape(-1)
     xyz = torch.stack([x[None].expand(B, -1), y[None].expand(B, -1), focals[:, None].expand(B, H * W)], -1)
     d = xyz / (torch.norm(xyz, dim=-1, keepdim=True) + 1e-12)          # util.py:87-91
-    z = torch.linspace(ray_start, ray_end, num_steps).reshape(1, 1, num_steps, 1)
+    z = torch.linspace(ray_start, ray_end, num_steps, device=dev).reshape(1, 1, num_steps, 1)
     z = z.expand(B, H * W, num_steps, 1) + (focals / scales).view(B, 1, 1, 1)
     pts = d[:, :, None, :] * z
     return pts, z, d
@@ -138,8 +139,8 @@ def knn1(points, vertices, chunk=4096):
 
     d2 = (dx*dx + dy*dy) + dz*dz with one fp32 rounding per operation; lowest index on ties."""
     B, N, _ = points.shape
-    d2min = torch.empty(B, N, dtype=torch.float32)
-    idx = torch.empty(B, N, dtype=torch.int64)
+    d2min = torch.empty(B, N, dtype=torch.float32, device=points.device)
+    idx = torch.empty(B, N, dtype=torch.int64, device=points.device)
     for b in range(B):
         vx, vy, vz = (vertices[b, :, k][None].float() for k in range(3))
         for s in range(0, N, chunk):
@@ -340,8 +341,9 @@ def synthesis_network(params, x, style, fixed_style, cfg, training=True, stats_o
 
 def synthesis_input(params, B, Hg, Wg, prefix="synthesis_input."):
     """SynthesisInput.get_2d_coords + forward (map3d_layers.py:260-275): sin(Conv1x1_{2->F}(coords))."""
-    i = torch.linspace(-1, 1, Hg)
-    j = torch.linspace(-1, 1, Wg)
+    w = params[prefix + "network.0.weight"]
+    i = torch.linspace(-1, 1, Hg, device=w.device, dtype=torch.float32).to(w.dtype)
+    j = torch.linspace(-1, 1, Wg, device=w.device, dtype=torch.float32).to(w.dtype)
     coords = torch.stack([i[:, None].expand(Hg, Wg), j[None, :].expand(Hg, Wg)], 0)[None].repeat(B, 1, 1, 1)
     return torch.sin(F.conv2d(coords, params[prefix + "network.0.weight"], params[prefix + "network.0.bias"]))
 
@@ -417,7 +419,7 @@ def discriminator_forward(params, images, cfg, training=True, stats_out=None):
     if min(x.shape[2:4]) > 1:
         latents = F.conv2d(x, params["latent_layer.weight"], params["latent_layer.bias"]).view(x.shape[0], -1)
     else:
-        latents = torch.zeros(x.shape[0], cfg["latent_dim"], dtype=x.dtype)
+        latents = torch.zeros(x.shape[0], cfg["latent_dim"], dtype=x.dtype, device=x.device)
     outs = [ch[nb - 1]] + [ch[nb - i - 1] for i in range(1, nb - 1)] + [64]
     ins = [ch[nb]] + [2 * ch[nb - i] for i in range(1, nb - 1)] + [2 * ch[1]]
     x = res_block(params, "body_up.0", x, 1, False, ins[0] != outs[0], training, stats_out)

@@ -1,6 +1,7 @@
 """CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
 include/hg3d.h declares, the module surfaces carry the reference's state_dict schema, the drop-in
 import paths resolve, and the product path fails loudly without a GPU (no fallback)."""
+import copy
 import importlib
 import json
 import os
@@ -159,3 +160,42 @@ def test_segmentation_loss_matches_reference_trainer():
         loss.backward()
         assert abs(float(loss) - gold["loss"][i]) < 1e-5 * max(1.0, abs(gold["loss"][i])), i
         assert abs(float(s.grad.double().norm()) - gold["grad_norm"][i]) < 1e-5 * gold["grad_norm"][i], i
+
+
+def test_initialisation_statistics_match_reference(pkg):
+    """From-scratch training must start from the reference's distributions: per-tensor std / abs-max of every parameter
+    (3-seed averages) against the unmodified reference modules (tests/golden/make_init_stats.py).  Catches e.g. the
+    spectral-normed discriminator convolutions, whose `weight_orig` the reference re-draws with kaiming-normal through
+    the aliased `.weight` (unet_discriminators.py:74-78,121)."""
+    gen = importlib.import_module("3dhumangan_b200.modules.generator")
+    disc = importlib.import_module("3dhumangan_b200.modules.discriminator")
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "init_stats.json")))
+    cfg = pkg.configs.extract_metadata(copy.deepcopy(pkg.configs.MAP3DBN512), 0)
+    seeds = 3
+    got = {"G": {}, "D": {}}
+    numel = {}
+    for seed in range(seeds):
+        torch.manual_seed(100 + seed)
+        for key, m in (("G", gen.Map3DGenerator(**cfg)), ("D", disc.UNetDiscriminator(**cfg))):
+            for n, p in m.named_parameters():
+                r = got[key].setdefault(n, [0.0, 0.0])
+                numel[key, n] = p.numel()
+                r[0] += (float(p.detach().std()) if p.numel() > 1 else 0.0) / seeds
+                r[1] += float(p.detach().abs().max()) / seeds
+    bad = []
+    checked = 0
+    for key in ("G", "D"):
+        assert set(got[key]) == set(ref[key])
+        for n, (mean, std, amax) in ref[key].items():
+            s, a = got[key][n]
+            if amax == 0 or (std == 0 and numel[key, n] > 1):      # constant initialisation (zeros / ones)
+                if abs(a - amax) > 1e-6:
+                    bad.append((key, n, "absmax", a, amax))
+                continue
+            if numel[key, n] < 64:                 # 1-3 element tensors: sample statistics say nothing
+                continue
+            tol = max(0.03, 6.0 / (2 * numel[key, n] * seeds) ** 0.5)      # ~6 sigma of the sample std, both sides
+            checked += 1
+            if abs(s - std) > tol * std:
+                bad.append((key, n, "std", s, std, tol))
+    assert checked > 250 and not bad, bad[:10]

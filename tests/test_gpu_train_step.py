@@ -40,3 +40,119 @@ def test_train_iteration_updates_both_networks(pkg):
         assert torch.isfinite(p).all()
     # the discriminator loss on fixed data goes down under its own updates
     assert losses[-1][0] < losses[0][0]
+
+
+def _oracle_d_step(port, ts, pg, pd, batch, cfg, u, noise, do_r1):
+    """The discriminator step of phase_trainer.py:344-444 (gan_lambda = 0, segmentation loss, optional R1) composed from
+    the oracle's forward functions under plain torch autograd -- the checker for `Trainer.train_discriminator`."""
+    import torch
+    with torch.no_grad():
+        fake = port.generator_forward(pg, batch["z_d"], batch["cond"], cfg, u, noise, training=True)["rgbs"]
+    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "weight_u" not in k and "weight_v" not in k else v.clone())
+         for k, v in pd.items()}
+    real = batch["images"].clone().requires_grad_(True)
+    st = {}
+    out_real = port.discriminator_forward(P, real, cfg, training=True, stats_out=st)
+    pen = 0.0
+    if do_r1:
+        g = torch.autograd.grad(torch.softmax(out_real["segments"], dim=1).sum(), real, create_graph=True)[0]
+        pen = 0.5 * cfg["r1_lambda"] * g.reshape(g.shape[0], -1).pow(2).sum(1).mean()
+    P2 = dict(P)
+    P2.update({k: v.detach() for k, v in st.items()})          # second pass: power iteration continues from the first
+    out_gen = port.discriminator_forward(P2, fake, cfg, training=True)
+    L = cfg["label_dim"]
+    seg = ts.segmentation_loss(out_real["segments"], batch["labels"], L) + \
+        ts.segmentation_loss(out_gen["segments"], torch.zeros_like(batch["labels"]), L)
+    loss = seg * cfg["segmentation_lambda"] + 4 * pen
+    loss.backward()
+    return loss.detach(), (pen.detach() if do_r1 else None), {k: v.grad for k, v in P.items() if isinstance(v, torch.Tensor) and v.requires_grad}
+
+
+@pytest.mark.parametrize("do_r1", [False, True])
+def test_discriminator_step_matches_oracle_composition(pkg, port, monkeypatch, do_r1):
+    """Loss value, R1 penalty (double backward through the discriminator, r1_lambda = 0.25 as in MAP3DBN) and parameter
+    gradients of `Trainer.train_discriminator` against the same step composed from the oracle under torch autograd."""
+    gen = importlib.import_module("3dhumangan_b200.modules.generator")
+    disc = importlib.import_module("3dhumangan_b200.modules.discriminator")
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    rng = importlib.import_module("3dhumangan_b200.rng")
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        cfg = pkg.configs.baseline_config("tiny")
+        cfg.update(gen_height=64, gen_width=64, render_height=8, render_width=8, num_steps=32, nerf_noise=0.5,
+                   r1_lambda=0.25, grad_clip=1e9)
+        cfg["phases"] = [dict(cfg["phases"][3 if do_r1 else 0])]
+        B = 2
+        pg = {k: v.cuda() for k, v in port.init_generator_params(cfg, seed=5, sigma_gain=200.0, sigma_bias=1.0).items()}
+        pd = {k: v.cuda() for k, v in port.init_discriminator_params(cfg, seed=6).items()}
+        G = gen.Map3DGenerator(**cfg).cuda().train()
+        G.load_state_dict(pg, strict=True)
+        G.set_device(torch.device("cuda:0"))
+        D = disc.UNetDiscriminator(**cfg).cuda().train()
+        D.load_state_dict(pd, strict=True)
+        g = torch.Generator().manual_seed(7)
+        batch = dict(z_d=torch.randn(B, cfg["latent_dim"], generator=g).cuda(),
+                     cond={k: v.cuda() for k, v in pkg.synthetic.make_conditions(B, seed=8).items()},
+                     images=torch.randn(B, 3, 64, 64, generator=g).clamp_(-1, 1).cuda(),
+                     labels=torch.randint(0, cfg["label_dim"], (B, 64, 64), generator=g).cuda())
+        u, noise = rng.draw_render_noise(B, 64, 32, "cuda", cfg["sample_dist"])
+        monkeypatch.setattr(rng, "draw_render_noise", lambda *a, **k: (u, noise))
+        ref_loss, ref_pen, ref_grads = _oracle_d_step(port, ts, pg, pd, batch, cfg, u, noise, do_r1)
+        t = ts.Trainer(G, D, cfg, amp=False, ddp=False)
+        loss = t.train_discriminator(batch)
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * abs(float(ref_loss)), (float(loss), float(ref_loss), ref_pen)
+    if do_r1:
+        assert float(ref_pen) > 1e-4 * float(ref_loss)          # the penalty is a visible part of the loss in this case
+    errs = {}
+    scale = max(float(v.norm()) for v in ref_grads.values() if v is not None)
+    for n, p in D.named_parameters():
+        r = ref_grads.get(n)
+        if r is None or float(r.norm()) < 1e-5 * scale:
+            continue
+        assert p.grad is not None, n
+        errs[n] = float((p.grad.double() - r.double()).norm() / r.double().norm())
+    assert len(errs) > 50
+    vals = sorted(errs.values())
+    assert vals[len(vals) // 2] < 2e-2, (vals[len(vals) // 2], sorted(errs.items(), key=lambda kv: -kv[1])[:5])
+    assert vals[-1] < 0.3, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_trainer_amp_gradscaler_and_param_groups(pkg):
+    """fp16 autocast + GradScaler around both steps (phase_trainer.py:355,396,462), five learning-rate groups
+    (phase_trainer.py:57-76), EMA in parameters() order (ema.py:29-48)."""
+    gen = importlib.import_module("3dhumangan_b200.modules.generator")
+    disc = importlib.import_module("3dhumangan_b200.modules.discriminator")
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    cfg = pkg.configs.baseline_config("tiny")
+    cfg.update(gen_height=64, gen_width=64, render_height=8, render_width=8, num_steps=32, nerf_noise=0.5)
+    B = 2
+    torch.manual_seed(0)
+    G = gen.Map3DGenerator(**cfg).cuda().train()
+    G.set_device(torch.device("cuda:0"))
+    D = disc.UNetDiscriminator(**cfg).cuda().train()
+    t = ts.Trainer(G, D, cfg, amp=True, ddp=False)
+    groups = {g["name"]: g for g in t.optimizer_G.param_groups}
+    assert set(groups) == {"generator", "appearance_codes", "neural_field_mapping", "synthesis_mapping", "neural_field"}
+    assert groups["neural_field"]["lr"] == pytest.approx(cfg["gen_lr"] * 0.05)
+    assert groups["neural_field_mapping"]["lr"] == pytest.approx(cfg["gen_lr"] * 0.05)
+    assert groups["synthesis_mapping"]["lr"] == pytest.approx(cfg["gen_lr"])
+    assert sum(len(g["params"]) for g in groups.values()) == len(list(G.parameters()))
+    batch = dict(cond={k: v.cuda() for k, v in pkg.synthetic.make_conditions(B, seed=1).items()},
+                 images=torch.randn(B, 3, 64, 64, device="cuda").clamp_(-1, 1),
+                 labels=torch.randint(1, cfg["label_dim"], (B, 64, 64), device="cuda"))
+    p0 = [p.detach().clone() for p in G.parameters() if p.requires_grad]
+    for _ in range(4):                    # phases 0..3: the last one is a do_r1 phase (r1_lambda = 0: the graph is still built)
+        d, g_ = t.iteration(batch)
+        assert torch.isfinite(d) and torch.isfinite(g_)
+    assert D.step == 4 and G.step == 4
+    moved = sum(int(not torch.equal(a, b.detach())) for a, b in zip(p0, [p for p in G.parameters() if p.requires_grad]))
+    assert moved > 200
+    # EMA follows the parameters: shadow = p0 + sum of lerps, strictly between the start and the current value where moved
+    for s, a, b in list(zip(t.ema.shadow_params, p0, [p for p in G.parameters() if p.requires_grad]))[:20]:
+        if not torch.equal(a, b.detach()):
+            assert not torch.equal(s, a)
+            assert float((s - a).abs().max()) <= float((b.detach() - a).abs().max()) * 1.0001 + 1e-12
