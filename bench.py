@@ -391,7 +391,17 @@ def run_gpu(args, pkg):
     value = imgs / (ms_total / 1000.0)
     e2e = imgs / (ms_e2e / 1000.0)
 
+    run_leg = args.workload == "C2" and not args.no_train
     if rank != 0:
+        if run_leg:
+            getattr(G, "_graphs", {}).clear()
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            try:
+                train_leg(args, pkg, dev, rank, world, args.train_batch, args.train_steps, 3, args.precision, args.train_split)
+            except Exception:
+                import traceback
+                traceback.print_exc()
         _leave(world, G)
         return
 
@@ -450,36 +460,57 @@ def run_gpu(args, pkg):
         "roofline": roof,
         "cpu_baseline": cpu,
         "kernels": breakdown,
+        "train_step": None,
     }
+    # Second metric of BASELINE.json (G+D training iteration) in the same run, on every rank, so that the driver's
+    # N = 1, 2, 4, 8 scaling runs carry both curves.  The forward line must survive a failure or a hang of this leg:
+    # a watchdog on rank 0 prints the line without it after 15 minutes.
+    if run_leg:
+        import threading
+
+        def give_up():
+            line["train_step"] = {"error": "training leg did not finish within 900 s"}
+            emit(line)
+            os._exit(0)
+
+        dog = threading.Timer(900.0, give_up)
+        dog.daemon = True
+        dog.start()
+        getattr(G, "_graphs", {}).clear()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        try:
+            line["train_step"] = train_leg(args, pkg, dev, rank, world, args.train_batch, args.train_steps, 3, args.precision,
+                                           args.train_split)
+        except Exception as err:
+            import traceback
+            traceback.print_exc()
+            line["train_step"] = {"error": f"{type(err).__name__}: {str(err)[:300]}"}
+        dog.cancel()
     emit(line)
     _leave(world, G)
 
 
-def run_train(args, pkg):
-    """--workload C3: one G+D training iteration (discriminator step, generator step) per step, BASELINE.json's second
-    metric.  Weak scaling over ranks (own batch per rank, gradients averaged over NCCL, SyncBatchNorm statistics
-    all-reduced inside the generator)."""
+def train_leg(args, pkg, dev, rank, world, B, steps, warm, precision, split):
+    """BASELINE.json's second metric: one G+D training iteration (discriminator step, then generator step) per step through
+    `train_step.Trainer` -- the mirror of the reference's PhaseTrainer (DDP wrappers with their gradient all-reduce over
+    NCCL when world > 1, SyncBatchNorm statistics all-reduced inside the generator, five Adam groups, clip, EMA, R1 on its
+    2-of-8 phase schedule).  B images per GPU per iteration, in `split` micro-batches (the reference's `batch_split`).
+    Returns the sub-object that goes into the JSON line (rank 0) or None."""
     import torch.distributed as dist
     abi = importlib.import_module("3dhumangan_b200.abi")
     gen = importlib.import_module("3dhumangan_b200.modules.generator")
     disc = importlib.import_module("3dhumangan_b200.modules.discriminator")
     ts = importlib.import_module("3dhumangan_b200.train_step")
-    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=dev)
-    abi.require_device()
     cfg = workload_cfg(pkg, "C2")
     cfg["nerf_noise"] = 0.5                      # SURVEY.md §8d: C3 trains with sigma noise
-    B = args.batch
+    cfg["batch_split"] = split
+    cfg["hg_precision"] = precision
     torch.manual_seed(0)
     G = gen.Map3DGenerator(**cfg).to(dev).train()
     G.set_device(dev)
     D = disc.UNetDiscriminator(**cfg).to(dev).train()
-    og, od = ts.make_optimizers(G, D, cfg)
-    kw = dict(cfg, hg_precision=args.precision)
+    trainer = ts.Trainer(G, D, cfg, amp=False)
     Hg, Wg = cfg["gen_height"], cfg["gen_width"]
     gcpu = torch.Generator().manual_seed(5 + rank)
     host = dict(z_d=torch.randn(B, cfg["latent_dim"], generator=gcpu), z_g=torch.randn(B, cfg["latent_dim"], generator=gcpu),
@@ -493,40 +524,49 @@ def run_train(args, pkg):
     loss_h = torch.empty(2).pin_memory()
 
     def step_resident():
-        return ts.train_iteration(G, D, og, od, resident, kw)
+        return trainer.iteration(resident)
 
     def step_e2e():
         batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         batch["cond"] = {k: v.to(dev, non_blocking=True) for k, v in cond_h.items()}
-        d, g = ts.train_iteration(G, D, og, od, batch, kw)
-        loss_h.copy_(torch.stack([d, g]), non_blocking=True)
+        d, g = trainer.iteration(batch)
+        loss_h.copy_(torch.stack([d.float(), torch.as_tensor(g, device=dev).float()]), non_blocking=True)
 
-    def timed(fn, n):
+    per_iter = []
+
+    def timed(fn, n, record=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(n):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        ev[0].record()
+        for i in range(n):
+            r1 = bool(cfg["phases"][D.step % len(cfg["phases"])]["do_r1"])
             fn()
-        e.record()
+            ev[i + 1].record()
+            if record:
+                per_iter.append([r1, ev[i], ev[i + 1]])
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        t = torch.tensor([s.elapsed_time(e)], device=dev)
+        t = torch.tensor([ev[0].elapsed_time(ev[n])], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    warm = max(args.warmup, 3)
+    torch.cuda.reset_peak_memory_stats()
     for _ in range(warm):
         step_resident()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(dev.index) if rank == 0 else None
     abi.LAUNCHES = 0
-    ms_total = timed(step_resident, args.steps)
+    ms_total = timed(step_resident, steps, record=True)
     launches = abi.LAUNCHES
     clocks = sampler.stop() if sampler else None
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
+    finite = bool(torch.isfinite(loss_h).all())
+    it_ms = [(r1, a.elapsed_time(b)) for r1, a, b in per_iter]
+    ms_r1 = [m for r1, m in it_ms if r1]
+    ms_plain = [m for r1, m in it_ms if not r1]
     abi.TIMING = []
     torch.cuda.synchronize()
     step_resident()
@@ -537,27 +577,59 @@ def run_train(args, pkg):
         d[0] += s_.elapsed_time(e_)
         d[1] += 1
     abi.TIMING = None
+    peak_mem = torch.cuda.max_memory_allocated() / 1e9
+    del trainer, G, D, resident
+    torch.cuda.empty_cache()
     if rank != 0:
-        _leave(world, G)
-        return
-    imgs = B * world * args.steps
-    line = {
+        return None
+    imgs = B * world * steps
+    # reference-equivalent work of an iteration: 10.8 TFLOP per image as the reference executes it
+    eq_tflops = 10.8 * imgs / (ms_total / 1e3)
+    pk = peaks()
+    return {
         "metric": "images_per_sec_GD_train_step_512x512", "value": imgs / (ms_total / 1e3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.precision == "fp32x3" else "bf16",
-        "data": "synthetic",
-        "config": {"workload": f"C3: one discriminator step + one generator step (segmentation loss, R1 weight 0 as in configs/map3d.py:98-191), "
-                               f"batch {B}/GPU, 512x512, render 96x96, 32 samples/ray, hidden 256, Adam, grad clip 1, random init, synthetic data",
-                   "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single GPU",
-                   "l2": "activations >> 126 MB L2: no flush needed", "precision": args.precision, "launch": "eager"},
+        "steps": steps, "warmup": warm, "ms_per_step": ms_total / steps, "scaling": "weak",
+        "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)" if precision == "fp32x3" else "bf16 products, fp32 storage",
+        "config": {"workload": f"C3: one discriminator step + one generator step per iteration (train_step.Trainer = PhaseTrainer's "
+                               f"steps: segmentation loss, R1 on its 2-of-8 phase schedule with r1_lambda = {cfg['r1_lambda']} as in "
+                               f"configs/map3d.py:98-191, five Adam groups, grad clip 1, EMA), {B} images/GPU/iteration in {split} "
+                               f"micro-batch(es) of {B // split} (the reference's batch_split), 512x512, render 96x96, 32 samples/ray, "
+                               f"hidden 256, random init, synthetic images / labels / poses; no path-length regulariser exists in the reference",
+                   "global_batch": B * world,
+                   "parallelism": (f"dp{world}: DistributedDataParallel(find_unused_parameters=True) gradient all-reduce over NCCL for G and D "
+                                   f"+ SyncBatchNorm statistics") if world > 1 else "single GPU",
+                   "precision": precision, "launch": "eager"},
         "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None,
-        "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                "ms_per_step": ms_e2e / steps},
+        "gpu_launches": launches, "losses_finite": finite, "clocks": clocks, "peak_mem_gb": peak_mem,
+        "iteration_ms": {"do_r1": (sum(ms_r1) / len(ms_r1)) if ms_r1 else None,
+                         "plain": (sum(ms_plain) / len(ms_plain)) if ms_plain else None,
+                         "r1_iterations_timed": len(ms_r1), "plain_iterations_timed": len(ms_plain),
+                         "schedule": "do_r1 on 2 of 8 phases (configs/map3d.py:104-113)"},
+        "roofline": {"bound": "tensor", "achieved": eq_tflops / world, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": eq_tflops / world / pk["bf16_tflops_sustained"], "traffic": None,
+                     "note": "reference-equivalent FLOPs of the whole iteration (10.8 TFLOP/image, SURVEY.md 8d) per GPU vs the "
+                             "sustained bf16 tensor peak; fp32x3 issues 3 MMA passes per product"},
         "kernels": {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])},
     }
-    emit(line)
-    _leave(world, G)
+
+
+def run_train(args, pkg):
+    """--workload C3: only the G+D training-iteration metric, as its own JSON line."""
+    import torch.distributed as dist
+    abi = importlib.import_module("3dhumangan_b200.abi")
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    abi.require_device()
+    leg = train_leg(args, pkg, dev, rank, world, args.train_batch, args.steps, max(args.warmup, 3), args.precision, args.train_split)
+    if rank == 0:
+        leg.update(higher_is_better=True, vs_baseline=None, data="synthetic", cpu_baseline=None)
+        emit(leg)
+    _leave(world, None)
 
 
 def _leave(world, G):
@@ -565,7 +637,8 @@ def _leave(world, G):
     by live CUDA graphs blocks, so drop the graphs, drain the device and leave the process directly."""
     if world <= 1:
         return
-    getattr(G, "_graphs", {}).clear()
+    if G is not None:
+        getattr(G, "_graphs", {}).clear()
     torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
@@ -584,6 +657,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate (profiling runs)")
+    ap.add_argument("--no-train", action="store_true", help="skip the G+D training-iteration leg of the default run")
+    ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per training iteration (config C3: 16)")
+    ap.add_argument("--train-split", type=int, default=2, help="micro-batches per iteration (the reference's batch_split)")
+    ap.add_argument("--train-steps", type=int, default=4, help="timed training iterations in the default run")
     args = ap.parse_args()
     claim_stdout()
     pkg = importlib.import_module("3dhumangan_b200")

@@ -65,9 +65,9 @@ def test_generator_forward_at_c2_size(pkg, port, monkeypatch, mode, graph):
     G = _generator(cfg, params)
     cg, zg = _to(cond, "cuda"), z.cuda()
     with torch.no_grad():
+        # graph=True: the returned pixels come from the REPLAY of the captured forward (the warm-up run's effects on the
+        # buffers are rolled back before the capture), i.e. exactly one forward from the initial state, like the oracle's
         out = G(zg, cg, **dict(cfg, hg_cuda_graph=graph))
-        if graph:       # second replay: the graph itself, not the warm-up run (buffers advance; pixels use batch statistics)
-            out = G(zg, cg, **dict(cfg, hg_cuda_graph=graph))
     torch.cuda.synchronize()
     pg = _to(params, "cuda")
     stats = {}
