@@ -66,6 +66,8 @@ SIGNATURES = {
     "hg_pool_add": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_void_p]),
     "hg_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hg_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "hg_spectral_entry_bytes": (c_int, []),
+    "hg_spectral_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p]),
 }
 
 
@@ -171,6 +173,33 @@ def linear(X, Wimg, Nb, N, bias=None, passes=3, out=None):
         call("hg_linear", c_void_p(X.data_ptr()), X.stride(0), M, K, ptr(Wimg), Nb, N, ptr(bias),
                               ptr(out), out.stride(0), passes, stream())
     return out
+
+
+_SN_TABLES = {}
+
+
+def spectral_norm(ws, us, vs, training, eps=1e-12):
+    """One launch for a list of weights: power iteration (training: u / v buffers updated in place) and 1/sigma.
+    ws: tensors whose first dim is N (viewed as [N, K]), us [N], vs [K].  Returns inv_sigma [n] fp32."""
+    import numpy as np
+    dev = ws[0].device
+    key = tuple((w.data_ptr(), u.data_ptr(), v.data_ptr(), w.shape[0], w.numel() // w.shape[0]) for w, u, v in zip(ws, us, vs))
+    ent = _SN_TABLES.get(key)
+    if ent is None:
+        assert int(lib().hg_spectral_entry_bytes()) == 32
+        for w, u, v in zip(ws, us, vs):
+            assert w.is_contiguous() and u.is_contiguous() and v.is_contiguous() and w.dtype == u.dtype == v.dtype == torch.float32
+        tab = np.zeros((len(ws), 4), dtype=np.int64)
+        for i, (w_, u_, v_, n, k) in enumerate(key):
+            tab[i] = (w_, u_, v_, n | (k << 32))
+        if len(_SN_TABLES) > 64:
+            _SN_TABLES.clear()
+        ent = _SN_TABLES[key] = (torch.from_numpy(tab).to(dev), max(k_[3] for k_ in key), max(k_[4] for k_ in key))
+    table, max_n, max_k = ent
+    inv = torch.empty(len(ws), dtype=torch.float32, device=dev)
+    with torch.cuda.device_of(inv):
+        call("hg_spectral_norm", ptr(table), len(ws), max_n, max_k, ptr(inv), int(bool(training)), float(eps), stream())
+    return inv
 
 
 def vertex_ik(fk, lbs):

@@ -4,8 +4,8 @@ Mirrors `UNetDiscriminator.forward` / `ResBlock.forward` (lib/discriminators/une
 125-160).  Per ResBlock: two implicit-GEMM 3x3 convolutions with LeakyReLU / nearest up-sample / channel
 concat folded into the operand producer and the residual add folded into the second conv's epilogue (up
 path) or into the pooling kernel (down path); the two 1x1 heads run as ONE convolution with 27 outputs.
-Spectral normalisation (one power iteration per training forward, buffers updated in place) is a handful
-of tiny torch ops per conv; 1/sigma is applied while packing the bf16 operand image.
+Spectral normalisation (one power iteration per training forward, buffers updated in place) is ONE launch of
+`hg_spectral_norm` for all 30 convolutions; 1/sigma is applied while packing the bf16 operand image.
 """
 from __future__ import annotations
 
@@ -15,15 +15,18 @@ import torch.nn.functional as F
 from .. import abi
 
 
-def _sigma_inv(P, name, training, eps=1e-12):
-    w = P[name + ".weight_orig"]
-    u, v = P[name + ".weight_u"], P[name + ".weight_v"]
-    wm = w.reshape(w.shape[0], -1)
-    with torch.no_grad():
-        if training:
-            v.copy_(F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps))
-            u.copy_(F.normalize(torch.mv(wm, v), dim=0, eps=eps))
-        return (1.0 / torch.dot(u, torch.mv(wm, v))).reshape(1)
+def sn_layer_names(P):
+    """State-dict prefixes (without the trailing dot) of the spectral-normed convolutions, in registration order."""
+    return [k[:-len(".weight_orig")] for k in P if k.endswith(".weight_orig")]
+
+
+def _sigma_inv_all(P, training):
+    """{name: 1/sigma [1]} for every spectral-normed convolution: ONE `hg_spectral_norm` launch (power iteration with the
+    u / v buffers updated in place when training), unet_discriminators.py:18."""
+    names = sn_layer_names(P)
+    inv = abi.spectral_norm([P[n + ".weight_orig"].detach() for n in names], [P[n + ".weight_u"] for n in names],
+                            [P[n + ".weight_v"] for n in names], training)
+    return {n: inv[i:i + 1] for i, n in enumerate(names)}
 
 
 def _pack_conv(w, scale_dev=None):
@@ -46,10 +49,11 @@ def discriminator_forward(module, images, passes=None):
     B = x.shape[0]
     nb = module.num_blocks
     sn = not module._cfg.get("disable_spectral_norm", False)
+    inv_sigma = _sigma_inv_all(P, training) if sn else {}
 
     def conv(name, x1, *, ksize, H, W, x2=None, up2=False, pre_lrelu=False, residual=None, res_up2=False):
         if sn:
-            img, Nb = _pack_conv(P[name + ".weight_orig"], _sigma_inv(P, name, training))
+            img, Nb = _pack_conv(P[name + ".weight_orig"], inv_sigma[name])
         else:
             img, Nb = _pack_conv(P[name + ".weight"])
         Cout = P[name + ".bias"].shape[0]

@@ -10,7 +10,8 @@ ops, so that first-order gradients w.r.t. images (generator step) and parameters
                                    are themselves differentiable (R1 double backward, phase_trainer.py:259-294)
     LeakyReLU        `ops.bias_act` (hg_bias_act / hg_bias_act_grad)
     avg-pool / nearest up-sample   `ops.upfirdn2d` with a 2x2 box filter (its backward is another upfirdn pass)
-    spectral norm    torch autograd on W / sigma (one power iteration per training forward, buffers in place)
+    spectral norm    `hg_spectral_norm` (one launch for all layers: power iteration, buffers in place) + a differentiable
+                     W / sigma scale node (`synthesis_ops.SpectralScale`)
     residual add, channel concat, the full-extent `latent_layer`: torch (`+`, `cat`, one library GEMM)
 
 Mirrors UNetDiscriminator.forward / ResBlock.forward (lib/discriminators/unet_discriminators.py:47-72, 125-160).
@@ -138,20 +139,6 @@ def _up(x):
     return _Resample2x.apply(x, True, 1.0)
 
 
-def _sn_weight(P, name, training, enabled, eps=1e-12):
-    if not enabled:
-        return P[name + ".weight"]
-    w = P[name + ".weight_orig"]
-    u, v = P[name + ".weight_u"], P[name + ".weight_v"]
-    wm = w.reshape(w.shape[0], -1)
-    with torch.no_grad():
-        if training:
-            v.copy_(F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps))
-            u.copy_(F.normalize(torch.mv(wm, v), dim=0, eps=eps))
-    sigma = torch.dot(u.detach().clone(), torch.mv(wm, v.detach().clone()))
-    return w / sigma
-
-
 def discriminator_forward_train(module, images, passes=3, masks=None):
     """Differentiable forward.  `masks`: optional list that receives the LeakyReLU masks in application order (tests)."""
     abi.require_device()
@@ -160,9 +147,13 @@ def discriminator_forward_train(module, images, passes=3, masks=None):
     sn = not module._cfg.get("disable_spectral_norm", False)
     nb = module.num_blocks
     B = images.shape[0]
+    from .discriminator_ops import sn_layer_names
+    from .synthesis_ops import sn_weights
+    w_sn = sn_weights(P, [n + "." for n in sn_layer_names(P)], training) if sn else {}
 
     def conv(name, x, spectral=True):
-        return Conv2dSame.apply(x, _sn_weight(P, name, training, sn and spectral), P[name + ".bias"], passes)
+        w = w_sn[name + "."] if (sn and spectral) else P[name + ".weight"]
+        return Conv2dSame.apply(x, w, P[name + ".bias"], passes)
 
     x = images.float()
     skips = []

@@ -62,8 +62,9 @@ def _kaiming_leaky_(w, a=0.2):
 
 
 class MappingNetwork(nn.Module):
-    """z -> (freq, phase) for the SIREN (lib/components/mapping_networks.py:13-41).  Four tiny
-    [B,256] GEMMs: plain library calls (cuBLAS via torch), fp32."""
+    """z -> (freq, phase) for the SIREN (lib/components/mapping_networks.py:13-41).  The four dense layers run on the
+    tcgen05 GEMM (`ops.dense`, fp32 via the bf16x3 split), LeakyReLU on `ops.bias_act`; the `nn.Linear` /
+    `nn.LeakyReLU` children only hold the parameters under the reference's state_dict names."""
 
     def __init__(self, latent_dim, map_hidden_dim, map_output_dim):
         super().__init__()
@@ -78,16 +79,22 @@ class MappingNetwork(nn.Module):
             self.network[-1].weight *= 0.25
 
     def forward(self, z):
-        z = z.to(torch.float32)
-        z = z * (z.square().mean(dim=1, keepdim=True) + 1e-8).rsqrt()
-        fp = self.network(z)
-        half = fp.shape[-1] // 2
-        return fp[..., :half], fp[..., half:]
+        from ..ops import bias_act
+        from ..ops.dense import dense
+        x = z.to(torch.float32)
+        x = x * (x.square().mean(dim=1, keepdim=True) + 1e-8).rsqrt()
+        for m in self.network:
+            if isinstance(m, nn.Linear):
+                x = dense(x, m.weight, m.bias)
+            else:
+                x = bias_act.bias_act(x, None, act="lrelu", alpha=m.negative_slope, gain=1.0)
+        half = x.shape[-1] // 2
+        return x[..., :half], x[..., half:]
 
 
 class FullyConnectedLayer(nn.Module):
-    """StyleGAN-style equalised-lr dense layer (mapping_networks.py:92-121); bias+activation through
-    the sm_100a `bias_act` op."""
+    """StyleGAN-style equalised-lr dense layer (mapping_networks.py:92-121): the product on the tcgen05 GEMM with the
+    weight gain folded into the operand packing (`ops.dense`), bias + activation through the `bias_act` kernel."""
 
     def __init__(self, in_features, out_features, bias=True, activation="linear", lr_multiplier=1, bias_init=0):
         super().__init__()
@@ -99,15 +106,13 @@ class FullyConnectedLayer(nn.Module):
 
     def forward(self, x):
         from ..ops import bias_act
-        w = self.weight.to(x.dtype) * self.weight_gain
+        from ..ops.dense import dense
         b = self.bias
-        if b is not None:
-            b = b.to(x.dtype)
-            if self.bias_gain != 1:
-                b = b * self.bias_gain
-        if self.activation == "linear" and b is not None:
-            return torch.addmm(b.unsqueeze(0), x, w.t())
-        return bias_act.bias_act(x.matmul(w.t()), b, act=self.activation)
+        if b is not None and self.bias_gain != 1:
+            b = b * self.bias_gain
+        if self.activation == "linear":
+            return dense(x, self.weight, b, gain=self.weight_gain)
+        return bias_act.bias_act(dense(x, self.weight, None, gain=self.weight_gain), b, act=self.activation)
 
 
 class TwoPartMappingNetwork(nn.Module):

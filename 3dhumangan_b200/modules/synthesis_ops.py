@@ -28,21 +28,43 @@ STAT_STRIDE = 520  # doubles per statistics row: [0:256] sum, [256:512] sumsq, [
 
 
 def spectral_sigma_batched(w_list, u_list, v_list, training, eps=1e-12):
-    """One power iteration per training forward for a list of same-shape [N,K] matrices
-    (torch.nn.utils.spectral_norm semantics, map3d_layers.py:205-206).  Updates u/v in place.
-    Returns 1/sigma as a tensor [n]."""
-    W = torch.stack([w.reshape(w.shape[0], -1) for w in w_list])          # [n,N,K]
-    u = torch.stack(list(u_list))                                         # [n,N]
-    v = torch.stack(list(v_list))                                         # [n,K]
+    """One power iteration per training forward for a list of weights (torch.nn.utils.spectral_norm semantics,
+    map3d_layers.py:205-206) in ONE launch of `hg_spectral_norm`; u / v are updated in place.  Returns 1/sigma [n]."""
+    return abi.spectral_norm(list(w_list), list(u_list), list(v_list), training, eps)
+
+
+class SpectralScale(torch.autograd.Function):
+    """W / sigma with sigma = u^T W v (u, v constants): forward = W * inv_sigma (inv_sigma from hg_spectral_norm), backward
+    dW = g / sigma - <g, W> / sigma^2 * u v^T -- elementwise torch ops only, differentiable again."""
+
+    @staticmethod
+    def forward(ctx, w, u, v, inv_sigma):
+        ctx.save_for_backward(w, u, v, inv_sigma)
+        return w * inv_sigma
+
+    @staticmethod
+    def backward(ctx, g):
+        w, u, v, inv_sigma = ctx.saved_tensors
+        wm = w.reshape(w.shape[0], -1)
+        gm = g.reshape(w.shape[0], -1)
+        coef = (gm * wm).sum() * inv_sigma * inv_sigma
+        dw = gm * inv_sigma - coef * (u[:, None] * v[None, :])
+        return dw.reshape(w.shape), None, None, None
+
+
+def sn_weights(P, names, training, suffix=""):
+    """{name: W/sigma with autograd history to weight_orig} for a list of spectral-normed layers: ONE batched
+    power-iteration launch, then a differentiable scale per layer.  `names` are state_dict prefixes ending in '.'."""
+    ws = [P[n + "weight_orig"] for n in names]
+    us = [P[n + "weight_u"] for n in names]
+    vs = [P[n + "weight_v"] for n in names]
     with torch.no_grad():
-        if training:
-            v = F.normalize(torch.bmm(W.transpose(1, 2), u[:, :, None])[:, :, 0], dim=1, eps=eps)
-            u = F.normalize(torch.bmm(W, v[:, :, None])[:, :, 0], dim=1, eps=eps)
-            for i, (ub, vb) in enumerate(zip(u_list, v_list)):
-                ub.copy_(u[i])
-                vb.copy_(v[i])
-        sigma = (u * torch.bmm(W, v[:, :, None])[:, :, 0]).sum(1)
-    return 1.0 / sigma
+        inv = abi.spectral_norm([w.detach() for w in ws], us, vs, training)
+    out = {}
+    for i, n in enumerate(names):
+        # clones: the buffers are overwritten by the next forward's power iteration while this graph may still be alive
+        out[n] = SpectralScale.apply(ws[i], us[i].detach().clone(), vs[i].detach().clone(), inv[i])
+    return out
 
 
 def _gamma_beta_interleaved(wg, bg, wb, bb):

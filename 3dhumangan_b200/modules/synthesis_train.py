@@ -35,22 +35,9 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from .. import abi
-from .synthesis_ops import STAT_STRIDE, _PtrView, _gamma_beta_interleaved, _spade, all_reduce_stats, is_pixel_style
+from .synthesis_ops import STAT_STRIDE, _PtrView, _gamma_beta_interleaved, _spade, all_reduce_stats, is_pixel_style, sn_weights
 
 C = 256
-
-
-def _sn_weight(P, name, training, eps=1e-12):
-    """W / sigma with torch.nn.utils.spectral_norm semantics: power iteration without autograd (buffers updated
-    in place when training), sigma = u^T W v differentiable w.r.t. W only."""
-    w = P[name + "weight_orig"].reshape(C, C)
-    u, v = P[name + "weight_u"], P[name + "weight_v"]
-    with torch.no_grad():
-        if training:
-            v.copy_(F.normalize(torch.mv(w.t(), u), dim=0, eps=eps))
-            u.copy_(F.normalize(torch.mv(w, v), dim=0, eps=eps))
-    sigma = torch.dot(u.detach().clone(), torch.mv(w, v.detach().clone()))
-    return w / sigma
 
 
 class SynthesisTape:
@@ -129,6 +116,9 @@ def synthesis_forward_train(params, feat_lr, fixed_style, cfg, *, passes=3, pref
     abi.synth_input(w_in, P[input_prefix + "network.0.bias"].detach(), ic, jc, x0, stats[0], B)
     tape.input = dict(w=w_in, ic=ic, jc=jc, prefix=input_prefix)
 
+    # spectral normalisation of the 18 convolutions: one launch (power iteration, buffers in place), W / sigma with history
+    w_sns = sn_weights(P, [blk(k) + f"conv_{j}." for k, j in halves], True)
+
     rgb_cur = None
     cur, cur_bstride = x0, 0
     block_in = None
@@ -158,7 +148,7 @@ def synthesis_forward_train(params, feat_lr, fixed_style, cfg, *, passes=3, pref
             if (bn + "num_batches_tracked") in P:
                 P[bn + "num_batches_tracked"] += 1
         conv = blk(k) + f"conv_{j}."
-        w_sn = _sn_weight(P, conv, True)
+        w_sn = w_sns[conv].reshape(C, C)
         wimg = abi.pack_weight(w_sn.detach().contiguous(), Nb=256)[0]
         if j == 0:
             block_in = (cur, cur_bstride, idx)

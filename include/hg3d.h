@@ -228,6 +228,15 @@ int hg_pool_add(const float* a, int pool_a, const float* b, int pool_b, float* o
 /* out[B,O] = x[B,K] . w[O,K]^T + bias: the full-extent `latent_layer` convolution (:117-118,135). */
 int hg_dense(const float* x, const float* w, const float* bias, float* out, int B, int K, int O, void* stream);
 
+/* Spectral normalisation of a list of weights in one launch: torch.nn.utils.spectral_norm's forward pre-hook as applied at
+ * lib/components/map3d_layers.py:205-206 (18 synthesis convolutions) and lib/discriminators/unet_discriminators.py:18
+ * (30 discriminator convolutions).  table: `count` entries of hg_spectral_entry_bytes() = 32 bytes
+ * { const float* w [N,K]; float* u [N]; float* v [K]; int32 N; int32 K }.  training != 0: v <- normalize(W^T u),
+ * u <- normalize(W v) written back in place; inv_sigma[i] = 1 / (u . W v).  max_n / max_k bound the table's shapes. */
+int hg_spectral_entry_bytes(void);
+int hg_spectral_norm(const void* table, int count, int max_n, int max_k, float* inv_sigma, int training, float eps,
+                     void* stream);
+
 /* ---- StyleGAN3 native ops named by the reference ---------------------------------------------- */
 /* y = clamp(act(x + b[(i / stepB) % sizeB]) * gain)   replaces bias_act.cpp:32 / bias_act.cu:24 (forward).
  * act: 1 linear 2 relu 3 lrelu 4 tanh 5 sigmoid 6 elu 7 selu 8 softplus 9 swish; clamp < 0 disables. */

@@ -111,3 +111,54 @@ def test_upfirdn2d_gradients(port):
             res.append((gx.detach().cpu(), gw.detach().cpu()))
         assert torch.allclose(res[1][0], res[0][0], rtol=1e-5, atol=1e-5), kw
         assert torch.allclose(res[1][1], res[0][1], rtol=1e-4, atol=1e-4), kw
+
+
+def test_spectral_norm_kernel_matches_torch():
+    """hg_spectral_norm: a table of matrices of different shapes in one launch vs torch.nn.utils.spectral_norm's arithmetic
+    (one power iteration in training mode with in-place buffer updates; stored vectors in eval mode)."""
+    import importlib
+    import torch.nn.functional as F
+    abi = importlib.import_module("3dhumangan_b200.abi")
+    g = torch.Generator().manual_seed(0)
+    shapes = [(256, 256), (128, 27), (512, 4608), (64, 2304), (3, 64), (256, 1152)]
+    ws = [torch.randn(n, k, generator=g).cuda() / k ** 0.5 for n, k in shapes]
+    us = [F.normalize(torch.randn(n, generator=g), dim=0).cuda() for n, _ in shapes]
+    vs = [F.normalize(torch.randn(k, generator=g), dim=0).cuda() for _, k in shapes]
+    for training in (True, False, True):
+        ref = []
+        for w, u, v in zip(ws, us, vs):
+            wd, ud, vd = w.double(), u.double(), v.double()
+            if training:
+                vd = F.normalize(wd.t() @ ud, dim=0, eps=1e-12)
+                ud = F.normalize(wd @ vd, dim=0, eps=1e-12)
+            ref.append((ud, vd, torch.dot(ud, wd @ vd)))
+        inv = abi.spectral_norm(ws, us, vs, training)
+        torch.cuda.synchronize()
+        for i, (ud, vd, sig) in enumerate(ref):
+            assert abs(float(inv[i]) * float(sig) - 1.0) < 2e-6, (i, training)
+            assert float((us[i].double() - ud).norm()) < 2e-6 and float((vs[i].double() - vd).norm()) < 2e-6, (i, training)
+    a = abi.spectral_norm(ws, us, vs, False)
+    b = abi.spectral_norm(ws, us, vs, False)
+    assert torch.equal(a, b)                                 # deterministic summation order
+
+
+def test_dense_forward_backward_matches_torch():
+    """ops.dense (the mapping networks' layers on hg_linear): value, dX, dW, db vs fp64 torch, incl. contraction > 256."""
+    import importlib
+    dn = importlib.import_module("3dhumangan_b200.ops.dense")
+    g = torch.Generator().manual_seed(1)
+    for (M, K, N, gain) in [(8, 256, 256, 1.0), (5, 256, 2048, 0.01 / 16), (16, 420, 420, 1.0), (300, 64, 96, 2.0)]:
+        x = torch.randn(M, K, generator=g)
+        w = torch.randn(N, K, generator=g) / K ** 0.5
+        b = torch.randn(N, generator=g)
+        gy = torch.randn(M, N, generator=g)
+        xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+        yr = xr @ (wr * gain).t() + br
+        yr.backward(gy.double())
+        xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
+        y = dn.dense(xc, wc, bc, gain=gain)
+        y.backward(gy.cuda())
+        torch.cuda.synchronize()
+        rel = lambda a_, r_: float((a_.detach().cpu().double() - r_).norm() / r_.norm())
+        assert rel(y, yr.detach()) < 2e-5, (M, K, N)
+        assert rel(xc.grad, xr.grad) < 2e-5 and rel(wc.grad, wr.grad) < 2e-5 and rel(bc.grad, br.grad) < 1e-5, (M, K, N)
