@@ -61,6 +61,7 @@ SIGNATURES = {
     "hg_bias_act_grad": (c_int, [c_void_p] * 6 + [c_long, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_resample2x": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_void_p]),
     "hg_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 14 + [c_float, c_void_p]),
+    "hg_upfirdn2d_sep2": (c_int, [c_void_p, c_void_p, c_void_p, c_long] + [c_int] * 9 + [c_float, c_void_p]),
     "hg_conv2d": (c_int, [c_void_p, c_int, c_void_p, c_int] + [c_int] * 6 + [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
                               c_void_p, c_int, c_void_p]),
     "hg_pool_add": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_void_p]),

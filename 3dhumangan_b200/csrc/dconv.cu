@@ -11,6 +11,7 @@
 // K = taps x Cin in chunks of 64 (one tap, 64 channels); a 4-slot operand ring decouples the row warps
 // from the MMA thread.  Weights are pre-packed as [Cout, tap, Cin] (hg_pack_weight).
 // AvgPool2d(2) of the down path is a separate streaming kernel (hg_pool_add).
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -300,6 +301,21 @@ __global__ void dense_kernel(const float* __restrict__ x, const float* __restric
 
 }  // namespace hg
 
+// dconv_halo.cu
+int hg_conv3x3_halo_launch(const float* x1, int C1, const float* x2, int C2, int B, int H, int W, int up2, int pre_lrelu,
+                           const void* wimg, int Cout, int Nb, const float* bias, const float* residual, int res_up2,
+                           float* out, int passes, void* stream);
+bool hg_conv3x3_halo_eligible(int C1, int C2, int H, int W, int ksize, int Cout, int Nb);
+
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HG3D_CONV_HALO");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" {
 
 int hg_conv2d(const float* x1, int C1, const float* x2, int C2, int B, int H, int W, int up2, int pre_lrelu, int ksize,
@@ -318,6 +334,11 @@ int hg_conv2d(const float* x1, int C1, const float* x2, int C2, int B, int H, in
   HG_REQUIRE(!small || C2 == 0, "hg_conv2d: the small-Cin path takes a single input");
   const int nblocks = (Cout + Nb - 1) / Nb;
   HG_REQUIRE(nblocks <= 2, "hg_conv2d: at most two N blocks (Cout <= 2*Nb)");
+  // 3x3 convolutions on rows of >= 128 pixels (84 % of the discriminator's FLOPs): one haloed operand tile per K chunk,
+  // nine taps by descriptor offset (dconv_halo.cu)
+  if (!small && halo_enabled() && hg_conv3x3_halo_eligible(C1, C2, H, W, ksize, Cout, Nb))
+    return hg_conv3x3_halo_launch(x1, C1, x2, C2, B, H, W, up2, pre_lrelu, wimg, Cout, Nb, bias, residual, res_up2, out,
+                                  passes, stream);
   hg::ConvArgs a{x1, x2, C1, C2, B, H, W, up2, pre_lrelu, ksize, static_cast<const uint8_t*>(wimg), Cout, Nb, nblocks,
                  small ? 1 : taps * Cin / 64, bias, residual, out, small, res_up2};
   const int tiles = B * ((H * W + 127) / 128);

@@ -190,6 +190,158 @@ __global__ void __launch_bounds__(128) upfirdn2d_kernel(const float* __restrict_
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused separable 2x resampler: BOTH 1-D passes of a separable up-by-2 or down-by-2 FIR in one kernel, the intermediate
+// in shared memory.  These are the reference's only upfirdn2d call shapes (augment.py:314,325: `upsample2d(x, sym6, up=2)`,
+// `downsample2d(x, sym6, down=2)` with the 12-tap sym6 filter, executed there as two 1-D passes, upfirdn2d.py:243-244).
+// HBM traffic = read x + write y (the two-pass form also writes and re-reads an intermediate of the larger size).
+//
+// Per CTA: an output tile TOH x TOW.  (1) the input tile it depends on is staged in shared memory (zero outside the
+// image: that IS the padding); (2) horizontal pass -> `mid` [input rows x TOW]; (3) vertical pass -> global.  In (2) and
+// (3) a thread produces 4 consecutive outputs from one register window (T/2+2 values for up, T+6 for down), so a
+// shared-memory word is read ~1/3 as often as a scalar tap loop would; all register indices are compile-time constants
+// (T is a template parameter, the polyphase selection depends only on the parity of the padding: one uniform branch).
+//   up  : y[o] = sum_t g[e + 2t] * x[i0 + t],  e = (pad0 - o) & 1, i0 = (o + e - pad0) / 2        (zero-insertion skipped)
+//   down: y[o] = sum_k g[k] * x[2o + k - pad0]
+// g = filter flipped unless flip_filter (upfirdn2d.py:200-203), times sqrt(gain) per axis.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int T, bool kUp>
+struct SepGeom {
+  static constexpr int TOW = 64;
+  static constexpr int TOH = kUp ? 64 : 32;
+  static constexpr int NV = kUp ? T / 2 + 2 : T + 6;                 // register window for 4 outputs
+  static constexpr int TIW = kUp ? TOW / 2 + T / 2 + 1 : 2 * TOW + T - 2;
+  static constexpr int TIH = kUp ? TOH / 2 + T / 2 + 1 : 2 * TOH + T - 2;
+  static constexpr int PIN = TIW | 1;                                 // odd pitches: conflict-free column walks
+  static constexpr int PMID = TOW + 1;
+  static constexpr int SMEM = (TIH * PIN + TIH * PMID + T) * 4;
+};
+
+// first input index touched by output o (floor semantics for negative values)
+template <bool kUp>
+__device__ __forceinline__ int sep_first(int o, int pad0) {
+  if (kUp) return (o - pad0 + 1) >> 1;      // ceil((o - pad0) / 2)
+  return 2 * o - pad0;
+}
+
+// 4 outputs from a register window v[]; `odd` = parity of (o0 - pad0) (up only)
+template <int T, bool kUp>
+__device__ __forceinline__ void sep_fir4(const float* __restrict__ v, const float* __restrict__ g, bool odd, float (&o)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o[q] = 0.f;
+  if (kUp) {
+    // c = o - pad0.  c even: e = 0, start (c/2 - b);  c odd: e = 1, start ((c+1)/2 - b);  b = ceil(c0 / 2)
+    if (!odd) {       // c0 even: b = c0/2; q=0: e0 s0 | q=1: e1 s1 | q=2: e0 s1 | q=3: e1 s2
+#pragma unroll
+      for (int t = 0; t < T / 2; ++t) {
+        o[0] = fmaf(g[2 * t], v[t], o[0]);
+        o[1] = fmaf(g[2 * t + 1], v[t + 1], o[1]);
+        o[2] = fmaf(g[2 * t], v[t + 1], o[2]);
+        o[3] = fmaf(g[2 * t + 1], v[t + 2], o[3]);
+      }
+    } else {          // c0 odd: b = (c0+1)/2; q=0: e1 s0 | q=1: e0 s0 | q=2: e1 s1 | q=3: e0 s1
+#pragma unroll
+      for (int t = 0; t < T / 2; ++t) {
+        o[0] = fmaf(g[2 * t + 1], v[t], o[0]);
+        o[1] = fmaf(g[2 * t], v[t], o[1]);
+        o[2] = fmaf(g[2 * t + 1], v[t + 1], o[2]);
+        o[3] = fmaf(g[2 * t], v[t + 1], o[3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = fmaf(g[k], v[2 * q + k], o[q]);
+    }
+  }
+}
+
+template <int T, bool kUp>
+__global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restrict__ x, const float* __restrict__ f,
+                                                            float* __restrict__ y, int inH, int inW, int outH, int outW,
+                                                            int padx0, int pady0, int flip, float gain_axis, int tiles_x,
+                                                            int tiles_y) {
+  using G = SepGeom<T, kUp>;
+  extern __shared__ float sep_smem[];
+  float* in_s = sep_smem;                       // [TIH][PIN]
+  float* mid = in_s + G::TIH * G::PIN;          // [TIH][PMID]
+  float* gs = mid + G::TIH * G::PMID;           // [T]
+  const int tid = threadIdx.x;
+  if (tid < T) gs[tid] = (flip ? f[tid] : f[T - 1 - tid]) * gain_axis;
+  const int tile = blockIdx.x;
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
+  const long plane = tile / (tiles_x * tiles_y);
+  const int ox0 = tx * G::TOW, oy0 = ty * G::TOH;
+  const int ix0 = sep_first<kUp>(ox0, padx0), iy0 = sep_first<kUp>(oy0, pady0);
+  const float* xp = x + plane * inH * inW;
+  // ---- (1) stage the input tile (coalesced rows; zero fill = padding)
+  for (int i = tid; i < G::TIH * G::TIW; i += 256) {
+    const int r = i / G::TIW, c = i - r * G::TIW;
+    const int gy = iy0 + r, gx = ix0 + c;
+    float v = 0.f;
+    if (gy >= 0 && gy < inH && gx >= 0 && gx < inW) v = __ldg(xp + static_cast<long>(gy) * inW + gx);
+    in_s[r * G::PIN + c] = v;
+  }
+  __syncthreads();
+  float g[T];
+#pragma unroll
+  for (int k = 0; k < T; ++k) g[k] = gs[k];
+  const bool oddx = ((ox0 - padx0) & 1) != 0, oddy = ((oy0 - pady0) & 1) != 0;
+  // ---- (2) horizontal: items = (input row, group of 4 output columns); consecutive threads walk down the rows
+  for (int i = tid; i < G::TIH * (G::TOW / 4); i += 256) {
+    const int r = i % G::TIH, a = i / G::TIH;
+    const int b = sep_first<kUp>(ox0 + 4 * a, padx0) - ix0;
+    float v[G::NV];
+#pragma unroll
+    for (int j = 0; j < G::NV; ++j) v[j] = (b + j < G::TIW) ? in_s[r * G::PIN + b + j] : 0.f;
+    float o[4];
+    sep_fir4<T, kUp>(v, g, oddx, o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mid[r * G::PMID + 4 * a + q] = o[q];
+  }
+  __syncthreads();
+  // ---- (3) vertical: items = (output column, group of 4 output rows); consecutive threads = consecutive columns
+  float* yp = y + plane * outH * outW;
+  for (int i = tid; i < G::TOW * (G::TOH / 4); i += 256) {
+    const int c = i % G::TOW, a = i / G::TOW;
+    const int b = sep_first<kUp>(oy0 + 4 * a, pady0) - iy0;
+    float v[G::NV];
+#pragma unroll
+    for (int j = 0; j < G::NV; ++j) v[j] = (b + j < G::TIH) ? mid[(b + j) * G::PMID + c] : 0.f;
+    float o[4];
+    sep_fir4<T, kUp>(v, g, oddy, o);
+    const int ox = ox0 + c;
+    if (ox < outW) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int oy = oy0 + 4 * a + q;
+        if (oy < outH) __stcs(yp + static_cast<long>(oy) * outW + ox, o[q]);
+      }
+    }
+  }
+}
+
+template <int T>
+static int launch_sep(bool up, const float* x, const float* f, float* y, long planes, int inH, int inW, int outH, int outW,
+                      int padx0, int pady0, int flip, float gain, cudaStream_t st) {
+  const float ga = sqrtf(gain);
+  if (up) {
+    using G = SepGeom<T, true>;
+    const int txn = (outW + G::TOW - 1) / G::TOW, tyn = (outH + G::TOH - 1) / G::TOH;
+    cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    upfirdn2d_sep_kernel<T, true><<<static_cast<unsigned>(planes * txn * tyn), 256, G::SMEM, st>>>(
+        x, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn, tyn);
+  } else {
+    using G = SepGeom<T, false>;
+    const int txn = (outW + G::TOW - 1) / G::TOW, tyn = (outH + G::TOH - 1) / G::TOH;
+    cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    upfirdn2d_sep_kernel<T, false><<<static_cast<unsigned>(planes * txn * tyn), 256, G::SMEM, st>>>(
+        x, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn, tyn);
+  }
+  return check_launch("hg_upfirdn2d_sep2");
+}
+
 // 2x2 average pooling / nearest-neighbour 2x up-sampling with a scale factor (each is the other's adjoint up to the
 // scale: d avgpool = 0.25 * up(dy), d up = 4 * avgpool(dy)).  The discriminator's ResBlocks use them between
 // convolutions (unet_discriminators.py:30,60-70); pure streaming, one float2 / float4 per lane.
@@ -301,6 +453,25 @@ int hg_upfirdn2d(const float* x, const float* f, float* y, int NC, int inH, int 
   hg::upfirdn2d_kernel<<<grid, 128, fH * fW * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       x, f, y, NC, inH, inW, outH, outW, fH, fW, upx, upy, downx, downy, padx0, pady0, flip_filter, gain);
   return hg::check_launch("hg_upfirdn2d");
+}
+
+int hg_upfirdn2d_sep2(const float* x, const float* f, float* y, long planes, int inH, int inW, int outH, int outW, int taps,
+                      int up, int padx0, int pady0, int flip_filter, float gain, void* stream) {
+  HG_REQUIRE(x && f && y, "hg_upfirdn2d_sep2: null pointer");
+  HG_REQUIRE(planes > 0 && inH > 0 && inW > 0 && outH > 0 && outW > 0, "hg_upfirdn2d_sep2: bad shape");
+  HG_REQUIRE(gain >= 0.f, "hg_upfirdn2d_sep2: gain must be non-negative");
+  HG_REQUIRE(planes * ((outW + 63) / 64) * ((outH + 31) / 32) < (1L << 31), "hg_upfirdn2d_sep2: too many tiles");
+  auto st = static_cast<cudaStream_t>(stream);
+  switch (taps) {
+    case 4: return hg::launch_sep<4>(up != 0, x, f, y, planes, inH, inW, outH, outW, padx0, pady0, flip_filter, gain, st);
+    case 6: return hg::launch_sep<6>(up != 0, x, f, y, planes, inH, inW, outH, outW, padx0, pady0, flip_filter, gain, st);
+    case 8: return hg::launch_sep<8>(up != 0, x, f, y, planes, inH, inW, outH, outW, padx0, pady0, flip_filter, gain, st);
+    case 12: return hg::launch_sep<12>(up != 0, x, f, y, planes, inH, inW, outH, outW, padx0, pady0, flip_filter, gain, st);
+    case 16: return hg::launch_sep<16>(up != 0, x, f, y, planes, inH, inW, outH, outW, padx0, pady0, flip_filter, gain, st);
+    default: break;
+  }
+  hg::set_error("hg_upfirdn2d_sep2: taps must be one of 4, 6, 8, 12, 16 (got %d)", taps);
+  return 1;
 }
 
 int hg_resample2x(const float* x, float* y, long planes, int inH, int inW, int up, float scale, void* stream) {

@@ -15,6 +15,15 @@ from .. import abi
 _KMAX = 256
 
 
+def _rows(t):
+    """Row-major copy with canonical strides (a [K,1] transpose reports is_contiguous() with stride(1) == K)."""
+    if t.stride(1) == 1 and t.stride(0) == t.shape[1] and (t.data_ptr() % 16) == 0:
+        return t
+    out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+    out.copy_(t)
+    return out
+
+
 def _gemm_nt(a, b, scale=1.0, bias=None, passes=3):
     """a [M,K] @ (scale * b [N,K])^T (+ bias) -> [M,N] fp32, through hg_linear in contraction slices of <= 256."""
     a = a.float()
@@ -24,11 +33,10 @@ def _gemm_nt(a, b, scale=1.0, bias=None, passes=3):
     out = None
     for k0 in range(0, K, _KMAX):
         k1 = min(K, k0 + _KMAX)
-        img, Nb = abi.pack_weight(b[:, k0:k1] if (k0 == 0 and k1 == K and b.is_contiguous()) else b[:, k0:k1].contiguous(),
-                                  scale=float(scale))
+        img, Nb = abi.pack_weight(_rows(b[:, k0:k1]), scale=float(scale))
         xa = a[:, k0:k1]
-        if xa.stride(1) != 1 or (xa.data_ptr() % 16) != 0:
-            xa = xa.contiguous()
+        if xa.stride(1) != 1 or (xa.data_ptr() % 16) != 0 or xa.shape[0] == 1:
+            xa = _rows(xa)
         part = abi.linear(xa, img, Nb, N, bias=bias if k0 == 0 else None, passes=passes)
         out = part if out is None else out.add_(part)
     return out

@@ -89,6 +89,44 @@ class _Pass(torch.autograd.Function):
         return dx, None, None
 
 
+_SEP_TAPS = (4, 6, 8, 12, 16)
+
+
+class _SepPass(torch.autograd.Function):
+    """Both 1-D passes of a separable 2x up- or down-sampling FIR in ONE kernel (`hg_upfirdn2d_sep2`, the intermediate stays
+    in shared memory).  geom = (up, down, px0, px1, py0, py1, flip, gain) with (up, down) in {(2, 1), (1, 2)}.  Its adjoint
+    is the other direction with the filter mirrored, so the backward is another `_SepPass` (any order)."""
+
+    @staticmethod
+    def forward(ctx, x, f1d, geom):
+        up, down, px0, px1, py0, py1, flip, gain = geom
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        T = f1d.numel()
+        outH = (H * up + py0 + py1 - T) // down + 1
+        outW = (W * up + px0 + px1 - T) // down + 1
+        ctx.geom, ctx.in_hw = geom, (H, W)
+        ctx.save_for_backward(f1d)
+        y = torch.empty(B, C, max(outH, 0), max(outW, 0), dtype=torch.float32, device=x.device)
+        if y.numel():
+            with torch.cuda.device_of(x):
+                abi.call("hg_upfirdn2d_sep2", abi.ptr(x), abi.ptr(f1d), abi.ptr(y), B * C, H, W, outH, outW, T, int(up == 2),
+                         px0, py0, int(bool(flip)), float(gain), abi.stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (f1d,) = ctx.saved_tensors
+        up, down, px0, px1, py0, py1, flip, gain = ctx.geom
+        ih, iw = ctx.in_hw
+        oh, ow = dy.shape[2], dy.shape[3]
+        T = f1d.numel()
+        back = (down, up, T - px0 - 1, iw * up - ow * down + px0 - up + 1, T - py0 - 1, ih * up - oh * down + py0 - up + 1,
+                not flip, gain)
+        dx = _SepPass.apply(dy, f1d, back) if ctx.needs_input_grad[0] else None
+        return dx, None, None
+
+
 def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl="cuda"):
     assert x.ndim == 4
     upx, upy = _pair(up)
@@ -99,7 +137,11 @@ def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl="cu
         f = torch.ones(1, 1, dtype=torch.float32, device=x.device)
     f = f.detach().to(device=x.device, dtype=torch.float32).contiguous()
     flip = bool(flip_filter)
-    if f.ndim == 2:
+    fused = (f.ndim == 1 and f.numel() in _SEP_TAPS and upx == upy and downx == downy and (upx, downx) in ((2, 1), (1, 2))
+             and float(gain) >= 0)
+    if fused:       # the reference's call shapes (augment.py:314,325): one kernel, no HBM round trip of the intermediate
+        y = _SepPass.apply(xin, f, (upx, downx, px0, px1, py0, py1, flip, float(gain)))
+    elif f.ndim == 2:
         y = _Pass.apply(xin, f, (upx, upy, downx, downy, px0, px1, py0, py1, flip, float(gain)))
     else:  # separable: a [1,fw] pass then a [fh,1] pass, gain split as in upfirdn2d.py:243-244
         g = float(gain) ** 0.5

@@ -268,24 +268,36 @@ class Trainer:
         z = self._z(batch, "z_g", B, real_images.device)
         split = B // self.batch_split
         total = 0.0
-        for s in range(self.batch_split):
-            sl = slice(s * split, (s + 1) * split)
-            with self._autocast():
-                sub = {k: v[sl] for k, v in cond.items()}
-                gen_outputs = self.generator_ddp(z[sl], sub, latent_indices=None, **meta)
-                out = self.discriminator_ddp(gen_outputs[phase["gen_modal"]], sub, alpha=alpha, mode="gen", **meta)
-                pred_gen = out["prediction"]
-                gan_lambda = meta["gan_lambda"] if phase["uncond"] else 0
-                gan_loss = gan_lambda * F.softplus(-pred_gen).mean() if gan_lambda > 0 else 0 * pred_gen.sum()
-                latent_loss = out["latents"].sum() * 0
-                if meta["segmentation_lambda"] > 0:
-                    seg = segmentation_loss(out["segments"], labels[sl], meta["label_dim"],
-                                            meta.get("segmentation_weights")) * meta["segmentation_lambda"]
-                else:
-                    seg = out["segments"].sum() * 0
-                g_loss = (gan_loss + latent_loss + seg) / self.batch_split
-                self.scaler.scale(g_loss).backward()
-            total = total + g_loss.detach()
+        # The reference leaves the discriminator's parameters trainable here and lets autograd fill (and DDP all-reduce)
+        # gradients that `optimizer_D.zero_grad()` throws away at the start of the next discriminator step
+        # (phase_trainer.py:301, 474).  Same parameter updates without that work: freeze them for this step and call the
+        # bare module (no reducer bookkeeping, no weight-gradient kernels, no all-reduce of unused gradients).
+        d_params = list(self.discriminator.parameters())
+        flags = [p.requires_grad for p in d_params]
+        for p in d_params:
+            p.requires_grad_(False)
+        try:
+            for s in range(self.batch_split):
+                sl = slice(s * split, (s + 1) * split)
+                with self._autocast():
+                    sub = {k: v[sl] for k, v in cond.items()}
+                    gen_outputs = self.generator_ddp(z[sl], sub, latent_indices=None, **meta)
+                    out = self.discriminator(gen_outputs[phase["gen_modal"]], sub, alpha=alpha, mode="gen", **meta)
+                    pred_gen = out["prediction"]
+                    gan_lambda = meta["gan_lambda"] if phase["uncond"] else 0
+                    gan_loss = gan_lambda * F.softplus(-pred_gen).mean() if gan_lambda > 0 else 0 * pred_gen.sum()
+                    latent_loss = out["latents"].sum() * 0
+                    if meta["segmentation_lambda"] > 0:
+                        seg = segmentation_loss(out["segments"], labels[sl], meta["label_dim"],
+                                                meta.get("segmentation_weights")) * meta["segmentation_lambda"]
+                    else:
+                        seg = out["segments"].sum() * 0
+                    g_loss = (gan_loss + latent_loss + seg) / self.batch_split
+                    self.scaler.scale(g_loss).backward()
+                total = total + g_loss.detach()
+        finally:
+            for p, f in zip(d_params, flags):
+                p.requires_grad_(f)
         self.scaler.unscale_(self.optimizer_G)
         torch.nn.utils.clip_grad_norm_(self.generator_ddp.parameters(), meta["grad_clip"])
         self.scaler.step(self.optimizer_G)

@@ -262,6 +262,12 @@ int hg_resample2x(const float* x, float* y, long planes, int inH, int inW, int u
 int hg_upfirdn2d(const float* x, const float* f, float* y, int NC, int inH, int inW, int outH, int outW, int fH,
                  int fW, int upx, int upy, int downx, int downy, int padx0, int pady0, int flip_filter, float gain,
                  void* stream);
+/* Both 1-D passes of a SEPARABLE 2x resampler in one kernel (intermediate in shared memory): the reference's only call
+ * shapes, upsample2d / downsample2d with the 12-tap sym6 filter (augment.py:314,325; two passes at upfirdn2d.py:243-244).
+ * f [taps] with taps in {4,6,8,12,16}; up != 0: up = 2, down = 1; up == 0: up = 1, down = 2 (both axes).  gain is the
+ * total gain (sqrt per axis).  out size = (in * up + pad0 + pad1 - taps) / down + 1 (computed by the caller). */
+int hg_upfirdn2d_sep2(const float* x, const float* f, float* y, long planes, int inH, int inW, int outH, int outW, int taps,
+                      int up, int padx0, int pady0, int flip_filter, float gain, void* stream);
 
 #ifdef __cplusplus
 }

@@ -126,3 +126,46 @@ def test_training_graph_matches_inference_and_oracle_gradients(port, monkeypatch
         if e > 5e-4:
             bad[n] = e
     assert not bad, sorted(bad.items(), key=lambda t: -t[1])[:8]
+
+
+@pytest.mark.parametrize("shape", [
+    # B, C1, C2, Cout, H, W, up2, pre_lrelu, residual ('', 'full', 'half')
+    (2, 64, 0, 64, 4, 128, False, False, ""),
+    (1, 128, 0, 128, 6, 256, False, True, "full"),
+    (2, 128, 64, 256, 8, 128, True, True, "half"),
+    (1, 256, 0, 64, 10, 384, True, True, ""),
+    (3, 64, 0, 32, 2, 128, False, False, "full"),
+])
+def test_haloed_conv3x3_matches_torch(shape):
+    """dconv_halo.cu (one haloed operand tile per K chunk, nine taps by descriptor row offset): every fused option against
+    torch in fp64 -- image borders (zero padding), several tiles per CTA, two accumulator sets, two N sub-blocks, concat."""
+    import torch.nn.functional as TF
+    abi = importlib.import_module("3dhumangan_b200.abi")
+    dops = importlib.import_module("3dhumangan_b200.modules.discriminator_ops")
+    B, C1, C2, Cout, H, W, up2, pre, res = shape
+    g = torch.Generator().manual_seed(sum(shape[:6]))
+    Hs, Ws = (H // 2, W // 2) if up2 else (H, W)
+    x1 = torch.randn(B, C1, Hs, Ws, generator=g)
+    x2 = torch.randn(B, C2, Hs, Ws, generator=g) if C2 else None
+    w = torch.randn(Cout, C1 + C2, 3, 3, generator=g) / (9 * (C1 + C2)) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    r = None
+    if res == "full":
+        r = torch.randn(B, Cout, H, W, generator=g)
+    elif res == "half":
+        r = torch.randn(B, Cout, H // 2, W // 2, generator=g)
+    xin = (x1 if x2 is None else torch.cat([x1, x2], 1)).double()
+    if pre:
+        xin = TF.leaky_relu(xin, 0.2)
+    if up2:
+        xin = TF.interpolate(xin, scale_factor=2, mode="nearest")
+    ref = TF.conv2d(xin, w.double(), bias.double(), padding=1)
+    if r is not None:
+        ref = ref + (TF.interpolate(r.double(), scale_factor=2, mode="nearest") if res == "half" else r.double())
+    img, Nb = dops._pack_conv(w.cuda())
+    for passes, tol in ((3, 2e-5), (1, 2e-2)):
+        out = abi.conv2d(x1.cuda(), img, Cout, Nb, ksize=3, H=H, W=W, x2=None if x2 is None else x2.cuda(), up2=up2, pre_lrelu=pre,
+                         bias=bias.cuda(), residual=None if r is None else r.cuda(), res_up2=(res == "half"), passes=passes)
+        torch.cuda.synchronize()
+        e = rel_l2(out.cpu(), ref)
+        assert e < tol, (shape, passes, e)

@@ -147,7 +147,7 @@ def test_dense_forward_backward_matches_torch():
     import importlib
     dn = importlib.import_module("3dhumangan_b200.ops.dense")
     g = torch.Generator().manual_seed(1)
-    for (M, K, N, gain) in [(8, 256, 256, 1.0), (5, 256, 2048, 0.01 / 16), (16, 420, 420, 1.0), (300, 64, 96, 2.0)]:
+    for (M, K, N, gain) in [(8, 256, 256, 1.0), (1, 256, 256, 1.0), (5, 256, 2048, 0.01 / 16), (16, 420, 420, 1.0), (300, 64, 96, 2.0)]:
         x = torch.randn(M, K, generator=g)
         w = torch.randn(N, K, generator=g) / K ** 0.5
         b = torch.randn(N, generator=g)
@@ -162,3 +162,25 @@ def test_dense_forward_backward_matches_torch():
         rel = lambda a_, r_: float((a_.detach().cpu().double() - r_).norm() / r_.norm())
         assert rel(y, yr.detach()) < 2e-5, (M, K, N)
         assert rel(xc.grad, xr.grad) < 2e-5 and rel(wc.grad, wr.grad) < 2e-5 and rel(bc.grad, br.grad) < 1e-5, (M, K, N)
+
+
+@pytest.mark.parametrize("taps", [4, 8, 12, 16])
+def test_upfirdn2d_fused_separable_multi_tile(port, taps):
+    """The fused two-axis kernel (hg_upfirdn2d_sep2) over many tiles, both padding parities, negative padding (crop),
+    flip on / off, sizes that are not multiples of the tile -- against the reference's zero-insert / pad / conv / decimate."""
+    uf = importlib.import_module("3dhumangan_b200.ops.upfirdn2d")
+    g = torch.Generator().manual_seed(10 + taps)
+    f = uf.setup_filter(torch.rand(taps, generator=g) - 0.3, separable=True)
+    assert f.ndim == 1
+    x = torch.randn(2, 3, 150, 201, generator=g)
+    cases = []
+    for pad in ([taps // 2, taps // 2 - 1] * 2, [taps // 2 + 1, taps // 2, taps // 2 - 2, taps // 2 + 3], [-3, taps, taps - 1, -2]):
+        for flip in (False, True):
+            cases.append(dict(f=f, up=2, padding=pad, flip_filter=flip, gain=4))
+            cases.append(dict(f=f, down=2, padding=pad, flip_filter=flip, gain=1.5))
+    for kw in cases:
+        ref = port.upfirdn2d_ref(x, **kw)
+        with torch.no_grad():
+            got = uf.upfirdn2d(x.cuda(), **{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}).cpu()
+        assert got.shape == ref.shape, (kw, got.shape, ref.shape)
+        assert torch.allclose(got, ref, rtol=2e-5, atol=2e-5), (kw["padding"], kw.get("up"), kw["flip_filter"], (got - ref).abs().max())

@@ -86,7 +86,7 @@ def test_discriminator_step_matches_oracle_composition(pkg, port, monkeypatch, d
     try:
         cfg = pkg.configs.baseline_config("tiny")
         cfg.update(gen_height=64, gen_width=64, render_height=8, render_width=8, num_steps=32, nerf_noise=0.5,
-                   r1_lambda=10.0, grad_clip=1e9, gan_lambda=1.0 if do_r1 else 0)
+                   r1_lambda=1.0, grad_clip=1e9, gan_lambda=1.0 if do_r1 else 0)
         cfg["phases"] = [dict(cfg["phases"][3 if do_r1 else 0])]
         B = 2
         pg = {k: v.cuda() for k, v in port.init_generator_params(cfg, seed=5, sigma_gain=200.0, sigma_bias=1.0).items()}
@@ -116,11 +116,11 @@ def test_discriminator_step_matches_oracle_composition(pkg, port, monkeypatch, d
     scale = max(float(v.norm()) for v in ref_grads.values() if v is not None)
     for n, p in D.named_parameters():
         r = ref_grads.get(n)
-        if r is None or float(r.norm()) < 1e-5 * scale:
+        if r is None or float(r.norm()) < 1e-6 * scale:
             continue
         assert p.grad is not None, n
         errs[n] = float((p.grad.double() - r.double()).norm() / r.double().norm())
-    assert len(errs) > 50
+    assert len(errs) > 25, len(errs)
     vals = sorted(errs.values())
     assert vals[len(vals) // 2] < 2e-2, (vals[len(vals) // 2], sorted(errs.items(), key=lambda kv: -kv[1])[:5])
     assert vals[-1] < 0.3, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
