@@ -51,7 +51,7 @@ struct HaloArgs {
 enum { HA_FULL = 0, HA_EMPTY = 1, HB_FULL = 2 /*4*/, HB_EMPTY = 6 /*4*/, HACC_FULL = 10 /*2*/, HACC_EMPTY = 12 /*2*/ };
 
 template <int kPasses>
-__global__ void __maxnreg__(144) conv3x3_halo_kernel(HaloArgs a) {
+__global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_hi = smem;
