@@ -67,6 +67,8 @@ SIGNATURES = {
     "hg_pool_add": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_void_p]),
     "hg_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hg_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "hg_conv3x3_wgrad_halo_workspace_bytes": (ctypes.c_size_t, []),
+    "hg_conv3x3_wgrad_halo": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p, c_void_p, c_int, c_void_p]),
     "hg_spectral_entry_bytes": (c_int, []),
     "hg_spectral_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p]),
 }
@@ -450,13 +452,51 @@ def conv2d(x1, wimg, Cout, Nb, *, ksize, H, W, x2=None, up2=False, pre_lrelu=Fal
 _CONV_WS = {}
 
 
-def conv2d_wgrad(dy, x, ksize, passes=3):
-    """dW [Cout,Cin,k,k], dbias [Cout] of a stride-1 'same' convolution (csrc/dconv_bwd.cu): one launch per
-    (256 output, 256 input)-channel chunk and per group of taps that fits the 512 TMEM columns."""
-    import ctypes
+_WGH_WS = {}
+
+
+def _conv3x3_wgrad_halo(dy, x, passes):
+    """3x3 weight gradient on rows of >= 128 pixels (csrc/dconv_wgrad_halo.cu): per (128 output, 64 input)-channel block two
+    launches (5 + 4 taps, 8 x 64 TMEM columns at most), the input converted once per image row instead of once per tap."""
     B, Cout, H, W = dy.shape
     Cin = x.shape[1]
     dev = dy.device
+    ws = _WGH_WS.get(dev)
+    if ws is None:
+        ws = _WGH_WS[dev] = torch.empty(int(lib().hg_conv3x3_wgrad_halo_workspace_bytes()) // 4, dtype=torch.float32, device=dev)
+    dW = torch.empty(Cout, Cin, 9, dtype=torch.float32, device=dev)
+    db = torch.empty(Cout, dtype=torch.float32, device=dev)
+    groups = ([0, 1, 2, 3, 4], [5, 6, 7, 8])
+    for co0 in range(0, Cout, 128):
+        nco = min(128, Cout - co0)
+        for ci0 in range(0, Cin, 64):
+            nci = min(64, Cin - ci0)
+            for gi, taps in enumerate(groups):
+                n = len(taps)
+                tdy = (ctypes.c_int * n)(*[t // 3 - 1 for t in taps])
+                tdx = (ctypes.c_int * n)(*[t % 3 - 1 for t in taps])
+                dw = torch.empty(n, 128, 64, dtype=torch.float32, device=dev)
+                first = ci0 == 0 and gi == 0
+                dbt = torch.empty(128, dtype=torch.float32, device=dev) if first else None
+                with torch.cuda.device_of(dy):
+                    call("hg_conv3x3_wgrad_halo", ptr(dy), ptr(x), ptr(dw), ptr(dbt), ptr(ws), B, H, W, Cout, Cin, co0, nco, ci0, nci,
+                         n, ctypes.cast(tdy, c_void_p), ctypes.cast(tdx, c_void_p), passes, stream())
+                dW[co0:co0 + nco, ci0:ci0 + nci, taps[0]:taps[-1] + 1] = dw[:, :nco, :nci].permute(1, 2, 0)
+                if first:
+                    db[co0:co0 + nco] = dbt[:nco]
+    return dW.reshape(Cout, Cin, 3, 3), db
+
+
+def conv2d_wgrad(dy, x, ksize, passes=3):
+    """dW [Cout,Cin,k,k], dbias [Cout] of a stride-1 'same' convolution.  3x3 on rows of >= 128 pixels: the haloed kernel
+    (csrc/dconv_wgrad_halo.cu); otherwise csrc/dconv_bwd.cu: one launch per (256 output, 256 input)-channel chunk and per
+    group of taps that fits the 512 TMEM columns."""
+    B, Cout, H, W = dy.shape
+    Cin = x.shape[1]
+    dev = dy.device
+    dy, x = dy.contiguous(), x.contiguous()
+    if ksize == 3 and W % 128 == 0 and os.environ.get("HG3D_WGRAD_HALO", "1") != "0":
+        return _conv3x3_wgrad_halo(dy, x, passes)
     ws = _CONV_WS.get(dev)
     if ws is None:
         ws = _CONV_WS[dev] = torch.empty(int(lib().hg_conv2d_wgrad_workspace_bytes()) // 4, dtype=torch.float32, device=dev)
@@ -464,7 +504,6 @@ def conv2d_wgrad(dy, x, ksize, passes=3):
     db = torch.empty(Cout, dtype=torch.float32, device=dev)
     pad = ksize // 2
     taps = [(ky, kx) for ky in range(ksize) for kx in range(ksize)]
-    dy, x = dy.contiguous(), x.contiguous()
     for co0 in range(0, Cout, 256):
         nco = min(256, Cout - co0)
         nmh = 2 if nco > 128 else 1

@@ -169,3 +169,32 @@ def test_haloed_conv3x3_matches_torch(shape):
         torch.cuda.synchronize()
         e = rel_l2(out.cpu(), ref)
         assert e < tol, (shape, passes, e)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 128, 4, 128), (1, 128, 64, 34, 128), (2, 192, 256, 8, 256), (1, 96, 200, 6, 128),
+                                   (3, 64, 64, 64, 128)])
+def test_haloed_conv3x3_weight_gradient_matches_torch(shape):
+    """dconv_wgrad_halo.cu (input rows converted once, read as an MN-major operand, taps by descriptor row offset, ring of input
+    rows, several strips per CTA) against torch autograd in fp64; also through the Conv2dSame autograd node."""
+    import torch.nn.functional as TF
+    abi = importlib.import_module("3dhumangan_b200.abi")
+    dt = importlib.import_module("3dhumangan_b200.modules.discriminator_train")
+    B, Cin, Cout, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).double().requires_grad_(True)
+    b = torch.zeros(Cout, dtype=torch.float64, requires_grad=True)
+    TF.conv2d(x.double(), w, b, padding=1).backward(dy.double())
+    for passes, tol in ((3, 2e-5), (1, 2e-2)):
+        dw, db = abi.conv2d_wgrad(dy.cuda(), x.cuda(), 3, passes=passes)
+        torch.cuda.synchronize()
+        assert dw.shape == w.shape
+        e = rel_l2(dw.cpu(), w.grad)
+        assert e < tol, (shape, passes, e)
+        assert rel_l2(db.cpu(), b.grad) < 1e-5
+    xg = x.cuda().requires_grad_(True)
+    wg = w.detach().float().cuda().requires_grad_(True)
+    bg = torch.zeros(Cout, device="cuda", requires_grad=True)
+    dt.Conv2dSame.apply(xg, wg, bg, 3).backward(dy.cuda())
+    assert rel_l2(wg.grad.cpu(), w.grad) < 2e-5
