@@ -48,7 +48,8 @@ struct HaloArgs {
   float* out;
 };
 
-enum { HA_FULL = 0, HA_EMPTY = 1, HB_FULL = 2 /*4*/, HB_EMPTY = 6 /*4*/, HACC_FULL = 10 /*2*/, HACC_EMPTY = 12 /*2*/ };
+enum { HA_FULL = 0 /*4: one per row segment*/, HA_EMPTY = 4 /*4*/, HB_FULL = 8 /*4*/, HB_EMPTY = 12 /*4*/, HACC_FULL = 16 /*2*/,
+       HACC_EMPTY = 18 /*2*/ };
 
 template <int kPasses>
 __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a) {
@@ -64,8 +65,7 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) tab_bias[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
   if (threadIdx.x == 0) {
-    mbar_init(bars + HA_FULL, 8);
-    mbar_init(bars + HA_EMPTY, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(bars + HA_FULL + i, 8); mbar_init(bars + HA_EMPTY + i, 1); }
     for (int i = 0; i < kHcBStages; ++i) { mbar_init(bars + HB_FULL + i, 1); mbar_init(bars + HB_EMPTY + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bars + HACC_FULL + i, 1); mbar_init(bars + HACC_EMPTY + i, 4); }
     fence_mbar_init();
@@ -89,37 +89,37 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
 
   if (warp < 8) {
     // ------------------------------------------------------------------ operand producers
+    // The operand buffer of a chunk is FOUR row segments with their own full / empty barriers: the MMA thread walks the taps
+    // dy = -1, 0, +1 (segments {0,1}, {1,2}, {2,3} for the two pixel tiles), so segment 0 of the NEXT chunk can be rebuilt
+    // after a third of this chunk's MMAs, segment 1 after two thirds -- the producers (latency-bound on their loads) overlap
+    // the MMAs although the buffer is not duplicated.
     const int t = threadIdx.x;                 // 0..255
-    const int px = t & 127, sp = t >> 7;       // interior pixel, segment pair {sp, sp + 2}
-    uint32_t n = 0;                            // chunk counter (A buffer phase)
+    const int px = t & 127, half = t >> 7;     // one interior pixel, 32 of the chunk's 64 channels (two batches of 16)
+    const int hside = t >> 3, hg8 = t & 7;     // threads 0..15: halo pixel (left / right), 8 channels
+    uint32_t n = 0;                            // chunk counter (segment barrier phase)
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int xb = tile % xtiles, yb = (tile / xtiles) % ytiles, b = tile / (xtiles * ytiles);
       const int x0 = xb * 128, y0 = yb * 2;
-      // source offsets of this thread's two interior rows (y = y0 - 1 + s, x = x0 + px)
-      long off[2];
-      bool ok[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int y = y0 - 1 + sp + 2 * r;
-        ok[r] = y >= 0 && y < a.H;
-        const int sy = ok[r] ? (a.up2 ? y >> 1 : y) : 0, sx = a.up2 ? (x0 + px) >> 1 : x0 + px;
-        off[r] = static_cast<long>(sy) * Ws + sx;
-      }
-      // halo row of this warp: segment warp >> 1, left (x0 - 1) or right (x0 + 128) column; lanes 0-7 take 8 channels each
-      const int hs = warp >> 1, hx = (warp & 1) ? x0 + 128 : x0 - 1, hy = y0 - 1 + hs;
-      const bool hok = hy >= 0 && hy < a.H && hx >= 0 && hx < a.W;
-      const long hoff = hok ? static_cast<long>(a.up2 ? hy >> 1 : hy) * Ws + (a.up2 ? hx >> 1 : hx) : 0;
-      const uint32_t hrow = hs * kHcSeg + ((warp & 1) ? kHcSeg - 1 : 0);
-
+      const int sx = a.up2 ? (x0 + px) >> 1 : x0 + px;
+      const int hx = hside ? x0 + 128 : x0 - 1;
+      const bool hxok = t < 16 && hx >= 0 && hx < a.W;
+      const int hsx = hxok ? (a.up2 ? hx >> 1 : hx) : 0;
       for (int cb = 0; cb < cblocks; ++cb, ++n) {
         const int c0 = cb * 64;
         const float* plane = c0 < a.C1 ? a.x1 + (static_cast<long>(b) * a.C1 + c0) * HWs
                                        : a.x2 + (static_cast<long>(b) * a.C2 + (c0 - a.C1)) * HWs;
-        // 8 batches of 16 channels (2 rows x 4 quarters), software-pipelined two deep: 32 value registers
         float v[2][16];
-        auto issue = [&](float (&dst)[16], int bi) {
-          const float* src = plane + static_cast<long>((bi & 3) * 16) * HWs + off[bi >> 2];
+        auto rowinfo = [&](int s, bool& ok, long& off) {
+          const int y = y0 - 1 + s;
+          ok = y >= 0 && y < a.H;
+          off = static_cast<long>(ok ? (a.up2 ? y >> 1 : y) : 0) * Ws;
+        };
+        auto issue = [&](float (&dst)[16], int bi) {             // batch bi = segment * 2 + quarter
+          bool ok;
+          long off;
+          rowinfo(bi >> 1, ok, off);
+          const float* src = plane + static_cast<long>(half * 32 + (bi & 1) * 16) * HWs + off + sx;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dst[j]) : "l"(src));
@@ -127,53 +127,60 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
           }
         };
         auto convert = [&](const float (&cur)[16], int bi) {
-          const int r = bi >> 2;
-          const uint32_t row = (sp + 2 * r) * kHcSeg + 1 + px;
+          bool ok;
+          long off;
+          rowinfo(bi >> 1, ok, off);
+          const uint32_t row = (bi >> 1) * kHcSeg + 1 + px;
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             float y[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float val = ok[r] ? cur[g * 8 + j] : 0.f;
+              float val = ok ? cur[g * 8 + j] : 0.f;
               if (a.pre_lrelu) val = val > 0.f ? val : 0.2f * val;
               y[j] = val;
             }
-            store_a8<kPasses == 3>(a_hi, a_lo, row, (bi & 3) * 16 + g * 8, y);
+            store_a8<kPasses == 3>(a_hi, a_lo, row, half * 32 + (bi & 1) * 16 + g * 8, y);
           }
         };
-        // loads of the first batch are in flight while the previous chunk's MMAs still read the buffer
         issue(v[0], 0);
-        float hv[8];
-        if (lane < 8) {
-          const float* src = plane + static_cast<long>(lane * 8) * HWs + hoff;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(hv[j]) : "l"(src));
-            src += HWs;
-          }
-        }
         issue(v[1], 1);
-        mbar_wait(bars + HA_EMPTY, (n & 1) ^ 1);
 #pragma unroll
-        for (int bi = 0; bi < 8; bi += 2) {
-          convert(v[0], bi);
-          if (bi + 2 < 8) issue(v[0], bi + 2);
-          convert(v[1], bi + 1);
-          if (bi + 3 < 8) issue(v[1], bi + 3);
-        }
-        if (lane < 8) {
-          float y[8];
+        for (int s = 0; s < 4; ++s) {
+          // halo pixels of this segment (threads 0..15), loaded before the wait like the batches above
+          float hv[8];
+          bool hok = false;
+          if (t < 16) {
+            bool ok;
+            long off;
+            rowinfo(s, ok, off);
+            hok = ok && hxok;
+            const float* src = plane + static_cast<long>(hg8 * 8) * HWs + off + hsx;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float val = hok ? hv[j] : 0.f;
-            if (a.pre_lrelu) val = val > 0.f ? val : 0.2f * val;
-            y[j] = val;
+            for (int j = 0; j < 8; ++j) {
+              asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(hv[j]) : "l"(src));
+              src += HWs;
+            }
           }
-          store_a8<kPasses == 3>(a_hi, a_lo, hrow, lane * 8, y);
+          mbar_wait(bars + HA_EMPTY + s, (n & 1) ^ 1);
+          convert(v[0], 2 * s);
+          if (s < 3) issue(v[0], 2 * s + 2);
+          convert(v[1], 2 * s + 1);
+          if (s < 3) issue(v[1], 2 * s + 3);
+          if (t < 16) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float val = hok ? hv[j] : 0.f;
+              if (a.pre_lrelu) val = val > 0.f ? val : 0.2f * val;
+              y[j] = val;
+            }
+            store_a8<kPasses == 3>(a_hi, a_lo, s * kHcSeg + (hside ? kHcSeg - 1 : 0), hg8 * 8, y);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars + HA_FULL + s);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + HA_FULL);
       }
     }
   } else if (warp < 12) {
@@ -237,10 +244,13 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
         mbar_wait(bars + HACC_EMPTY + set, ((it / nsets) & 1) ^ 1);
         tc_fence_after();
         for (int cb = 0; cb < cblocks; ++cb, ++n) {
-          mbar_wait(bars + HA_FULL, n & 1);
-          tc_fence_after();
           for (int tap = 0; tap < 9; ++tap) {
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            if (dx == -1) {       // first tap of a filter row: its two segments are {dy + 1, dy + 2}
+              if (dy == -1) mbar_wait(bars + HA_FULL + 0, n & 1);
+              mbar_wait(bars + HA_FULL + dy + 2, n & 1);
+              tc_fence_after();
+            }
             const uint32_t r0 = static_cast<uint32_t>((dy + 1) * kHcSeg + dx + 1) * 128u;    // pixel tile mt = 0
             const uint32_t r1 = r0 + kHcSeg * 128u;                                          // pixel tile mt = 1
             const bool first = cb == 0 && tap == 0;
@@ -267,8 +277,11 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
                 if (++st == kHcBStages) { st = 0; ph ^= 1; }
               }
             }
+            if (dx == 1) {        // last tap of a filter row: segment dy + 1 is not read again (dy = +1: nor is segment 3)
+              umma_commit(bars + HA_EMPTY + dy + 1);
+              if (dy == 1) umma_commit(bars + HA_EMPTY + 3);
+            }
           }
-          umma_commit(bars + HA_EMPTY);
         }
         umma_commit(bars + HACC_FULL + set);
       }
