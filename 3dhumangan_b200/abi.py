@@ -47,7 +47,8 @@ SIGNATURES = {
                              + [c_int] * 5 + [c_void_p]),
     "hg_render_heads": (c_int, [c_void_p] * 8 + [c_int, c_int, c_void_p]),
     "hg_render_heads_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
-    "hg_render_composite": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
+    "hg_render_composite": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p]),
+    "hg_blocked_conv_wide": (c_int, [c_void_p] * 4 + [c_int, c_float] + [c_void_p] * 9 + [c_int] * 4 + [c_void_p]),
     "hg_render_composite_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "hg_wgrad_blocked": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "hg_spade_a1": (c_int, [c_void_p, c_long, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
@@ -341,12 +342,12 @@ def render_heads_bwd(out3, linc, mod3, dsig, drgbp, *, B, N):
     return acc
 
 
-def render_composite(sig, z, noise, rgbp, feat, *, B, R, S, noise_std, white_back, softplus):
+def render_composite(sig, z, noise, rgbp, feat, *, B, R, S, noise_std, white_back, softplus, last_back=False):
     ray_out = torch.empty(B, R, 260, dtype=torch.float32, device=sig.device)
     w = torch.empty(B, R * S, dtype=torch.float32, device=sig.device)
     with torch.cuda.device_of(sig):
         call("hg_render_composite", ptr(sig), ptr(z), ptr(noise), ptr(rgbp), ptr(feat), ptr(ray_out), ptr(w), B, R, S,
-             float(noise_std), int(bool(white_back)), int(bool(softplus)), stream())
+             float(noise_std), int(bool(white_back)), int(bool(softplus)), int(bool(last_back)), stream())
     return ray_out, w
 
 

@@ -139,6 +139,7 @@ struct CompArgs {
   int B, R, S;
   float noise_std;
   int white_back, softplus;
+  int last_back;         // fwd only: the last sample of a ray absorbs the remaining transmittance (volume_rendering.py:38-41)
 };
 
 __device__ __forceinline__ float comp_alpha(const CompArgs& a, long gp, int s, const float* zs, int row, float& dens_grad) {
@@ -193,15 +194,16 @@ __global__ void __launch_bounds__(128) composite_kernel(CompArgs a) {
     a.w_out[gp] = w;
     // weighted sums: warp w handles channels w, w+4, ...; lane l holds points l, l+32, l+64, l+96
     for (int c = warp; c < kRC + 4; c += 4) {
+      auto value = [&](int p) {
+        if (c < kRC) return ft[c * 128 + p];
+        if (c < kRC + 3) return 1.f / (1.f + expf(-a.rgbp[(static_cast<long>(b) * 3 + (c - kRC)) * N + ti * 128 + p]));
+        return zs[p];                                 // depth
+      };
       float part[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int p = lane + 32 * i;
-        float v;
-        if (c < kRC) v = ft[c * 128 + p];
-        else if (c < kRC + 3) v = 1.f / (1.f + expf(-a.rgbp[(static_cast<long>(b) * 3 + (c - kRC)) * N + ti * 128 + p]));
-        else v = zs[p];                               // depth
-        part[i] = wg[p] * v;
+        part[i] = wg[p] * value(p);
       }
       if (S >= 32) {
         // every 32-point group lies inside one ray: full warp reduction, then add the groups of a ray
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(128) composite_kernel(CompArgs a) {
             float v = 0.f;
             for (int i = 0; i < gpr; ++i) v += part[r * gpr + i];
             float* ro = a.ray_out + (static_cast<long>(b) * a.R + ray0 + r) * 260;
+            if (a.last_back && c < kRC + 3) v += (1.f - rayw[r]) * value(r * S + S - 1);
             if (c < kRC + 3) ro[c] = v + back * (1.f - rayw[r]);
             else ro[259] = v + (1.f - rayw[r]) * zs[r * S + S - 1];
           }
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(128) composite_kernel(CompArgs a) {
           for (int i = 0; i < 4; ++i) {
             const int r = (lane + 32 * i) / S;
             float* ro = a.ray_out + (static_cast<long>(b) * a.R + ray0 + r) * 260;
+            if (a.last_back && c < kRC + 3) part[i] += (1.f - rayw[r]) * value(r * S + S - 1);
             if (c < kRC + 3) ro[c] = part[i] + back * (1.f - rayw[r]);
             else ro[259] = part[i] + (1.f - rayw[r]) * zs[r * S + S - 1];
           }
@@ -296,12 +300,13 @@ static int comp_check(int B, int R, int S, const char* who) {
 
 int hg_render_composite(const float* sig, const float* z, const float* noise, const float* rgbp, const float* feat,
                         float* ray_out, float* weights, int B, int R, int S, float noise_std, int white_back,
-                        int clamp_softplus, void* stream) {
+                        int clamp_softplus, int last_back, void* stream) {
   HG_REQUIRE(sig && z && rgbp && feat && ray_out && weights, "hg_render_composite: null pointer");
   if (int rc = comp_check(B, R, S, "hg_render_composite")) return rc;
   hg::CompArgs a{};
   a.sig = sig; a.z = z; a.noise = noise; a.rgbp = rgbp; a.feat = feat; a.ray_out = ray_out; a.w_out = weights;
   a.B = B; a.R = R; a.S = S; a.noise_std = noise_std; a.white_back = white_back; a.softplus = clamp_softplus;
+  a.last_back = last_back;
   hg::composite_kernel<false><<<B * (R * S / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return hg::check_launch("hg_render_composite");
 }

@@ -91,6 +91,9 @@ struct SpadeArgs {
   const float* ascale;   // backward operand: per-(b,c) scale [B,C] applied to the incoming gradient, or null
   const float* rk_v;     // backward epilogue: rank-k term  acc += sum_j rgb_w[j][c] * rk_v[b][j][pixel]  (k = rk_n <= 3)
   int rk_n;
+  const float* mod2;     // forward, K = 512: [B,2,C] table of the SECOND source's channels (null: the first table serves both,
+                         // as for the renderer's first FiLM layer); lets a 512-channel layer (hidden_dim 384 / 420 zero-padded
+                         // to 2 x 256) be modulated per channel
 };
 
 struct SynSmem {
@@ -571,20 +574,30 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
           } else {   // no table = identity (plain 1x1 convolution)
             m.tab_g1[i] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 0) * kC + i] : 1.f;
             m.tab_g0[i] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 1) * kC + i] : 0.f;
+            if (a.mod2) {      // second source's table lives in the (otherwise pixel-style only) gamma/beta bias table
+              m.tab_bgb[i] = a.mod2[(static_cast<long>(b) * 2 + 0) * kC + i];
+              m.tab_bgb[kC + i] = a.mod2[(static_cast<long>(b) * 2 + 1) * kC + i];
+            }
           }
         }
         rows_barrier();
         cur_b = b;
       }
       const bool valid = ti * 128 + row < a.HW;
-      uint32_t tg1 = smem_u32(kBwd ? m.tab_as : m.tab_g1), tg0 = smem_u32(m.tab_g0);
-      opaque(tg1);   // the tables may just have been refreshed: no table load may move above this point
-      opaque(tg0);
+      uint32_t tg1a = smem_u32(kBwd ? m.tab_as : m.tab_g1), tg0a = smem_u32(m.tab_g0);
+      uint32_t tg1b = smem_u32(m.tab_bgb), tg0b = smem_u32(m.tab_bgb + kC);
+      opaque(tg1a);   // the tables may just have been refreshed: no table load may move above this point
+      opaque(tg0a);
+      opaque(tg1b);
+      opaque(tg0b);
       const float slope = a.slope;
       const bool sine = a.act == 1, scaled = kBwd && a.ascale != nullptr;
+      const bool two_tables = !kBwd && a.mod2 != nullptr;
 #pragma unroll 1
       for (int kc = 0; kc < a.nkc; ++kc, ++acnt) {
         const int c0 = (kc * 64 + h * 32) & (kC - 1);
+        const bool second = two_tables && kc * 64 >= kC;
+        const uint32_t tg1 = second ? tg1b : tg1a, tg0 = second ? tg0b : tg0a;
         float cur[32];
         take_x_pair(m, xg, h, row, lane, cur);
         const uint32_t slot = acnt & 1;
@@ -1046,6 +1059,35 @@ int hg_act_conv1x1_blocked(const float* x, const float* x2, const float* mod, in
   a.B = B; a.HW = Hg * Wg; a.Hg = Hg; a.Wg = Wg;
   a.nkc = x2 ? 8 : 4; a.xC = hg::kC; a.slope = 0.2f; a.cout = hg::kC; a.act = act;
   return launch_blocked_gemm(a, passes, false, static_cast<cudaStream_t>(stream), "hg_act_conv1x1_blocked");
+}
+
+int hg_blocked_conv_wide(const float* x, const float* x2, const float* mod, const float* mod2, int act, float slope,
+                         const void* wimg, const float* bias, const float* skip, float* out, double* stats,
+                         const float* rgb_w, const float* rgb_b, const float* rgb_in, float* rgb_out, int B, int Hg, int Wg,
+                         int passes, void* stream) {
+  HG_REQUIRE(x && wimg && bias && out, "hg_blocked_conv_wide: null pointer");
+  HG_REQUIRE(act == 0 || act == 1, "hg_blocked_conv_wide: act must be 0 (LeakyReLU(slope)) or 1 (sine)");
+  HG_REQUIRE(!mod2 || (mod && x2), "hg_blocked_conv_wide: mod2 needs mod and a second source");
+  HG_REQUIRE(!rgb_w || (rgb_b && rgb_out), "hg_blocked_conv_wide: rgb_b / rgb_out missing");
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_blocked_conv_wide: passes must be 1 or 3");
+  HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_blocked_conv_wide: bad shape");
+  const long T = (Hg * Wg + 127) / 128;
+  hg::SpadeArgs a{};
+  a.x = x;
+  a.x_bstride = T * hg::kC * 128;
+  a.x2 = x2;
+  a.mod = mod;
+  a.mod2 = mod2;
+  a.wimg = static_cast<const uint8_t*>(wimg);
+  a.bias = bias;
+  a.skip = skip;
+  a.skip_bstride = T * hg::kC * 128;
+  a.out = out;
+  a.stats = stats;
+  a.rgb_w = rgb_w; a.rgb_b = rgb_b; a.rgb_in = rgb_in; a.rgb_out = rgb_out;
+  a.B = B; a.HW = Hg * Wg; a.Hg = Hg; a.Wg = Wg;
+  a.nkc = x2 ? 8 : 4; a.xC = hg::kC; a.slope = slope; a.cout = hg::kC; a.act = act;
+  return launch_blocked_gemm(a, passes, false, static_cast<cudaStream_t>(stream), "hg_blocked_conv_wide");
 }
 
 int hg_conv1x1_blocked_bwd(const float* g, const float* g2, const float* aux, const float* mod, const void* wimg_t,

@@ -335,6 +335,17 @@ class Map3DGenerator(nn.Module):
         cond = {k: conditions[k] for k in ("skeletons_xyz", "vertices", "tpose_vertices", "fk_matrices", "lbs_weights",
                                            "cam2world_matrices", "intrinsics", "scales")}
         u, noise = rng.draw_render_noise(B, Rh * Rw, S, dev, cfg.get("sample_dist", None))
+        if self.hidden_dim != 256:
+            # hidden_dim 384 (MAP3DBN) / 420 (MAP3DBN512L, the released checkpoint): the zero-padded 2 x 256 path on the
+            # general blocked-GEMM engine (modules/wide_ops.py); forward only
+            if self._wants_grad():
+                raise RuntimeError("hg3d: gradients are built for hidden_dim == 256 (the 512-pixel curricula); hidden_dim "
+                                   f"{self.hidden_dim} runs forward only -- call it under torch.no_grad()")
+            from . import wide_ops
+            feats, rgb01, depth = wide_ops.render_forward_wide(P, freq, phase, cond, cfg, u, noise, passes=passes)
+            rgb = wide_ops.synthesis_forward_wide(P, feats, styles.reshape(B, -1), cfg, training=self.training, passes=passes)
+            rgb_render = (rgb01 * 2 - 1).reshape(B, Rh, Rw, 3).permute(0, 3, 1, 2)
+            return rgb, rgb_render, depth
         if self._wants_grad():
             # training step of the generator: layer-by-layer renderer + taped synthesis network (render_train.py,
             # synthesis_train.py); the fused inference kernels below keep nothing for a backward pass

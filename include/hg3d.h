@@ -162,6 +162,14 @@ int hg_conv1x1_blocked_bwd(const float* g, const float* g2, const float* aux, co
  * x2 NULL = K 256.  One FiLM-SIREN layer of COORDCONCATSIREN (modulated.py:41-75) over tile-blocked points. */
 int hg_act_conv1x1_blocked(const float* x, const float* x2, const float* mod, int act, const void* wimg, const float* bias,
                            float* out, int B, int Hg, int Wg, int passes, void* stream);
+/* The same engine with every option exposed: K = 256 or 512 input channels from one or two tile-blocked sources, a
+ * modulation table per source (mod / mod2 [B,2,256]; null = identity), act 0 = LeakyReLU(slope) / 1 = sine, residual add,
+ * next-layer BatchNorm statistics, ToRGB accumulation -- one output half (256 channels) of a layer whose width was
+ * zero-padded to 512: hidden_dim 384 (configs/map3d.py:61) and 420 (:254, the released checkpoint) run on it. */
+int hg_blocked_conv_wide(const float* x, const float* x2, const float* mod, const float* mod2, int act, float slope,
+                         const void* wimg, const float* bias, const float* skip, float* out, double* stats,
+                         const float* rgb_w, const float* rgb_b, const float* rgb_in, float* rgb_out, int B, int Hg, int Wg,
+                         int passes, void* stream);
 /* hg_wgrad_blocked with y = act(x*g1+g0), act 0 LeakyReLU 0.2 / 1 sine / 2 identity, and dout scaled per (sample, row) by
  * pscale [B,256] (NULL = 1). */
 int hg_act_wgrad_blocked(const float* dout, const float* pscale, const float* x, long x_bstride, int Cx, const float* mod,
@@ -172,14 +180,14 @@ int hg_act_wgrad_blocked(const float* dout, const float* pscale, const float* x,
  *                       (mod3 [B,2,256] = f, phi of the last FiLM slice; modulated.py:62-73).
  * hg_render_heads_bwd:  acc[4*256+4] fp64 += (d w_sigma, d W_rgb[0..2], d b[0..3]).
  * hg_render_composite(_bwd): vr.ray_integration (volume_rendering.py:12-56) and its gradient; ray_out / dray [B,R,260] =
- *                       feat(256) | rgb(3) | depth; last_back = False only; S in {8,16,32,64,128}. */
+ *                       feat(256) | rgb(3) | depth; last_back in the forward only; S in {8,16,32,64,128}. */
 int hg_render_heads(const float* out3, const float* linc, const float* mod3, const float* w_sigma, const float* w_rgb,
                     const float* heads_b, float* sig, float* rgbp, int B, int N, void* stream);
 int hg_render_heads_bwd(const float* out3, const float* linc, const float* mod3, const float* dsig, const float* drgbp,
                         double* acc, int B, int N, void* stream);
 int hg_render_composite(const float* sig, const float* z, const float* noise, const float* rgbp, const float* feat,
                         float* ray_out, float* weights, int B, int R, int S, float noise_std, int white_back,
-                        int clamp_softplus, void* stream);
+                        int clamp_softplus, int last_back /* forward only: eval_last_back of the sample app */, void* stream);
 int hg_render_composite_bwd(const float* sig, const float* z, const float* noise, const float* rgbp, const float* feat,
                             const float* dray, float* dfeat, float* drgbp, float* dsig, int B, int R, int S,
                             float noise_std, int white_back, int clamp_softplus, void* stream);

@@ -30,6 +30,13 @@ CASES = {
     "g_small_isolated_legacy": ("C2", dict(gen_height=32, gen_width=32, render_height=8, render_width=8, hidden_dim=64,
                                             latent_dim=64, feature_dim=64, map3d_mode="isolated", legacy_mode=True,
                                             last_back=True), 5, 200.0, 1.0, 2, 0.0),
+    # the widths of the other two shipped curricula: MAP3DBN512L (420, isolated + legacy, the released checkpoint, with the
+    # sample app's last_back) and MAP3DBN (384, mixed) -- configs/map3d.py:194-290, :3-95
+    "g_h420_isolated_legacy": ("C2", dict(gen_height=32, gen_width=32, render_height=8, render_width=8, hidden_dim=420,
+                                           latent_dim=420, feature_dim=420, map3d_mode="isolated", legacy_mode=True,
+                                           last_back=True), 6, 200.0, 1.0, 2, 0.0),
+    "g_h384_mixed": ("C2", dict(gen_height=32, gen_width=16, render_height=8, render_width=4, hidden_dim=384, latent_dim=384,
+                                 feature_dim=384), 7, 200.0, 1.0, 2, 0.5),
 }
 D_CASES = {"d_tiny": (dict(gen_height=64, gen_width=64), 7, 2)}
 
@@ -75,8 +82,14 @@ def main():
     pkg = importlib.import_module("3dhumangan_b200")
     from oracle import port
     gens, discs, impl = reference_modules()
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]          # optional: regenerate just these cases
     manifest = {}
+    if only:
+        with open(os.path.join(HERE, "manifest.json")) as f:
+            manifest = json.load(f)
     for name in CASES:
+        if only and name not in only:
+            continue
         cfg, params, cond, z, B = build_case(pkg, port, name)
         seed = 1234
         out, fmap, depth, sd = run_reference_generator(gens, impl, cfg, copy.deepcopy(params), cond, z, seed)
@@ -90,6 +103,8 @@ def main():
         manifest[name] = {"rng_seed": seed, "recipe": [CASES[name][0], CASES[name][1], *CASES[name][2:]]}
         print(name, "rgbs", tuple(out["rgbs"].shape), float(out["rgbs"].abs().mean()))
     for name, (over, pseed, B) in D_CASES.items():
+        if only and name not in only:
+            continue
         cfg = pkg.configs.baseline_config("C2")
         cfg.update(over)
         params = port.init_discriminator_params(cfg, seed=pseed)

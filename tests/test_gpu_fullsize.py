@@ -190,3 +190,37 @@ def test_discriminator_at_512(pkg, port, path):
     for k in ("prediction", "latents", "segments"):
         e = rel_l2(out[k].detach(), ref[k])
         assert e < 1e-3, (k, e)
+
+
+@pytest.mark.parametrize("name,over", [("C1", {}), ("C2native", dict(hidden_dim=420, latent_dim=420, feature_dim=420, map3d_mode="isolated",
+                                                                  legacy_mode=True))])
+def test_other_widths_at_config_size(pkg, port, monkeypatch, name, over):
+    """BASELINE config C1 (MAP3DBN: hidden 384, gen 256x256, render 64x64) and the released checkpoint's shape (MAP3DBN512L:
+    hidden 420, 512x256, render 96x48, isolated + legacy) through the module call, on the zero-padded blocked-GEMM path
+    (modules/wide_ops.py), against the oracle on the device."""
+    B = 1
+    cfg, params, cond, z, u, noise = _case(pkg, port, name, B, 90, nerf_noise=0.5, **over)
+    rng = importlib.import_module("3dhumangan_b200.rng")
+    monkeypatch.setattr(rng, "draw_render_noise", lambda *a, **k: (u, noise))
+    G = _generator(cfg, params)
+    cg, zg = _to(cond, "cuda"), z.cuda()
+    with torch.no_grad():
+        out = G(zg, cg, **cfg)
+    torch.cuda.synchronize()
+    pg = _to(params, "cuda")
+    stats = {}
+    with torch.no_grad():
+        ref = port.generator_forward(pg, zg, cg, cfg, u, noise, training=True, stats_out=stats)
+    assert out["rgbs"].shape == ref["rgbs"].shape
+    assert rel_l2(out["rgbs_render"], ref["rgbs_render"]) < 1e-3, rel_l2(out["rgbs_render"], ref["rgbs_render"])
+    assert rel_l2(out["rgbs"], ref["rgbs"]) < 1e-3, rel_l2(out["rgbs"], ref["rgbs"])
+    blk = "synthesis_network.network.m3d_8."
+    assert rel_l2(G.state_dict()[blk + "spade_1.first_norm.running_var"], stats[blk + "spade_1.first_norm.running_var"]) < 1e-3
+    # the sample app's entry point on this width: truncated, eval-mode statistics after a few train-mode forwards
+    with torch.no_grad():
+        for _ in range(2):
+            G(zg, cg, **cfg)
+        G.eval()
+        o2 = G.staged_forward(zg, cg, truncation_psi=0.7, **dict(cfg, nerf_noise=0, last_back=True))
+    assert o2["rgbs"].shape == ref["rgbs"].shape and torch.isfinite(o2["rgbs"]).all()
+    assert o2["depths"].shape == (B, 1, cfg["render_height"], cfg["render_width"])

@@ -8,7 +8,9 @@ import torch
 from golden_util import generator_case, manifest, rel_l2
 
 pytestmark = pytest.mark.gpu
-CASES = [k for k in manifest() if k.startswith("g_tiny")]
+# g_tiny*: hidden 256 (fused kernels); g_small / g_h420 / g_h384: other widths (zero-padded path, modules/wide_ops.py),
+# incl. the released checkpoint's 420 with isolated style, legacy feature order and the sample app's last_back
+CASES = [k for k in manifest() if k.startswith("g_")]
 
 
 def _generator(pkg, cfg, params):
