@@ -212,8 +212,8 @@ struct SepGeom {
   static constexpr int NV = kUp ? T / 2 + 2 : T + 6;                 // register window for 4 outputs
   static constexpr int TIW = kUp ? TOW / 2 + T / 2 + 1 : 2 * TOW + T - 2;
   static constexpr int TIH = kUp ? TOH / 2 + T / 2 + 1 : 2 * TOH + T - 2;
-  static constexpr int PIN = TIW | 1;                                 // odd pitches: conflict-free column walks
-  static constexpr int PMID = TOW + 1;
+  static constexpr int PIN = (TIW + 3) & ~3;                          // multiples of 4: 16-byte row segments stay aligned
+  static constexpr int PMID = TOW + 4;
   static constexpr int SMEM = (TIH * PIN + TIH * PMID + T) * 4;
 };
 
@@ -263,11 +263,11 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restr
                                                             int padx0, int pady0, int flip, float gain_axis, int tiles_x,
                                                             int tiles_y) {
   using G = SepGeom<T, kUp>;
-  extern __shared__ float sep_smem[];
+  extern __shared__ __align__(16) float sep_smem[];
   float* in_s = sep_smem;                       // [TIH][PIN]
   float* mid = in_s + G::TIH * G::PIN;          // [TIH][PMID]
   float* gs = mid + G::TIH * G::PMID;           // [T]
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < T) gs[tid] = (flip ? f[tid] : f[T - 1 - tid]) * gain_axis;
   const int tile = blockIdx.x;
   const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
@@ -275,48 +275,86 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restr
   const int ox0 = tx * G::TOW, oy0 = ty * G::TOH;
   const int ix0 = sep_first<kUp>(ox0, padx0), iy0 = sep_first<kUp>(oy0, pady0);
   const float* xp = x + plane * inH * inW;
-  // ---- (1) stage the input tile (coalesced rows; zero fill = padding)
-  for (int i = tid; i < G::TIH * G::TIW; i += 256) {
-    const int r = i / G::TIW, c = i - r * G::TIW;
-    const int gy = iy0 + r, gx = ix0 + c;
-    float v = 0.f;
-    if (gy >= 0 && gy < inH && gx >= 0 && gx < inW) v = __ldg(xp + static_cast<long>(gy) * inW + gx);
-    in_s[r * G::PIN + c] = v;
+  // ---- (1) stage the input tile: a warp walks rows, lanes walk columns (coalesced; zero fill = padding, incl. the pitch tail)
+  for (int r = warp; r < G::TIH; r += 8) {
+    const int gy = iy0 + r;
+    const bool rowok = gy >= 0 && gy < inH;
+    const float* src = xp + static_cast<long>(rowok ? gy : 0) * inW;
+#pragma unroll
+    for (int c0 = 0; c0 < G::PIN; c0 += 32) {
+      const int c = c0 + lane;
+      if (c < G::PIN) {
+        const int gx = ix0 + c;
+        in_s[r * G::PIN + c] = (rowok && c < G::TIW && gx >= 0 && gx < inW) ? __ldg(src + gx) : 0.f;
+      }
+    }
   }
   __syncthreads();
   float g[T];
 #pragma unroll
   for (int k = 0; k < T; ++k) g[k] = gs[k];
   const bool oddx = ((ox0 - padx0) & 1) != 0, oddy = ((oy0 - pady0) & 1) != 0;
-  // ---- (2) horizontal: items = (input row, group of 4 output columns); consecutive threads walk down the rows
+  // ---- (2) horizontal: item = (input row, group of 4 output columns).  The window of group a starts at column 2a (up) / 8a
+  //      (down) of the staged tile -- even, so it is read as float2 (up) / float4 (down) -- and never leaves the tile.
   for (int i = tid; i < G::TIH * (G::TOW / 4); i += 256) {
-    const int r = i % G::TIH, a = i / G::TIH;
-    const int b = sep_first<kUp>(ox0 + 4 * a, padx0) - ix0;
-    float v[G::NV];
+    const int a = i & (G::TOW / 4 - 1), r = i / (G::TOW / 4);
+    const float* wsrc = in_s + r * G::PIN + (kUp ? 2 * a : 8 * a);
+    float v[G::NV + 3];
+    if (kUp) {
 #pragma unroll
-    for (int j = 0; j < G::NV; ++j) v[j] = (b + j < G::TIW) ? in_s[r * G::PIN + b + j] : 0.f;
+      for (int j = 0; j < (G::NV + 1) / 2; ++j) {
+        const float2 t2 = *reinterpret_cast<const float2*>(wsrc + 2 * j);
+        v[2 * j] = t2.x;
+        v[2 * j + 1] = t2.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < (G::NV + 3) / 4; ++j) {
+        const float4 t4 = *reinterpret_cast<const float4*>(wsrc + 4 * j);
+        v[4 * j] = t4.x; v[4 * j + 1] = t4.y; v[4 * j + 2] = t4.z; v[4 * j + 3] = t4.w;
+      }
+    }
     float o[4];
     sep_fir4<T, kUp>(v, g, oddx, o);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) mid[r * G::PMID + 4 * a + q] = o[q];
+    *reinterpret_cast<float4*>(mid + r * G::PMID + 4 * a) = make_float4(o[0], o[1], o[2], o[3]);
   }
   __syncthreads();
-  // ---- (3) vertical: items = (output column, group of 4 output rows); consecutive threads = consecutive columns
+  // ---- (3) vertical: item = (group of 4 output columns, group of 4 output rows): float4 columns of `mid`, 16 outputs,
+  //      float4 stores (rows of the output are 16-byte aligned when outW % 4 == 0)
   float* yp = y + plane * outH * outW;
-  for (int i = tid; i < G::TOW * (G::TOH / 4); i += 256) {
-    const int c = i % G::TOW, a = i / G::TOW;
-    const int b = sep_first<kUp>(oy0 + 4 * a, pady0) - iy0;
-    float v[G::NV];
+  const bool vec_ok = (outW & 3) == 0;
+  for (int i = tid; i < (G::TOW / 4) * (G::TOH / 4); i += 256) {
+    const int c4 = i & (G::TOW / 4 - 1), a = i / (G::TOW / 4);
+    const float* wsrc = mid + (kUp ? 2 * a : 8 * a) * G::PMID + 4 * c4;
+    float4 v4[G::NV];
 #pragma unroll
-    for (int j = 0; j < G::NV; ++j) v[j] = (b + j < G::TIH) ? mid[(b + j) * G::PMID + c] : 0.f;
-    float o[4];
-    sep_fir4<T, kUp>(v, g, oddy, o);
-    const int ox = ox0 + c;
-    if (ox < outW) {
+    for (int j = 0; j < G::NV; ++j) v4[j] = *reinterpret_cast<const float4*>(wsrc + j * G::PMID);
+    float col[G::NV], o0[4], o1[4], o2[4], o3[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int oy = oy0 + 4 * a + q;
-        if (oy < outH) __stcs(yp + static_cast<long>(oy) * outW + ox, o[q]);
+    for (int j = 0; j < G::NV; ++j) col[j] = v4[j].x;
+    sep_fir4<T, kUp>(col, g, oddy, o0);
+#pragma unroll
+    for (int j = 0; j < G::NV; ++j) col[j] = v4[j].y;
+    sep_fir4<T, kUp>(col, g, oddy, o1);
+#pragma unroll
+    for (int j = 0; j < G::NV; ++j) col[j] = v4[j].z;
+    sep_fir4<T, kUp>(col, g, oddy, o2);
+#pragma unroll
+    for (int j = 0; j < G::NV; ++j) col[j] = v4[j].w;
+    sep_fir4<T, kUp>(col, g, oddy, o3);
+    const int ox = ox0 + 4 * c4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int oy = oy0 + 4 * a + q;
+      if (oy >= outH) continue;
+      float* dst = yp + static_cast<long>(oy) * outW + ox;
+      if (vec_ok && ox + 3 < outW) {
+        __stcs(reinterpret_cast<float4*>(dst), make_float4(o0[q], o1[q], o2[q], o3[q]));
+      } else {
+        if (ox < outW) __stcs(dst, o0[q]);
+        if (ox + 1 < outW) __stcs(dst + 1, o1[q]);
+        if (ox + 2 < outW) __stcs(dst + 2, o2[q]);
+        if (ox + 3 < outW) __stcs(dst + 3, o3[q]);
       }
     }
   }
