@@ -70,6 +70,14 @@ SIGNATURES = {
     "hg_linear": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "hg_conv3x3_wgrad_halo_workspace_bytes": (ctypes.c_size_t, []),
     "hg_conv3x3_wgrad_halo": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p, c_void_p, c_int, c_void_p]),
+    "hg_label_histogram": (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p]),
+    "hg_seg_ce_coef": (c_int, [c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),
+    "hg_seg_ce": (c_int, [c_void_p] * 6 + [c_int, c_int, c_long, c_void_p]),
+    "hg_mt_entry_bytes": (c_int, []),
+    "hg_mt_chunk_bytes": (c_int, []),
+    "hg_mt_chunk_elems": (c_int, []),
+    "hg_mt_grad_norm": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "hg_mt_adam": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
     "hg_spectral_entry_bytes": (c_int, []),
     "hg_spectral_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p]),
 }

@@ -214,7 +214,7 @@ struct SepGeom {
   static constexpr int TIH = kUp ? TOH / 2 + T / 2 + 1 : 2 * TOH + T - 2;
   static constexpr int PIN = (TIW + 3) & ~3;                          // multiples of 4: 16-byte row segments stay aligned
   static constexpr int PMID = TOW + 4;
-  static constexpr int SMEM = (TIH * PIN + TIH * PMID + T) * 4;
+  static constexpr int SMEM = (2 * TIH * PIN + TIH * PMID + T) * 4;     // input tile double-buffered (cp.async prefetch)
 };
 
 // first input index touched by output o (floor semantics for negative values)
@@ -261,38 +261,53 @@ template <int T, bool kUp>
 __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restrict__ x, const float* __restrict__ f,
                                                             float* __restrict__ y, int inH, int inW, int outH, int outW,
                                                             int padx0, int pady0, int flip, float gain_axis, int tiles_x,
-                                                            int tiles_y) {
+                                                            int tiles_y, long nplanes) {
   using G = SepGeom<T, kUp>;
   extern __shared__ __align__(16) float sep_smem[];
-  float* in_s = sep_smem;                       // [TIH][PIN]
-  float* mid = in_s + G::TIH * G::PIN;          // [TIH][PMID]
-  float* gs = mid + G::TIH * G::PMID;           // [T]
+  float* in_buf = sep_smem;                          // [2][TIH][PIN]
+  float* mid = in_buf + 2 * G::TIH * G::PIN;         // [TIH][PMID]
+  float* gs = mid + G::TIH * G::PMID;                // [T]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < T) gs[tid] = (flip ? f[tid] : f[T - 1 - tid]) * gain_axis;
-  const int tile = blockIdx.x;
-  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
-  const long plane = tile / (tiles_x * tiles_y);
-  const int ox0 = tx * G::TOW, oy0 = ty * G::TOH;
-  const int ix0 = sep_first<kUp>(ox0, padx0), iy0 = sep_first<kUp>(oy0, pady0);
-  const float* xp = x + plane * inH * inW;
-  // ---- (1) stage the input tile: a warp walks rows, lanes walk columns (coalesced; zero fill = padding, incl. the pitch tail)
-  for (int r = warp; r < G::TIH; r += 8) {
-    const int gy = iy0 + r;
-    const bool rowok = gy >= 0 && gy < inH;
-    const float* src = xp + static_cast<long>(rowok ? gy : 0) * inW;
+  const long ntiles = static_cast<long>(nplanes) * tiles_x * tiles_y;
+  // ---- (1) stage an input tile with 4-byte cp.async (zero fill = padding, incl. the pitch tail): a warp walks rows, lanes
+  //      walk columns (coalesced).  The NEXT tile is prefetched while this one is filtered and stored.
+  auto prefetch = [&](long tile, float* dst) {
+    const int tx = static_cast<int>(tile % tiles_x), ty = static_cast<int>((tile / tiles_x) % tiles_y);
+    const long plane = tile / (static_cast<long>(tiles_x) * tiles_y);
+    const int ix0 = sep_first<kUp>(tx * G::TOW, padx0), iy0 = sep_first<kUp>(ty * G::TOH, pady0);
+    const float* xp = x + plane * inH * inW;
+    for (int r = warp; r < G::TIH; r += 8) {
+      const int gy = iy0 + r;
+      const bool rowok = gy >= 0 && gy < inH;
+      const float* src = xp + static_cast<long>(rowok ? gy : 0) * inW;
 #pragma unroll
-    for (int c0 = 0; c0 < G::PIN; c0 += 32) {
-      const int c = c0 + lane;
-      if (c < G::PIN) {
-        const int gx = ix0 + c;
-        in_s[r * G::PIN + c] = (rowok && c < G::TIW && gx >= 0 && gx < inW) ? __ldg(src + gx) : 0.f;
+      for (int c0 = 0; c0 < G::PIN; c0 += 32) {
+        const int c = c0 + lane;
+        if (c < G::PIN) {
+          const int gx = ix0 + c;
+          const bool ok = rowok && c < G::TIW && gx >= 0 && gx < inW;
+          const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * G::PIN + c));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
+        }
       }
     }
-  }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (blockIdx.x < ntiles) prefetch(blockIdx.x, in_buf);
   __syncthreads();
   float g[T];
 #pragma unroll
   for (int k = 0; k < T; ++k) g[k] = gs[k];
+  int cur = 0;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur ^= 1) {
+  const int tx = static_cast<int>(tile % tiles_x), ty = static_cast<int>((tile / tiles_x) % tiles_y);
+  const long plane = tile / (static_cast<long>(tiles_x) * tiles_y);
+  const int ox0 = tx * G::TOW, oy0 = ty * G::TOH;
+  const float* in_s = in_buf + cur * G::TIH * G::PIN;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();                                  // this tile's input has landed; everybody is done with the other buffer
+  if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, in_buf + (cur ^ 1) * G::TIH * G::PIN);
   const bool oddx = ((ox0 - padx0) & 1) != 0, oddy = ((oy0 - pady0) & 1) != 0;
   // ---- (2) horizontal: item = (input row, group of 4 output columns).  The window of group a starts at column 2a (up) / 8a
   //      (down) of the staged tile -- even, so it is read as float2 (up) / float4 (down) -- and never leaves the tile.
@@ -358,6 +373,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restr
       }
     }
   }
+  }   // tile loop
 }
 
 template <int T>
@@ -368,14 +384,16 @@ static int launch_sep(bool up, const float* x, const float* f, float* y, long pl
     using G = SepGeom<T, true>;
     const int txn = (outW + G::TOW - 1) / G::TOW, tyn = (outH + G::TOH - 1) / G::TOH;
     cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-    upfirdn2d_sep_kernel<T, true><<<static_cast<unsigned>(planes * txn * tyn), 256, G::SMEM, st>>>(
-        x, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn, tyn);
+    const long nt = planes * txn * tyn, cap = static_cast<long>(num_sms()) * 6;
+    upfirdn2d_sep_kernel<T, true><<<static_cast<unsigned>(nt < cap ? nt : cap), 256, G::SMEM, st>>>(
+        x, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn, tyn, planes);
   } else {
     using G = SepGeom<T, false>;
     const int txn = (outW + G::TOW - 1) / G::TOW, tyn = (outH + G::TOH - 1) / G::TOH;
     cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-    upfirdn2d_sep_kernel<T, false><<<static_cast<unsigned>(planes * txn * tyn), 256, G::SMEM, st>>>(
-        x, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn, tyn);
+    const long nt = planes * txn * tyn, cap = static_cast<long>(num_sms()) * 2;
+    upfirdn2d_sep_kernel<T, false><<<static_cast<unsigned>(nt < cap ? nt : cap), 256, G::SMEM, st>>>(
+        x, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn, tyn, planes);
   }
   return check_launch("hg_upfirdn2d_sep2");
 }

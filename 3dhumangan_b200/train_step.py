@@ -95,12 +95,18 @@ def generator_param_groups(named_params, meta):
     ]
 
 
-def make_optimizers(G, D, meta):
-    """Adam for G (five groups with the curriculum's learning-rate multipliers) and D, as PhaseTrainer.init_optimizer."""
+def make_optimizers(G, D, meta, fused=True):
+    """Adam for G (five groups with the curriculum's learning-rate multipliers) and D, as PhaseTrainer.init_optimizer.
+    fused=True: `ops.trainer_ops.FusedAdam` (same state_dict and arithmetic as torch.optim.Adam, one multi-tensor launch that
+    also carries the gradient clipping and the EMA); fused=False: torch.optim.Adam."""
     betas = tuple(float(b) for b in meta.get("betas", (0, 0.9)))
     wd = meta.get("weight_decay", 0)
-    og = torch.optim.Adam(generator_param_groups(G.named_parameters(), meta), lr=meta["gen_lr"], betas=betas, weight_decay=wd)
-    od = torch.optim.Adam(D.parameters(), lr=meta["disc_lr"], betas=betas, weight_decay=wd)
+    if fused:
+        from .ops.trainer_ops import FusedAdam as Adam
+    else:
+        Adam = torch.optim.Adam
+    og = Adam(generator_param_groups(G.named_parameters(), meta), lr=meta["gen_lr"], betas=betas, weight_decay=wd)
+    od = Adam(D.parameters(), lr=meta["disc_lr"], betas=betas, weight_decay=wd)
     return og, od
 
 
@@ -176,9 +182,12 @@ class Trainer:
     optional z_d / z_g latents (drawn like `z_sampler` otherwise)).  `meta` is the merged curriculum dict that the
     reference splats into every call."""
 
-    def __init__(self, G, D, meta, *, amp=None, ddp=None, amp_dtype=torch.float16, ema_decay=0.999):
+    def __init__(self, G, D, meta, *, amp=None, ddp=None, amp_dtype=torch.float16, ema_decay=0.999, fused=True):
+        """fused=True: the loss / clipping / Adam / EMA tail on the sm_100a kernels of csrc/trainer.cu (ops.trainer_ops);
+        fused=False: the same steps as torch calls (F.cross_entropy, clip_grad_norm_, torch.optim.Adam, foreach lerp)."""
         import torch.distributed as dist
         self.meta = dict(meta)
+        self.fused = bool(fused)
         self.amp = bool(self.meta.get("use_mixed_precision", False)) if amp is None else bool(amp)
         self.amp_dtype = amp_dtype
         self.scaler = torch.amp.GradScaler("cuda", enabled=self.amp and amp_dtype == torch.float16)
@@ -195,11 +204,31 @@ class Trainer:
         self.generator, self.discriminator = G, D
         # groups are selected by name substrings, which survive DDP's "module." prefix (the reference builds them from
         # `generator_ddp.named_parameters()`, phase_trainer.py:59)
-        self.optimizer_G, self.optimizer_D = make_optimizers(self.generator_ddp, self.discriminator_ddp, self.meta)
+        self.optimizer_G, self.optimizer_D = make_optimizers(self.generator_ddp, self.discriminator_ddp, self.meta, fused=self.fused)
         self.ema = ParameterEMA(G.parameters(), decay=ema_decay)
         self.batch_split = int(self.meta.get("batch_split", 1))
 
     # -- helpers
+    def _seg_loss(self, segments, gt):
+        if self.fused:
+            from .ops.trainer_ops import seg_ce_balanced
+            return seg_ce_balanced(segments, gt, self.meta["label_dim"], self.meta.get("segmentation_weights"))
+        return segmentation_loss(segments, gt, self.meta["label_dim"], self.meta.get("segmentation_weights"))
+
+    def _optimizer_step(self, opt, params, ema=None):
+        """unscale_ -> clip_grad_norm_ -> scaler.step (-> EMA): phase_trainer.py:313-316, 335-339."""
+        self.scaler.unscale_(opt)
+        if self.fused:
+            opt._stepped = False
+            self.scaler.step(opt, clip_max_norm=self.meta["grad_clip"], ema=ema)
+            if ema is not None and not opt._stepped:          # GradScaler skipped the step (inf / nan): the EMA still follows
+                ema.update(params)
+        else:
+            torch.nn.utils.clip_grad_norm_(params, self.meta["grad_clip"])
+            self.scaler.step(opt)
+            if ema is not None:
+                ema.update(params)
+
     def _autocast(self):
         return torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp)
 
@@ -243,10 +272,8 @@ class Trainer:
             else:
                 gan_loss = pred_gen.sum() * 0 + pred_real.sum() * 0
             if meta["segmentation_lambda"] > 0:
-                L = meta["label_dim"]
-                w = meta.get("segmentation_weights")
-                seg = (segmentation_loss(out_real["segments"], labels, L, w)
-                       + segmentation_loss(out_gen["segments"], torch.zeros_like(labels), L, w)) * meta["segmentation_lambda"]
+                seg = (self._seg_loss(out_real["segments"], labels)
+                       + self._seg_loss(out_gen["segments"], torch.zeros_like(labels))) * meta["segmentation_lambda"]
             else:
                 seg = (out_real["segments"].sum() + out_gen["segments"].sum()) * 0
             latent_loss = (out_real["latents"].sum() + out_gen["latents"].sum()) * 0      # latent_lambda = 0 in every shipped curriculum
@@ -254,9 +281,7 @@ class Trainer:
                 raise RuntimeError("hg3d: latent_lambda > 0 is not used by any shipped curriculum and is not built")
             d_loss = gan_loss + grad_penalty + seg + latent_loss
         self.scaler.scale(d_loss).backward()
-        self.scaler.unscale_(self.optimizer_D)
-        torch.nn.utils.clip_grad_norm_(self.discriminator_ddp.parameters(), meta["grad_clip"])
-        self.scaler.step(self.optimizer_D)
+        self._optimizer_step(self.optimizer_D, list(self.discriminator_ddp.parameters()))
         return d_loss.detach()
 
     # -- phase_trainer.py:321-341 + :446-560
@@ -288,8 +313,7 @@ class Trainer:
                     gan_loss = gan_lambda * F.softplus(-pred_gen).mean() if gan_lambda > 0 else 0 * pred_gen.sum()
                     latent_loss = out["latents"].sum() * 0
                     if meta["segmentation_lambda"] > 0:
-                        seg = segmentation_loss(out["segments"], labels[sl], meta["label_dim"],
-                                                meta.get("segmentation_weights")) * meta["segmentation_lambda"]
+                        seg = self._seg_loss(out["segments"], labels[sl]) * meta["segmentation_lambda"]
                     else:
                         seg = out["segments"].sum() * 0
                     g_loss = (gan_loss + latent_loss + seg) / self.batch_split
@@ -298,12 +322,23 @@ class Trainer:
         finally:
             for p, f in zip(d_params, flags):
                 p.requires_grad_(f)
-        self.scaler.unscale_(self.optimizer_G)
-        torch.nn.utils.clip_grad_norm_(self.generator_ddp.parameters(), meta["grad_clip"])
-        self.scaler.step(self.optimizer_G)
-        self.scaler.update()
-        self.ema.update(self.generator_ddp.parameters())
+        self._optimizer_step_g(list(self.generator_ddp.parameters()))
         return total
+
+    def _optimizer_step_g(self, gparams):
+        """phase_trainer.py:335-339: unscale_, clip, step, scaler.update(), EMA."""
+        self.scaler.unscale_(self.optimizer_G)
+        if self.fused:
+            self.optimizer_G._stepped = False
+            self.scaler.step(self.optimizer_G, clip_max_norm=self.meta["grad_clip"], ema=self.ema)
+            self.scaler.update()
+            if not self.optimizer_G._stepped:
+                self.ema.update(gparams)
+        else:
+            torch.nn.utils.clip_grad_norm_(gparams, self.meta["grad_clip"])
+            self.scaler.step(self.optimizer_G)
+            self.scaler.update()
+            self.ema.update(gparams)
 
     def iteration(self, batch, alpha=1.0):
         """base_trainer.py:366-446: discriminator step, generator step, step counters."""
@@ -322,7 +357,8 @@ def train_iteration(G, D, opt_g, opt_d, batch, cfg, trainer=None):
     builds a `Trainer` around them once (cached on G)."""
     t = trainer or getattr(G, "_hg_trainer", None)
     if t is None or t.discriminator is not D:
-        t = Trainer(G, D, cfg, amp=False)
+        from .ops.trainer_ops import FusedAdam
+        t = Trainer(G, D, cfg, amp=False, fused=isinstance(opt_g, FusedAdam) and isinstance(opt_d, FusedAdam))
         t.optimizer_G, t.optimizer_D = opt_g, opt_d
         G._hg_trainer = t
     return t.iteration(batch)

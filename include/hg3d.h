@@ -253,6 +253,29 @@ int hg_spectral_entry_bytes(void);
 int hg_spectral_norm(const void* table, int count, int max_n, int max_k, float* inv_sigma, int training, float eps,
                      void* stream);
 
+/* ---- loss + optimiser tail of a training iteration ---------------------------------------------------
+ * Class-balanced segmentation cross entropy, PhaseTrainer._calculate_segmentation_loss mode 'cross_entropy_balanced'
+ * (lib/trainers/phase_trainer.py:203-256): histogram of the int64 labels -> per-class coefficients (numel / (occ * n_occ) *
+ * prior / mean(prior); background and absent classes 0; all ones when no foreground label occurs) -> one pass over the
+ * logits [B,L,HW] that writes loss[0] = mean_px coef[gt] * CE and, optionally, d loss / d logits.  L <= 32. */
+int hg_label_histogram(const long* labels, long n, int L, int* hist, void* stream);
+int hg_seg_ce_coef(const int* hist, const float* prior /* [L] or NULL */, int L, double numel, float* coef, void* stream);
+int hg_seg_ce(const float* logits, const long* labels, const float* coef, float* dlogits /* or NULL */, float* loss,
+              double* workspace /* >= 2 * #SMs doubles */, int B, int L, long HW, void* stream);
+/* Multi-tensor global-norm clipping (torch.nn.utils.clip_grad_norm_, phase_trainer.py:314,336), torch.optim.Adam's update
+ * with per-group scalars (phase_trainer.py:57-76) and the generator's EMA (lib/components/ema.py:29-48) over a device table
+ * of tensors: entries { float* p, g, exp_avg, exp_avg_sq, ema; long n } (hg_mt_entry_bytes() = 48; g NULL = no gradient this
+ * step, ema NULL = no shadow), chunks { int tensor; int group; long offset } (hg_mt_chunk_bytes() = 16, hg_mt_chunk_elems()
+ * elements each).  norm_clip[0] = global norm, [1] = min(1, max_norm / (norm + 1e-6)).  scalars (HOST): 7 arrays of ngroups
+ * floats: lr, beta1, beta2, eps, weight_decay, 1 - beta1^t, sqrt(1 - beta2^t). */
+int hg_mt_entry_bytes(void);
+int hg_mt_chunk_bytes(void);
+int hg_mt_chunk_elems(void);
+int hg_mt_grad_norm(const void* table, const void* chunks, int nchunks, float max_norm, double* partials, float* norm_clip,
+                    void* stream);
+int hg_mt_adam(const void* table, const void* chunks, int nchunks, const float* norm_clip /* or NULL */, const float* scalars,
+               int ngroups, float ema_one_minus_decay, int write_clipped_grad, void* stream);
+
 /* ---- StyleGAN3 native ops named by the reference ---------------------------------------------- */
 /* y = clamp(act(x + b[(i / stepB) % sizeB]) * gain)   replaces bias_act.cpp:32 / bias_act.cu:24 (forward).
  * act: 1 linear 2 relu 3 lrelu 4 tanh 5 sigmoid 6 elu 7 selu 8 softplus 9 swish; clamp < 0 disables. */

@@ -184,3 +184,72 @@ def test_upfirdn2d_fused_separable_multi_tile(port, taps):
             got = uf.upfirdn2d(x.cuda(), **{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}).cpu()
         assert got.shape == ref.shape, (kw, got.shape, ref.shape)
         assert torch.allclose(got, ref, rtol=2e-5, atol=2e-5), (kw["padding"], kw.get("up"), kw["flip_filter"], (got - ref).abs().max())
+
+
+@pytest.mark.parametrize("case", ["balanced", "background_only", "prior"])
+def test_seg_ce_balanced_matches_trainer_formula(case):
+    """hg_seg_ce (one pass: loss + gradient) vs the torch restatement of PhaseTrainer._calculate_segmentation_loss
+    (train_step.segmentation_loss, itself pinned to the reference's values by tests/golden/seg_loss.npz on the CPU)."""
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    to = importlib.import_module("3dhumangan_b200.ops.trainer_ops")
+    g = torch.Generator().manual_seed(11)
+    B, L, H, W = 3, 26, 40, 56
+    logits = (torch.randn(B, L, H, W, generator=g) * 3).cuda()
+    if case == "background_only":
+        gt = torch.zeros(B, H, W, dtype=torch.int64).cuda()
+    else:
+        gt = torch.randint(0, L, (B, H, W), generator=g)
+        gt[gt == 7] = 0                                    # a class that never occurs
+        gt = gt.cuda()
+    prior = [1.0 + 0.1 * i for i in range(L)] if case == "prior" else None
+    a = logits.clone().requires_grad_(True)
+    ref = ts.segmentation_loss(a, gt, L, prior)
+    ref.backward()
+    b = logits.clone().requires_grad_(True)
+    got = to.seg_ce_balanced(b, gt, L, prior)
+    (got * 1.7).backward()
+    torch.cuda.synchronize()
+    assert abs(float(got) - float(ref)) < 2e-6 * max(1.0, abs(float(ref))), (float(got), float(ref))
+    assert float((b.grad / 1.7 - a.grad).abs().max()) < 2e-6 * float(a.grad.abs().max()) + 1e-12
+
+
+@pytest.mark.parametrize("betas,wd", [((0.0, 0.9), 0.0), ((0.9, 0.999), 0.01)])
+def test_fused_adam_clip_ema_matches_torch(betas, wd):
+    """FusedAdam.step(clip_max_norm, ema) vs clip_grad_norm_ + torch.optim.Adam + the reference's EMA update, two parameter
+    groups with different learning rates, tensors larger than one chunk, a parameter without gradient; state_dict interchange."""
+    to = importlib.import_module("3dhumangan_b200.ops.trainer_ops")
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    g = torch.Generator().manual_seed(12)
+    shapes = [(300, 41), (7,), (5000, 3), (64, 64, 1, 1), (3,)]
+    p_ref = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+    p_fus = [torch.nn.Parameter(p.detach().clone()) for p in p_ref]
+    groups = lambda ps: [{"params": ps[:2], "name": "a"}, {"params": ps[2:], "name": "b", "lr": 3e-3}]
+    o_ref = torch.optim.Adam(groups(p_ref), lr=1e-3, betas=betas, weight_decay=wd)
+    o_fus = to.FusedAdam(groups(p_fus), lr=1e-3, betas=betas, weight_decay=wd)
+    e_ref = ts.ParameterEMA(p_ref, decay=0.999)
+    e_fus = ts.ParameterEMA(p_fus, decay=0.999)
+    for it in range(4):
+        for i, (a, b) in enumerate(zip(p_ref, p_fus)):
+            if i == 4 and it % 2 == 0:                    # a parameter that gets no gradient in some steps
+                a.grad = b.grad = None
+                continue
+            gr = torch.randn(a.shape, generator=g).cuda() * (10.0 if it == 1 else 0.1)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        n_ref = torch.nn.utils.clip_grad_norm_(p_ref, 1.0)
+        o_ref.step()
+        e_ref.update(p_ref)
+        o_fus.step(clip_max_norm=1.0, ema=e_fus)
+        torch.cuda.synchronize()
+        assert abs(float(o_fus.last_grad_norm) - float(n_ref)) < 1e-5 * float(n_ref)
+        for a, b in zip(p_ref, p_fus):
+            assert float((a - b).abs().max()) < 2e-6 * float(a.abs().max()), it
+            if a.grad is not None:
+                assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-8)           # clipped in place on both sides
+        for a, b in zip(e_ref.shadow_params, e_fus.shadow_params):
+            assert float((a - b).abs().max()) < 2e-6 * float(a.abs().max())
+    assert e_ref.num_updates == e_fus.num_updates == 4
+    sd = o_ref.state_dict()
+    o_fus.load_state_dict(sd)                              # same schema: step / exp_avg / exp_avg_sq, param_groups with names
+    assert [g_["name"] for g_ in o_fus.param_groups] == ["a", "b"]
+    for k, v in o_fus.state_dict()["state"].items():
+        assert set(v) == {"step", "exp_avg", "exp_avg_sq"}
