@@ -84,7 +84,10 @@ class FusedAdam(torch.optim.Optimizer):
         return [(gi, p) for gi, grp in enumerate(self.param_groups) for p in grp["params"]]
 
     @torch.no_grad()
-    def step(self, closure=None, clip_max_norm=None, ema=None):
+    def step(self, closure=None, clip_max_norm=None, ema=None, ema_params=None):
+        """ema: an object with `shadow_params` / `decay` / `num_updates` (train_step.ParameterEMA = lib/components/ema.py);
+        ema_params: the parameter list the EMA was built from, in ITS order (`generator.parameters()`, ema.py:25 -- not the
+        order of the optimiser's groups).  Defaults to this optimiser's parameters in group order."""
         if closure is not None:
             raise RuntimeError("hg3d: FusedAdam does not take a closure")
         abi.require_device()
@@ -92,10 +95,12 @@ class FusedAdam(torch.optim.Optimizer):
         dev = flat[0][1].device
         shadow = None
         if ema is not None:      # shadow copies exist for the parameters that require grad, in parameters() order (ema.py:25)
-            req = [p for _, p in flat if p.requires_grad]
-            if len(req) != len(ema.shadow_params):
-                raise RuntimeError("hg3d: the EMA does not cover this optimiser's parameters")
+            req = [p for p in (ema_params if ema_params is not None else [q for _, q in flat]) if p.requires_grad]
+            if len(req) != len(ema.shadow_params) or any(p.shape != s.shape for p, s in zip(req, ema.shadow_params)):
+                raise RuntimeError("hg3d: the EMA's shadow parameters do not line up with `ema_params`")
             shadow = {id(p): s for p, s in zip(req, ema.shadow_params)}
+            if any(id(p) not in shadow for _, p in flat if p.requires_grad):
+                raise RuntimeError("hg3d: the EMA does not cover this optimiser's parameters")
         # per-(group, step) scalars
         sgroups, sidx = [], {}
         ents = np.zeros((len(flat), 6), dtype=np.int64)

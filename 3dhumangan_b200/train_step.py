@@ -220,7 +220,7 @@ class Trainer:
         self.scaler.unscale_(opt)
         if self.fused:
             opt._stepped = False
-            self.scaler.step(opt, clip_max_norm=self.meta["grad_clip"], ema=ema)
+            self.scaler.step(opt, clip_max_norm=self.meta["grad_clip"], ema=ema, ema_params=params if ema is not None else None)
             if ema is not None and not opt._stepped:          # GradScaler skipped the step (inf / nan): the EMA still follows
                 ema.update(params)
         else:
@@ -330,7 +330,7 @@ class Trainer:
         self.scaler.unscale_(self.optimizer_G)
         if self.fused:
             self.optimizer_G._stepped = False
-            self.scaler.step(self.optimizer_G, clip_max_norm=self.meta["grad_clip"], ema=self.ema)
+            self.scaler.step(self.optimizer_G, clip_max_norm=self.meta["grad_clip"], ema=self.ema, ema_params=gparams)
             self.scaler.update()
             if not self.optimizer_G._stepped:
                 self.ema.update(gparams)

@@ -226,8 +226,8 @@ def test_fused_adam_clip_ema_matches_torch(betas, wd):
     groups = lambda ps: [{"params": ps[:2], "name": "a"}, {"params": ps[2:], "name": "b", "lr": 3e-3}]
     o_ref = torch.optim.Adam(groups(p_ref), lr=1e-3, betas=betas, weight_decay=wd)
     o_fus = to.FusedAdam(groups(p_fus), lr=1e-3, betas=betas, weight_decay=wd)
-    e_ref = ts.ParameterEMA(p_ref, decay=0.999)
-    e_fus = ts.ParameterEMA(p_fus, decay=0.999)
+    e_ref = ts.ParameterEMA(p_ref[::-1], decay=0.999)       # the EMA's own order differs from the optimiser's group order
+    e_fus = ts.ParameterEMA(p_fus[::-1], decay=0.999)
     for it in range(4):
         for i, (a, b) in enumerate(zip(p_ref, p_fus)):
             if i == 4 and it % 2 == 0:                    # a parameter that gets no gradient in some steps
@@ -237,8 +237,8 @@ def test_fused_adam_clip_ema_matches_torch(betas, wd):
             a.grad, b.grad = gr.clone(), gr.clone()
         n_ref = torch.nn.utils.clip_grad_norm_(p_ref, 1.0)
         o_ref.step()
-        e_ref.update(p_ref)
-        o_fus.step(clip_max_norm=1.0, ema=e_fus)
+        e_ref.update(p_ref[::-1])
+        o_fus.step(clip_max_norm=1.0, ema=e_fus, ema_params=p_fus[::-1])
         torch.cuda.synchronize()
         assert abs(float(o_fus.last_grad_norm) - float(n_ref)) < 1e-5 * float(n_ref)
         for a, b in zip(p_ref, p_fus):
