@@ -227,11 +227,13 @@ def ray_integration(out, z, noise, noise_std, white_back, last_back, clamp_mode=
     return rgbf, depth, w
 
 
-def render(params, freq, phase, cond, cfg, u, noise):
+def render(params, freq, phase, cond, cfg, u, noise, dtype=None):
     """lib/generators/map3d_generator.py:381-523 with hierarchical_sample=False, staged=False.
 
     `u` [B,R,S,1] is the jitter draw, `noise` [B,R,S,1] the sigma-noise draw.
-    Returns rgb_render [B,3,Rh,Rw], feature_maps [B,F,Rh,Rw], depth [B,R,1], weights, nearest idx."""
+    Returns rgb_render [B,3,Rh,Rw], feature_maps [B,F,Rh,Rw], depth [B,R,1], weights, nearest idx.
+    `dtype` (tests only): evaluate the MLP and the integration in that dtype (parameters given in it); rays and geometry
+    features stay fp32, as the reference computes them (`.float()` casts at smpl.py:217,220)."""
     Rw, Rh, S = cfg["render_width"], cfg["render_height"], cfg["num_steps"]
     Fd, H = cfg["feature_dim"], cfg["hidden_dim"]
     focals = cond["intrinsics"][:, 0, 0]
@@ -248,6 +250,8 @@ def render(params, freq, phase, cond, cfg, u, noise):
         dirs = dw[:, :, None, :].expand(B, Rw * Rh, S, 3).reshape(B, -1, 3)
     geo, idx = geo_features(pw, cond["skeletons_xyz"], cond["vertices"], cond["tpose_vertices"],
                             cond["fk_matrices"], cond["lbs_weights"], cfg.get("legacy_mode", False))
+    if dtype is not None:
+        pw, geo, dirs, z, noise, freq, phase = (t.to(dtype) for t in (pw, geo, dirs, z, noise, freq, phase))
     out = siren(params, pw, freq, phase, geo, dirs, 2.0 / cfg["side_length"], H, cfg["neural_field_blocks"])
     out = out.reshape(B, Rw * Rh, S, Fd + 4)
     rgbf, depth, w = ray_integration(out, z, noise, cfg["nerf_noise"], cfg.get("white_back", False),
@@ -348,14 +352,16 @@ def synthesis_input(params, B, Hg, Wg, prefix="synthesis_input."):
     return torch.sin(F.conv2d(coords, params[prefix + "network.0.weight"], params[prefix + "network.0.bias"]))
 
 
-def generator_forward(params, z, cond, cfg, u, noise, training=True, stats_out=None):
+def generator_forward(params, z, cond, cfg, u, noise, training=True, stats_out=None, dtype=None):
     """Map3DGenerator.forward (map3d_generator.py:208-280), render + synthesis path.
 
-    Returns dict(rgbs, rgbs_render, feature_maps, depths, nearest_idx)."""
+    Returns dict(rgbs, rgbs_render, feature_maps, depths, nearest_idx).  `dtype`: see `render` (tests: an fp64 control)."""
     zz = z if cfg.get("neural_field_latent_input", True) else torch.zeros_like(z)
     freq, phase = mapping_network(params, zz)
     styles = synthesis_mapping(params, z)
-    rgb_r, fmap, depth, w, idx = render(params, freq, phase, cond, cfg, u, noise)
+    if dtype is not None:
+        styles = styles.to(dtype)
+    rgb_r, fmap, depth, w, idx = render(params, freq, phase, cond, cfg, u, noise, dtype=dtype)
     Hg, Wg = cfg["gen_height"], cfg["gen_width"]
     style = F.interpolate(fmap, (Hg, Wg), mode="bilinear")             # :244-245 (align_corners=False)
     x0 = synthesis_input(params, z.shape[0], Hg, Wg)

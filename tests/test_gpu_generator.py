@@ -171,4 +171,26 @@ def test_generator_backward_matches_oracle_autograd(port, monkeypatch):
     bad = {n: e for n, e in worst.items() if e > 0.1 and pc[n].grad.norm() > 1e-6 * max(v.grad.norm() for v in pc.values() if v.grad is not None)}
     assert not bad, sorted(bad.items(), key=lambda t: -t[1])[:8]
     med = sorted(worst.values())[len(worst) // 2]
-    assert med < 2e-2, med
+    # CONTROL (what this comparison can resolve).  The gradient of this network is ~100x more sensitive than its output:
+    # perturbing every half-block output of the ORACLE by a relative 1e-5 (8e-5 on the final image) moves ITS OWN gradients by
+    # 7.5e-3 at the median, while fp32 vs fp64 torch (1e-7 perturbations) differ by 3.5e-6.  So: perturb the oracle's forward by
+    # exactly the forward error the kernels show against it, and require the kernels' gradient error to stay within a
+    # small multiple of the gradient change that perturbation causes in the oracle itself.
+    fwd_err = float((out["rgbs"].detach().cpu() - ref["rgbs"].detach()).norm() / ref["rgbs"].detach().norm())
+    eps = max(fwd_err, 1e-6) / 8.0                       # 18 half-blocks: final error ~ 8 x the per-layer perturbation (measured)
+    gen_n = torch.Generator().manual_seed(99)
+    orig_half = port.spade_half
+    port.spade_half = lambda *a_, **k_: (lambda o: o * (1 + eps * torch.randn(o.shape, generator=gen_n)))(orig_half(*a_, **k_))
+    try:
+        pp = {n: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for n, v in params.items()}
+        refp = port.generator_forward(pp, z, cond, cfg, u, noise, training=True)
+    finally:
+        port.spade_half = orig_half
+    ((refp["rgbs"] * wgt).sum() + (refp["rgbs_render"] * wgt_r).sum()).backward()
+    ctrl = sorted(float((pp[n].grad - pc[n].grad).norm() / pc[n].grad.norm()) for n in worst if pp[n].grad is not None)
+    med_ctrl = ctrl[len(ctrl) // 2]
+    fwd_ctrl = float((refp["rgbs"].detach() - ref["rgbs"].detach()).norm() / ref["rgbs"].detach().norm())
+    print(f"gradient agreement: kernels vs oracle median {med:.2e} at forward error {fwd_err:.2e}; "
+          f"control (oracle vs its own perturbed forward, error {fwd_ctrl:.2e}) median {med_ctrl:.2e}")
+    assert med < 2e-2, (med, med_ctrl)
+    assert med < 4 * med_ctrl + 1e-3, (med, med_ctrl, fwd_err, fwd_ctrl)
