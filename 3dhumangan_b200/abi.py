@@ -78,6 +78,10 @@ SIGNATURES = {
     "hg_mt_chunk_elems": (c_int, []),
     "hg_mt_grad_norm": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "hg_mt_adam": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
+    "hg_smpl_shape_blocks": (c_int, [c_int]),
+    "hg_smpl_shape": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
+    "hg_smpl_pose": (c_int, [c_void_p, c_int, c_void_p, c_int] + [c_void_p] * 6 + [c_int, c_int, c_void_p]),
+    "hg_smpl_skin": (c_int, [c_void_p, c_long, c_void_p, c_void_p, c_int, c_void_p, c_long, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hg_spectral_entry_bytes": (c_int, []),
     "hg_spectral_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p]),
 }

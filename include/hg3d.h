@@ -253,6 +253,22 @@ int hg_spectral_entry_bytes(void);
 int hg_spectral_norm(const void* table, int count, int max_n, int max_k, float* inv_sigma, int training, float eps,
                      void* stream);
 
+/* ---- SMPL skinning in front of the path ------------------------------------------------------------------
+ * `lbs` of lib/components/smpl.py:11-107 (smplx.lbs: blend shapes, joint regression, Rodrigues, kinematic chain, skinning) and
+ * the re-skinning of SHHQDataset._preprocess_smpl_fix_body (lib/data/datasets.py:146-155).
+ * hg_smpl_shape: v_shaped [B,V,3] = v_template + shapedirs [V,3,NB] . betas [B,NB]; jpart [B, hg_smpl_shape_blocks(V), J, 3].
+ * hg_smpl_pose : pose [B,J,3] axis-angle (pose_is_rotmat 0) or [B,J,9]; joints [B,J,3], rot [B,J,9], feat [B,(J-1)*9] = R - I,
+ *                A [B,J,16] = rest-pose-relative rigid transforms (the generator's fk_matrices), joints_posed [B,J,3].
+ * hg_smpl_skin : verts = (sum_j w[v,j] A_j) [v_in + posedirs^T feat; 1]; feat / posedirs NULL = no pose blend shapes;
+ *                v_bstride / w_bstride 0 = shared by the batch. */
+int hg_smpl_shape_blocks(int V);
+int hg_smpl_shape(const float* v_template, const float* shapedirs, const float* betas, const float* j_regressor, float* v_shaped,
+                  float* jpart, int B, int V, int NB, int J, void* stream);
+int hg_smpl_pose(const float* jpart, int nblk, const float* pose, int pose_is_rotmat, const int* parents, float* joints, float* rot,
+                 float* feat, float* A, float* joints_posed, int B, int J, void* stream);
+int hg_smpl_skin(const float* v_in, long v_bstride, const float* feat, const float* posedirs, int P, const float* lbs_weights,
+                 long w_bstride, const float* A, float* verts, int B, int V, int J, void* stream);
+
 /* ---- loss + optimiser tail of a training iteration ---------------------------------------------------
  * Class-balanced segmentation cross entropy, PhaseTrainer._calculate_segmentation_loss mode 'cross_entropy_balanced'
  * (lib/trainers/phase_trainer.py:203-256): histogram of the int64 labels -> per-class coefficients (numel / (occ * n_occ) *
