@@ -91,8 +91,10 @@ def discriminator_forward(module, images, passes=None):
         H, W = x1.shape[2] * 2, x1.shape[3] * 2
         learned = (blk + ".conv_s.bias") in P
         if learned:
-            s = conv(blk + ".conv_s", x1, x2=x2, ksize=1, H=H, W=W, up2=True)
-            res_up2 = False
+            # shortcut = conv_s(up(x)) (:65-67) == up(conv_s(x)): a 1x1 convolution commutes with nearest up-sampling exactly, so it
+            # runs at the LOW resolution (a quarter of the pixels) and is up-sampled by the residual read of conv2's epilogue
+            s = conv(blk + ".conv_s", x1, x2=x2, ksize=1, H=H // 2, W=W // 2)
+            res_up2 = True
         else:
             if x2 is not None:
                 raise RuntimeError("hg3d: identity shortcut over a concatenated input does not occur in this architecture")

@@ -181,9 +181,8 @@ def discriminator_forward_train(module, images, passes=3, masks=None):
         blk = f"body_up.{i}"
         xin = x if i == 0 else torch.cat((skips[-i - 1], x), 1)
         learned = (blk + ".conv_s.bias") in P
-        s = _up(xin)
-        if learned:
-            s = conv(blk + ".conv_s", s)
+        # shortcut: conv_s(up(x)) == up(conv_s(x)) exactly (1x1 convolution, nearest up-sampling): convolve at the low resolution
+        s = _up(conv(blk + ".conv_s", xin)) if learned else _up(xin)
         dx = conv(blk + ".conv1.2", _up(_lrelu(xin, masks)))
         dx = conv(blk + ".conv2.1", _lrelu(dx, masks))
         x = s + dx

@@ -69,15 +69,15 @@ def peaks():
 
 
 def ncu_traffic(entry, workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture of the C2 workload (profiles/r1_final_ncu_summary.md); null for workloads that were not captured."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    if entry != "hg_spade_conv" or workload != "C2" or not os.path.exists(p):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the newest committed `ncu --set full`
+    capture of this workload (profiles/r2_ncu_traffic.json, written from tools/profile_r2.sh's export: the mean over the 18
+    half-block launches of one forward, all variants); null for workloads / kernels that were not captured.  (A profiler cannot
+    run inside the timed process; the capture is refreshed whenever the kernel changes.)"""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(p):
         return None
-    d = json.load(open(p))
-    # the 18 launches of a forward: 6 pixel-style + 12 const-style half-blocks (captured: one of each kind, no skip)
-    c, x = d["spade_const_kernel<3,0>"], d["spade_pixel_kernel<3>"]
-    return (12 * (c["dram_read"] + c["dram_write"]) + 6 * (x["dram_read"] + x["dram_write"])) / 18.0
+    d = json.load(open(p)).get(entry, {}).get(workload)
+    return None if d is None else d["dram_bytes_per_launch_mean_of_18"]
 
 
 def workload_cfg(pkg, name):
@@ -212,7 +212,9 @@ def kernel_costs(cfg, B):
     C = 256
     act = B * HW * C * 4
     return {
-        "hg_spade_conv": {"flops": 2.0 * B * HW * C * C, "bytes": 2.0 * act},           # read x + write out (skip/rgb extra)
+        # mean over the 18 half-block launches of a forward: read x + write out, + the residual input of the second half of blocks
+        # 4..8 (5 launches), + the 3-channel ToRGB accumulator of 6 launches (read + write)
+        "hg_spade_conv": {"flops": 2.0 * B * HW * C * C, "bytes": 2.0 * act + (5.0 / 18.0) * act + (6.0 / 18.0) * 2.0 * B * HW * 3 * 4},
         "hg_render_mlp": {"flops": 938496.0 * B * R * S, "bytes": B * R * S * (36 + 1) * 4.0 + B * R * 260 * 4.0},
         "hg_geo_features": {"flops": 8.0 * B * R * S * 6890, "bytes": B * R * S * (36 + 1 + 1) * 4.0},
     }
