@@ -338,8 +338,10 @@ int hg_conv2d(const float* x1, int C1, const float* x2, int C2, int B, int H, in
   const int nblocks = (Cout + Nb - 1) / Nb;
   HG_REQUIRE(nblocks <= 2, "hg_conv2d: at most two N blocks (Cout <= 2*Nb)");
   // tiny contractions (3-channel stem, 64 -> 27 heads): fp32 SIMT kernel, memory bound (dconv_small.cu)
-  if (small && halo_enabled())
-    return hg_conv_small_launch(x1, C1, B, H, W, up2, pre_lrelu, ksize, wimg, Cout, Nb, bias, residual, res_up2, out, stream);
+  if (small && halo_enabled()) {
+    const int rc = hg_conv_small_launch(x1, C1, B, H, W, up2, pre_lrelu, ksize, wimg, Cout, Nb, bias, residual, res_up2, out, stream);
+    if (rc >= 0) return rc;
+  }
   // 3x3 convolutions on rows of >= 128 pixels (84 % of the discriminator's FLOPs): one haloed operand tile per K chunk,
   // nine taps by descriptor offset (dconv_halo.cu)
   if (!small && halo_enabled() && hg_conv3x3_halo_eligible(C1, C2, H, W, ksize, Cout, Nb))

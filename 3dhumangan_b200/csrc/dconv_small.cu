@@ -22,15 +22,18 @@ struct SmallConvArgs {
   float* out;
 };
 
+// KS / CIN are compile-time: the (tap, channel) decomposition of k must not cost integer divisions per load
+template <int KS, int CIN>
 __global__ void __launch_bounds__(128) conv_small_kernel(SmallConvArgs a) {
-  __shared__ __align__(16) float ws[64][32];    // [k][co within the group]
+  constexpr int K = KS * KS * CIN;
+  static_assert(K <= 64, "single K chunk");
+  __shared__ __align__(16) float ws[K][32];    // [k][co within the group]
   __shared__ float bs[32];
-  const int K = a.ksize * a.ksize * a.Cin;
   const int co0 = blockIdx.y * 32;
-  for (int i = threadIdx.x; i < 64 * 32; i += 128) {
+  for (int i = threadIdx.x; i < K * 32; i += 128) {
     const int k = i >> 5, c = i & 31, n = co0 + c;
     float w = 0.f;
-    if (k < K && n < a.Cout) {
+    if (n < a.Cout) {
       const int nb = n / a.Nb, r = n % a.Nb;
       const uint8_t* hi = a.wimg + static_cast<size_t>(nb) * 2 * a.Nb * 128;
       const uint8_t* lo = hi + static_cast<size_t>(a.Nb) * 128;
@@ -43,36 +46,36 @@ __global__ void __launch_bounds__(128) conv_small_kernel(SmallConvArgs a) {
   if (threadIdx.x < 32) bs[threadIdx.x] = (a.bias && co0 + threadIdx.x < a.Cout) ? a.bias[co0 + threadIdx.x] : 0.f;
   __syncthreads();
   const long HW = static_cast<long>(a.H) * a.W;
-  const long pix = static_cast<long>(blockIdx.x) * 128 + threadIdx.x;
-  if (pix >= a.B * HW) return;
+  const long npix = static_cast<long>(a.B) * HW;
+  // persistent over pixel blocks: the weights of the channel group are staged once per CTA, not once per 128 pixels
+  for (long pix = static_cast<long>(blockIdx.x) * 128 + threadIdx.x; pix < npix; pix += static_cast<long>(gridDim.x) * 128) {
   const int b = static_cast<int>(pix / HW);
   const long q = pix - b * HW;
   const int py = static_cast<int>(q / a.W), px = static_cast<int>(q - static_cast<long>(py) * a.W);
   const int Hs = a.up2 ? a.H >> 1 : a.H, Ws = a.up2 ? a.W >> 1 : a.W;
   const long HWs = static_cast<long>(Hs) * Ws;
-  const float* xb = a.x + static_cast<long>(b) * a.Cin * HWs;
-  float v[64];
-  const int pad = a.ksize >> 1;
+  const float* xb = a.x + static_cast<long>(b) * CIN * HWs;
+  float v[K];
+  constexpr int pad = KS >> 1;
 #pragma unroll
-  for (int k = 0; k < 64; ++k) {
-    float val = 0.f;
-    if (k < K) {
-      const int tap = k / a.Cin, c = k - tap * a.Cin;
-      int sy = py + tap / a.ksize - pad, sx = px + tap % a.ksize - pad;
-      if (sy >= 0 && sy < a.H && sx >= 0 && sx < a.W) {
-        if (a.up2) { sy >>= 1; sx >>= 1; }
-        val = __ldg(xb + c * HWs + static_cast<long>(sy) * Ws + sx);
-        if (a.pre_lrelu) val = val > 0.f ? val : 0.2f * val;
-      }
+  for (int tap = 0; tap < KS * KS; ++tap) {
+    int sy = py + tap / KS - pad, sx = px + tap % KS - pad;
+    const bool in = sy >= 0 && sy < a.H && sx >= 0 && sx < a.W;
+    if (a.up2) { sy >>= 1; sx >>= 1; }
+    const float* src = xb + static_cast<long>(sy) * Ws + sx;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      float val = in ? __ldg(src + c * HWs) : 0.f;
+      if (a.pre_lrelu) val = val > 0.f ? val : 0.2f * val;
+      v[tap * CIN + c] = val;
     }
-    v[k] = val;
   }
   float acc[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) acc[c] = bs[c];
 #pragma unroll
-  for (int k = 0; k < 64; ++k) {
-    if (k < K) {
+  for (int k = 0; k < K; ++k) {
+    {
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
         const float4 w = *reinterpret_cast<const float4*>(&ws[k][c4 * 4]);
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(128) conv_small_kernel(SmallConvArgs a) {
       a.out[(static_cast<long>(b) * a.Cout + n) * HW + q] = o;
     }
   }
+  }
 }
 
 }  // namespace hg
@@ -103,7 +107,14 @@ int hg_conv_small_launch(const float* x, int Cin, int B, int H, int W, int up2, 
                          int Nb, const float* bias, const float* residual, int res_up2, float* out, void* stream) {
   hg::SmallConvArgs a{x, Cin, B, H, W, up2, pre_lrelu, ksize, static_cast<const uint8_t*>(wimg), Cout, Nb, bias, residual, res_up2, out};
   const long pixels = static_cast<long>(B) * H * W;
-  dim3 grid(static_cast<unsigned>((pixels + 127) / 128), static_cast<unsigned>((Cout + 31) / 32));
-  hg::conv_small_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  const unsigned groups = static_cast<unsigned>((Cout + 31) / 32);
+  const long blocks = (pixels + 127) / 128;
+  const long per_group = (static_cast<long>(hg::num_sms()) * 8 + groups - 1) / groups;      // ~8 resident CTAs per SM in total
+  dim3 grid(static_cast<unsigned>(blocks < per_group ? blocks : per_group), groups);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ksize == 3 && Cin == 3) hg::conv_small_kernel<3, 3><<<grid, 128, 0, st>>>(a);
+  else if (ksize == 1 && Cin == 3) hg::conv_small_kernel<1, 3><<<grid, 128, 0, st>>>(a);
+  else if (ksize == 1 && Cin == 64) hg::conv_small_kernel<1, 64><<<grid, 128, 0, st>>>(a);
+  else return -1;      // not a compiled shape: the caller falls back to the tensor-core kernel
   return hg::check_launch("hg_conv2d (small contraction)");
 }
