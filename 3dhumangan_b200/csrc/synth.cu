@@ -312,9 +312,15 @@ __device__ __forceinline__ void take_x_pair(const SynSmem& m, uint32_t& xg, int 
 
 // ------------------------------------------------------------------------------------------
 // warps 8-11: epilogue team (identical for both variants): tile `it` lives in TMEM half it&1.
+// The four epilogue warps -- one per scheduler, each a single instruction stream -- are the critical path of these
+// kernels (ncu: never waiting, ~5 cycles per instruction), so the per-element work is straight-line code: residual /
+// ToRGB / statistics are compile-time variants and rows past the image are handled by one warp-uniform branch per
+// 32-column group (with run-time flags inside the unrolled loop the plain half-block spent 391 instructions per group,
+// 45 % of them selects, zero-adds, register clears and branches).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const SynSmem& m, const TileMap& tm, uint32_t tmem,
-                                                   int q, int lane) {
+template <bool kSkip, bool kRgb, bool kStats>
+__device__ __forceinline__ void epilogue_team_variant(const SpadeArgs& a, const SynSmem& m, const TileMap& tm, uint32_t tmem,
+                                                      int q, int lane) {
   const int row = q * 32 + lane;
   uint32_t sg = 0;   // residual slices consumed
   uint32_t tbias = smem_u32(m.tab_bias), trgb = smem_u32(m.tab_rgbw);   // constant tables, written before init's barrier
@@ -323,24 +329,26 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
   // without a residual the 2 residual staging slots (32 KB) are free: per-warp [32][33] transpose scratch for the
   // statistics (32 STS + 32 LDS + 64 FP instead of a 248-instruction shuffle tree)
   const uint32_t scratch = smem_u32(m.x_st + kXs * (kXSlice / 4) + q * (32 * 33));
+  const int HW = a.HW, cout = a.cout, ncg = a.cout >> 5;
+  float* const outp = a.out;
   for (int it = 0; it < tm.count; ++it) {
     int b, ti;
     tm.get(it, b, ti);
     const uint32_t buf = it & 1;
     const int pix = ti * 128 + row;
-    const bool valid = pix < a.HW;
-    const long plane = (static_cast<long>(b) * tm.T + ti) * a.cout * 128 + row;
+    const bool valid = pix < HW;
+    const bool full = ti * 128 + 128 <= HW;      // warp-uniform: every row of the tile is a pixel
+    float* const orow = outp + (static_cast<long>(b) * tm.T + ti) * cout * 128 + row;
     mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
     tc_fence_after();
     float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-    const int ncg = a.cout >> 5;
 #pragma unroll 1
     for (int cg = 0; cg < ncg; ++cg) {
       const int c0 = cg * 32;
       uint32_t raw[32];
       tmem_ld32(tmem + buf * 256 + (static_cast<uint32_t>(q * 32) << 16) + c0, raw);
       float sk[32];
-      if (a.skip) {
+      if (kSkip) {
         const uint32_t sslot = kXs + sg % kSs;
         mbar_wait_sleep(m.bars + X_FULL + sslot, (sg / kSs) & 1);
         const uint32_t xs = smem_u32(m.x_st + sslot * (kXSlice / 4)) + row * 4;
@@ -349,9 +357,6 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
         __syncwarp();
         if (lane == 0) mbar_arrive(m.bars + X_EMPTY + sslot);
         ++sg;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sk[j] = 0.f;
       }
       tmem_ld_wait();
       float v[32];
@@ -362,11 +367,24 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int j = g * 8 + jj;
-          float o = __uint_as_float(raw[j]) + bs[jj] + sk[j];
-          if (valid) a.out[plane + (c0 + j) * 128] = o;
-          v[j] = valid ? o : 0.f;
+          v[j] = __uint_as_float(raw[j]) + bs[jj];
+          if (kSkip) v[j] += sk[j];
         }
-        if (a.rgb_w) {
+      }
+      float* const o = orow + c0 * 128;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j * 128] = v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (valid) o[j * 128] = v[j];
+          else v[j] = 0.f;
+        }
+      }
+      if (kRgb) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
           float w0[8], w1[8], w2[8];
           lds8(trgb + (c0 + g * 8) * 4, w0);
           lds8(trgb + (kC + c0 + g * 8) * 4, w1);
@@ -379,9 +397,9 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
           }
         }
       }
-      if (a.stats) {
+      if (kStats) {
         float t1, t2;
-        if (a.skip) {
+        if (kSkip) {
           float s2[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) s2[j] = v[j] * v[j];
@@ -392,14 +410,18 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
 #pragma unroll
           for (int j = 0; j < 32; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + (lane * 33 + j) * 4), "f"(v[j]) : "memory");
           __syncwarp();
-          t1 = 0.f;
-          t2 = 0.f;
+          float ta = 0.f, tb = 0.f, qa = 0.f, qb = 0.f;      // two chains each: the loop is latency bound on one
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const float x = lds_f32(scratch + (r * 33 + lane) * 4);
-            t1 += x;
-            t2 = fmaf(x, x, t2);
+          for (int r = 0; r < 32; r += 2) {
+            const float x0 = lds_f32(scratch + (r * 33 + lane) * 4);
+            const float x1 = lds_f32(scratch + ((r + 1) * 33 + lane) * 4);
+            ta += x0;
+            tb += x1;
+            qa = fmaf(x0, x0, qa);
+            qb = fmaf(x1, x1, qb);
           }
+          t1 = ta + tb;
+          t2 = qa + qb;
         }
         atomicAdd(m.st_sum + c0 + lane, t1);
         atomicAdd(m.st_sq + c0 + lane, t2);
@@ -408,11 +430,11 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(m.bars + ACC_EMPTY + buf);
-    if (a.rgb_w && valid) {   // this thread saw all 256 channels of its pixel
+    if (kRgb && valid) {   // this thread saw all 256 channels of its pixel
       const float r[3] = {r0, r1, r2};
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const long idx = (static_cast<long>(b) * 3 + j) * a.HW + pix;
+        const long idx = (static_cast<long>(b) * 3 + j) * HW + pix;
         float o = r[j] + a.rgb_b[j];
         if (a.rgb_in) o += a.rgb_in[idx];
         a.rgb_out[idx] = o;
@@ -420,11 +442,27 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
     }
   }
   asm volatile("bar.sync 2, 128;" ::: "memory");
-  if (a.stats) {
+  if (kStats) {
     for (int c = threadIdx.x - 256; c < kC; c += 128) {
       atomicAdd(a.stats + c, static_cast<double>(m.st_sum[c]));
       atomicAdd(a.stats + kC + c, static_cast<double>(m.st_sq[c]));
     }
+  }
+}
+
+// warp-uniform dispatch on the launch's flags
+__device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const SynSmem& m, const TileMap& tm, uint32_t tmem,
+                                                   int q, int lane) {
+  const int sel = (a.skip ? 4 : 0) | (a.rgb_w ? 2 : 0) | (a.stats ? 1 : 0);
+  switch (sel) {
+    case 0: epilogue_team_variant<false, false, false>(a, m, tm, tmem, q, lane); break;
+    case 1: epilogue_team_variant<false, false, true>(a, m, tm, tmem, q, lane); break;
+    case 2: epilogue_team_variant<false, true, false>(a, m, tm, tmem, q, lane); break;
+    case 3: epilogue_team_variant<false, true, true>(a, m, tm, tmem, q, lane); break;
+    case 4: epilogue_team_variant<true, false, false>(a, m, tm, tmem, q, lane); break;
+    case 5: epilogue_team_variant<true, false, true>(a, m, tm, tmem, q, lane); break;
+    case 6: epilogue_team_variant<true, true, false>(a, m, tm, tmem, q, lane); break;
+    default: epilogue_team_variant<true, true, true>(a, m, tm, tmem, q, lane); break;
   }
 }
 
@@ -436,23 +474,35 @@ __device__ __forceinline__ void epilogue_team_loop(const SpadeArgs& a, const Syn
 //     dpre = dL/dy * lrelu'(pre)           -> stored (tile-blocked, like every activation)
 //     S1[b,c] += dpre,  S2[b,c] += dpre*x  -> everything BatchNorm / gamma / beta need (DESIGN.md "Backward")
 // ------------------------------------------------------------------------------------------
+// Compile-time variants (the per-element work must be straight-line code: with run-time flags inside the 32-wide unrolled
+// loop the compiler emitted ~4 branches, 4 address LEAs and several constant reloads per element, and the four epilogue
+// warps -- one instruction stream per scheduler -- became the critical path of the kernel at 5.7 cycles per instruction):
+//   kSine  activation derivative cos(pre) (FiLM-SIREN) instead of the LeakyReLU / ReLU mask
+//   kRk    rank-3 term from the renderer's heads (rows beyond rk_n of the [3,C] weight table are zero)
+//   kPm    pixel-major [B,HW,cout] output
+template <bool kSine, bool kRk, bool kPm>
 __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynSmem& m, const TileMap& tm, uint32_t tmem,
                                                   int q, int lane) {
   const int row = q * 32 + lane;
   const int et = threadIdx.x - 256;   // 0..127 within the epilogue team
   uint32_t sg = 0;
   int cur_b = -1;
+  const int cout = a.cout;
+  double* const stats = a.stats;
   auto flush = [&](int b) {
-    for (int c = et; c < a.cout; c += 128) {
-      atomicAdd(a.stats + (static_cast<long>(b) * 2 + 0) * a.cout + c, static_cast<double>(m.st_sum[c]));
-      atomicAdd(a.stats + (static_cast<long>(b) * 2 + 1) * a.cout + c, static_cast<double>(m.st_sq[c]));
+    for (int c = et; c < cout; c += 128) {
+      atomicAdd(stats + (static_cast<long>(b) * 2 + 0) * cout + c, static_cast<double>(m.st_sum[c]));
+      atomicAdd(stats + (static_cast<long>(b) * 2 + 1) * cout + c, static_cast<double>(m.st_sq[c]));
       m.st_sum[c] = 0.f;
       m.st_sq[c] = 0.f;
     }
   };
   const float mslope = a.slope;
-  const int ncg = a.cout >> 5;
-  const bool sine = a.act == 1;
+  const int ncg = cout >> 5;
+  const int HW = a.HW, rk_n = a.rk_n;
+  const float* const modp = a.mod;
+  const float* const rkv = a.rk_v;
+  float* const outp = a.out;
   uint32_t trk = smem_u32(m.tab_rgbw);     // rank-k weights (loaded by init_common through a.rgb_w)
   opaque(trk);
   for (int it = 0; it < tm.count; ++it) {
@@ -461,9 +511,9 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
     if (b != cur_b) {   // per-sample tables and per-sample sums
       asm volatile("bar.sync 2, 128;" ::: "memory");
       if (cur_b >= 0) flush(cur_b);
-      for (int c = et; c < a.cout; c += 128) {
-        m.tab_g1[c] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 0) * a.cout + c] : 1.f;
-        m.tab_g0[c] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 1) * a.cout + c] : 0.f;
+      for (int c = et; c < cout; c += 128) {
+        m.tab_g1[c] = modp ? modp[(static_cast<long>(b) * 2 + 0) * cout + c] : 1.f;
+        m.tab_g0[c] = modp ? modp[(static_cast<long>(b) * 2 + 1) * cout + c] : 0.f;
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
       cur_b = b;
@@ -472,12 +522,16 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
     opaque(tg1);   // no table load may move above the refresh
     opaque(tg0);
     const uint32_t buf = it & 1;
-    const bool valid = ti * 128 + row < a.HW;
-    const long plane = a.out_pm ? (static_cast<long>(b) * a.HW + ti * 128 + row) * a.cout
-                                : (static_cast<long>(b) * tm.T + ti) * a.cout * 128 + row;
-    float rv[3] = {0.f, 0.f, 0.f};
-    if (a.rk_v && valid)
-      for (int j = 0; j < a.rk_n; ++j) rv[j] = a.rk_v[(static_cast<long>(b) * a.rk_n + j) * a.HW + ti * 128 + row];
+    const bool valid = ti * 128 + row < HW;
+    float* const orow = kPm ? outp + (static_cast<long>(b) * HW + ti * 128 + row) * cout
+                            : outp + (static_cast<long>(b) * tm.T + ti) * cout * 128 + row;
+    float rv0 = 0.f, rv1 = 0.f, rv2 = 0.f;
+    if (kRk && valid) {
+      const float* r = rkv + static_cast<long>(b) * rk_n * HW + ti * 128 + row;
+      rv0 = r[0];
+      if (rk_n > 1) rv1 = r[HW];
+      if (rk_n > 2) rv2 = r[2 * static_cast<long>(HW)];
+    }
     mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
     tc_fence_after();
 #pragma unroll 1
@@ -496,35 +550,39 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
         if (lane == 0) mbar_arrive(m.bars + X_EMPTY + sslot);
         ++sg;
       }
+      if (!valid) {      // rows past the image (last, partial tile only): the staged slice holds whatever the padding holds
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xs_[j] = 0.f;
+      }
       tmem_ld_wait();
       float v[32], w[32];
+      float* const o = kPm ? orow + c0 : orow + c0 * 128;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float t1[8], t0[8];
+        float t1[8], t0[8], k0[8], k1[8], k2[8];
         lds8(tg1 + (c0 + g * 8) * 4, t1);
         lds8(tg0 + (c0 + g * 8) * 4, t0);
+        if (kRk) {
+          lds8(trk + (c0 + g * 8) * 4, k0);
+          lds8(trk + (kC + c0 + g * 8) * 4, k1);
+          lds8(trk + (2 * kC + c0 + g * 8) * 4, k2);
+        }
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int j = g * 8 + jj;
           const float pre = fmaf(xs_[j], t1[jj], t0[jj]);
-          float acc = __uint_as_float(raw[j]);
-          if (a.rk_v) {
-            acc = fmaf(rv[0], lds_f32(trk + (c0 + j) * 4), acc);
-            if (a.rk_n > 1) {
-              acc = fmaf(rv[1], lds_f32(trk + (kC + c0 + j) * 4), acc);
-              acc = fmaf(rv[2], lds_f32(trk + (2 * kC + c0 + j) * 4), acc);
-            }
-          }
-          const float d = acc * (sine ? cos_red(pre) : (pre > 0.f ? 1.f : mslope));
-          if (valid && !a.out_pm) a.out[plane + (c0 + j) * 128] = d;
-          v[j] = valid ? d : 0.f;
-          w[j] = v[j] * xs_[j];
+          float acc = __uint_as_float(raw[j]);      // 0 for rows past the image (their operand rows are zero)
+          if (kRk) acc = fmaf(rv2, k2[jj], fmaf(rv1, k1[jj], fmaf(rv0, k0[jj], acc)));
+          const float d = acc * (kSine ? cos_red(pre) : (pre > 0.f ? 1.f : mslope));
+          if (!kPm && valid) o[j * 128] = d;
+          v[j] = d;
+          w[j] = d * xs_[j];
         }
       }
-      if (valid && a.out_pm) {
-        float4* o = reinterpret_cast<float4*>(a.out + plane + c0);
+      if (kPm && valid) {
+        float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
       const float s1 = transpose_reduce32(v, lane);
       const float s2 = transpose_reduce32(w, lane);
@@ -632,8 +690,17 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
       }
     }
   } else if (warp < 12) {
-    if (kBwd) epilogue_bwd_loop(a, m, tm, tmem, warp - 8, lane);
-    else epilogue_team_loop(a, m, tm, tmem, warp - 8, lane);
+    if (kBwd) {      // warp-uniform dispatch to a straight-line variant (the host side rejects the other combinations)
+      if (a.act == 1) {
+        if (a.rk_v) epilogue_bwd_loop<true, true, false>(a, m, tm, tmem, warp - 8, lane);
+        else epilogue_bwd_loop<true, false, false>(a, m, tm, tmem, warp - 8, lane);
+      } else {
+        if (a.out_pm) epilogue_bwd_loop<false, false, true>(a, m, tm, tmem, warp - 8, lane);
+        else epilogue_bwd_loop<false, false, false>(a, m, tm, tmem, warp - 8, lane);
+      }
+    } else {
+      epilogue_team_loop(a, m, tm, tmem, warp - 8, lane);
+    }
   } else if (warp == 12) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 256);
@@ -1100,6 +1167,8 @@ int hg_conv1x1_blocked_bwd(const float* g, const float* g2, const float* aux, co
   HG_REQUIRE(g && aux && wimg_t && out && sums, "hg_conv1x1_blocked_bwd: null pointer");
   HG_REQUIRE(Cout == 128 || Cout == 256, "hg_conv1x1_blocked_bwd: Cout must be 128 or 256 (got %d)", Cout);
   HG_REQUIRE(!pixel_major || Cout == 128, "hg_conv1x1_blocked_bwd: the pixel-major output is built for Cout == 128");
+  HG_REQUIRE(!(act == 1 && pixel_major) && !(act == 0 && rk_v),
+             "hg_conv1x1_blocked_bwd: compiled epilogues are sine [+ rank-k term] / LeakyReLU [+ pixel-major output]");
   HG_REQUIRE(passes == 1 || passes == 3, "hg_conv1x1_blocked_bwd: passes must be 1 or 3");
   HG_REQUIRE(B > 0 && Hg > 0 && Wg > 0, "hg_conv1x1_blocked_bwd: bad shape");
   const long T = (Hg * Wg + 127) / 128;

@@ -545,6 +545,7 @@ def train_leg(args, pkg, dev, rank, world, B, steps, warm, precision, split):
         loss_h.copy_(torch.stack([d.float(), torch.as_tensor(g, device=dev).float()]), non_blocking=True)
 
     per_iter = []
+    host_ms = []          # host time spent enqueueing an iteration (no synchronisation inside): ~ the GPU time => launch bound
 
     def timed(fn, n, record=False):
         if world > 1:
@@ -554,9 +555,11 @@ def train_leg(args, pkg, dev, rank, world, B, steps, warm, precision, split):
         ev[0].record()
         for i in range(n):
             r1 = bool(cfg["phases"][D.step % len(cfg["phases"])]["do_r1"])
+            t0 = time.perf_counter()
             fn()
             ev[i + 1].record()
             if record:
+                host_ms.append((time.perf_counter() - t0) * 1e3)
                 per_iter.append([r1, ev[i], ev[i + 1]])
         if world > 1:
             dist.barrier()
@@ -617,7 +620,8 @@ def train_leg(args, pkg, dev, rank, world, B, steps, warm, precision, split):
         "iteration_ms": {"do_r1": (sum(ms_r1) / len(ms_r1)) if ms_r1 else None,
                          "plain": (sum(ms_plain) / len(ms_plain)) if ms_plain else None,
                          "r1_iterations_timed": len(ms_r1), "plain_iterations_timed": len(ms_plain),
-                         "schedule": "do_r1 on 2 of 8 phases (configs/map3d.py:104-113)"},
+                         "schedule": "do_r1 on 2 of 8 phases (configs/map3d.py:104-113)",
+                         "host_enqueue_ms": sum(host_ms) / max(1, len(host_ms))},
         "roofline": {"bound": "tensor", "achieved": eq_tflops / world, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": eq_tflops / world / pk["bf16_tflops_sustained"], "traffic": None,
                      "note": "reference-equivalent FLOPs of the whole iteration (10.8 TFLOP/image, SURVEY.md 8d) per GPU vs the "
