@@ -112,9 +112,10 @@ def check(rc: int, what: str):
 
 LAUNCHES = 0        # kernels launched through this binding (bench.py reports it as gpu_launches)
 TIMING = None       # when a list: (name, start_event, end_event) per launch, recorded on the current stream
+TIMING_TAGS = False # tools: record "name[tag]" (layer shapes) instead of the bare entry-point name
 
 
-def call(name, *args):
+def call(name, *args, tag=None):
     """Invoke one launching entry point: count it, optionally bracket it with CUDA events, raise on error."""
     global LAUNCHES
     fn = getattr(lib(), name)
@@ -123,7 +124,7 @@ def call(name, *args):
         s.record()
         rc = fn(*args)
         e.record()
-        TIMING.append((name, s, e))
+        TIMING.append((f"{name}[{tag}]" if TIMING_TAGS and tag else name, s, e))
     else:
         rc = fn(*args)
     LAUNCHES += 1
@@ -458,7 +459,8 @@ def conv2d(x1, wimg, Cout, Nb, *, ksize, H, W, x2=None, up2=False, pre_lrelu=Fal
         out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x1.device)
     with torch.cuda.device_of(x1):
         call("hg_conv2d", ptr(x1), C1, ptr(x2), C2, B, H, W, int(bool(up2)), int(bool(pre_lrelu)), ksize, ptr(wimg), Cout, Nb,
-             ptr(bias), ptr(residual), int(bool(res_up2)), ptr(out), passes, stream())
+             ptr(bias), ptr(residual), int(bool(res_up2)), ptr(out), passes, stream(),
+             tag=f"{C1}+{C2}->{Cout} k{ksize} {H}x{W} B{B}{' up' if up2 else ''}" if TIMING_TAGS else None)
     return out
 
 
@@ -493,7 +495,8 @@ def _conv3x3_wgrad_halo(dy, x, passes):
                 dbt = torch.empty(128, dtype=torch.float32, device=dev) if first else None
                 with torch.cuda.device_of(dy):
                     call("hg_conv3x3_wgrad_halo", ptr(dy), ptr(x), ptr(dw), ptr(dbt), ptr(ws), B, H, W, Cout, Cin, co0, nco, ci0, nci,
-                         n, ctypes.cast(tdy, c_void_p), ctypes.cast(tdx, c_void_p), passes, stream())
+                         n, ctypes.cast(tdy, c_void_p), ctypes.cast(tdx, c_void_p), passes, stream(),
+                         tag=f"{Cin}->{Cout} {H}x{W} B{B}" if TIMING_TAGS else None)
                 dW[co0:co0 + nco, ci0:ci0 + nci, taps[0]:taps[-1] + 1] = dw[:, :nco, :nci].permute(1, 2, 0)
                 if first:
                     db[co0:co0 + nco] = dbt[:nco]
@@ -534,7 +537,8 @@ def conv2d_wgrad(dy, x, ksize, passes=3):
                 dbt = torch.empty(256, dtype=torch.float32, device=dev) if first else None
                 with torch.cuda.device_of(dy):
                     call("hg_conv2d_wgrad_taps", ptr(dy), ptr(x), ptr(dw), ptr(dbt), ptr(ws), B, H, W, Cout, Cin, co0, nco,
-                         ci0, nci, n, ctypes.cast(oy, c_void_p), ctypes.cast(ox, c_void_p), passes, stream())
+                         ci0, nci, n, ctypes.cast(oy, c_void_p), ctypes.cast(ox, c_void_p), passes, stream(),
+                         tag=f"{Cin}->{Cout} k{ksize} {H}x{W} B{B}" if TIMING_TAGS else None)
                 for i, (ky, kx) in enumerate(grp):
                     dW[co0:co0 + nco, ci0:ci0 + nci, ky, kx] = dw[i, :nco, :nci]
                 if first:

@@ -1,7 +1,11 @@
 // bias_act and upfirdn2d: the two StyleGAN3 native ops the reference ships as CUDA plugins
 // (lib/components/ops/bias_act.cu:24-165, lib/components/ops/upfirdn2d.cu:29-375), rebuilt as
 // vectorised HBM-streaming kernels for sm_100a.  Both are bandwidth-bound (<= 10 FLOP/B).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <string.h>
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace hg {
 
@@ -205,16 +209,30 @@ __global__ void __launch_bounds__(128) upfirdn2d_kernel(const float* __restrict_
 //   down: y[o] = sum_k g[k] * x[2o + k - pad0]
 // g = filter flipped unless flip_filter (upfirdn2d.py:200-203), times sqrt(gain) per axis.
 // ---------------------------------------------------------------------------------------------------------------------
+//
+// Round-2 tuning (ncu: the first version was issue bound at 44 thread-instructions per output, 22 % of them FMAs):
+//   * staging is ONE cp.async.bulk.tensor (TMA, 3-D box [1, TIH, PIN] of the [planes, H, W] tensor, out-of-bounds = zero fill =
+//     the padding) per tile instead of ~1 500 4-byte cp.async with their bounds checks (used when W % 4 == 0 and x is
+//     16-byte aligned; the cp.async path is kept for everything else);
+//   * the vertical pass runs on column PAIRS with FFMA2 (sm_100 packed fp32): half the FMA instructions;
+//   * a horizontal item makes 8 outputs from float4-aligned window reads, so its index arithmetic is amortised twice as far.
 template <int T, bool kUp>
 struct SepGeom {
   static constexpr int TOW = 64;
   static constexpr int TOH = kUp ? 64 : 32;
   static constexpr int NV = kUp ? T / 2 + 2 : T + 6;                 // register window for 4 outputs
+  static constexpr int NV8 = kUp ? T / 2 + 4 : T + 14;               // ... for 8 outputs
+  static constexpr int NVR = (NV8 + 3 + 3) & ~3;                      // read as float4, from up to 3 columns before the window
+  static constexpr int NV2 = T + 2;                                   // down, 2 outputs (vertical pass)
   static constexpr int TIW = kUp ? TOW / 2 + T / 2 + 1 : 2 * TOW + T - 2;
   static constexpr int TIH = kUp ? TOH / 2 + T / 2 + 1 : 2 * TOH + T - 2;
-  static constexpr int PIN = (TIW + 3) & ~3;                          // multiples of 4: 16-byte row segments stay aligned
+  // staged row: the tile may start up to 3 columns early (a TMA box must start on a 16-byte boundary of the row:
+  // tools/experiments/tma_probe.cu -- an unaligned innermost coordinate is an illegal-instruction fault)
+  static constexpr int PIN = (TIW + 3 + 3) & ~3;
   static constexpr int PMID = TOW + 4;
-  static constexpr int SMEM = (2 * TIH * PIN + TIH * PMID + T) * 4;     // input tile double-buffered (cp.async prefetch)
+  static constexpr int IN_BYTES = TIH * PIN * 4;
+  static constexpr int IN_STRIDE = (IN_BYTES + 127) & ~127;           // TMA destinations are 128-byte aligned
+  static constexpr int SMEM = 2 * IN_STRIDE + (TIH * PMID + T) * 4 + 16 + 128;   // input tile double-buffered
 };
 
 // first input index touched by output o (floor semantics for negative values)
@@ -224,11 +242,11 @@ __device__ __forceinline__ int sep_first(int o, int pad0) {
   return 2 * o - pad0;
 }
 
-// 4 outputs from a register window v[]; `odd` = parity of (o0 - pad0) (up only)
-template <int T, bool kUp>
-__device__ __forceinline__ void sep_fir4(const float* __restrict__ v, const float* __restrict__ g, bool odd, float (&o)[4]) {
+// NQ (4, or 2 for down) outputs from a register window v[]; `odd` = parity of (o0 - pad0) (up only)
+template <int T, bool kUp, int NQ = 4>
+__device__ __forceinline__ void sep_fir4(const float* __restrict__ v, const float* __restrict__ g, bool odd, float (&o)[NQ]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) o[q] = 0.f;
+  for (int q = 0; q < NQ; ++q) o[q] = 0.f;
   if (kUp) {
     // c = o - pad0.  c even: e = 0, start (c/2 - b);  c odd: e = 1, start ((c+1)/2 - b);  b = ceil(c0 / 2)
     if (!odd) {       // c0 even: b = c0/2; q=0: e0 s0 | q=1: e1 s1 | q=2: e0 s1 | q=3: e1 s2
@@ -252,150 +270,256 @@ __device__ __forceinline__ void sep_fir4(const float* __restrict__ v, const floa
 #pragma unroll
     for (int k = 0; k < T; ++k) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o[q] = fmaf(g[k], v[2 * q + k], o[q]);
+      for (int q = 0; q < NQ; ++q) o[q] = fmaf(g[k], v[2 * q + k], o[q]);
     }
   }
 }
 
-template <int T, bool kUp>
-__global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restrict__ x, const float* __restrict__ f,
-                                                            float* __restrict__ y, int inH, int inW, int outH, int outW,
-                                                            int padx0, int pady0, int flip, float gain_axis, int tiles_x,
-                                                            int tiles_y, long nplanes) {
-  using G = SepGeom<T, kUp>;
-  extern __shared__ __align__(16) float sep_smem[];
-  float* in_buf = sep_smem;                          // [2][TIH][PIN]
-  float* mid = in_buf + 2 * G::TIH * G::PIN;         // [TIH][PMID]
-  float* gs = mid + G::TIH * G::PMID;                // [T]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < T) gs[tid] = (flip ? f[tid] : f[T - 1 - tid]) * gain_axis;
-  const long ntiles = static_cast<long>(nplanes) * tiles_x * tiles_y;
-  // ---- (1) stage an input tile with 4-byte cp.async (zero fill = padding, incl. the pitch tail): a warp walks rows, lanes
-  //      walk columns (coalesced).  The NEXT tile is prefetched while this one is filtered and stored.
-  auto prefetch = [&](long tile, float* dst) {
-    const int tx = static_cast<int>(tile % tiles_x), ty = static_cast<int>((tile / tiles_x) % tiles_y);
-    const long plane = tile / (static_cast<long>(tiles_x) * tiles_y);
-    const int ix0 = sep_first<kUp>(tx * G::TOW, padx0), iy0 = sep_first<kUp>(ty * G::TOH, pady0);
-    const float* xp = x + plane * inH * inW;
-    for (int r = warp; r < G::TIH; r += 8) {
-      const int gy = iy0 + r;
-      const bool rowok = gy >= 0 && gy < inH;
-      const float* src = xp + static_cast<long>(rowok ? gy : 0) * inW;
+// the same on two adjacent columns at once (FFMA2): v[j] = (column c, column c+1) of window row j
+template <int T, bool kUp, int NQ>
+__device__ __forceinline__ void sep_fir_pair(const float2* __restrict__ v, const float* __restrict__ g, bool odd, float2 (&o)[NQ]) {
 #pragma unroll
-      for (int c0 = 0; c0 < G::PIN; c0 += 32) {
-        const int c = c0 + lane;
-        if (c < G::PIN) {
-          const int gx = ix0 + c;
-          const bool ok = rowok && c < G::TIW && gx >= 0 && gx < inW;
-          const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * G::PIN + c));
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
-        }
+  for (int q = 0; q < NQ; ++q) o[q] = make_float2(0.f, 0.f);
+  if (kUp) {
+    if (!odd) {
+#pragma unroll
+      for (int t = 0; t < T / 2; ++t) {
+        const float2 ge = make_float2(g[2 * t], g[2 * t]), go = make_float2(g[2 * t + 1], g[2 * t + 1]);
+        o[0] = __ffma2_rn(ge, v[t], o[0]);
+        o[1] = __ffma2_rn(go, v[t + 1], o[1]);
+        o[2] = __ffma2_rn(ge, v[t + 1], o[2]);
+        o[3] = __ffma2_rn(go, v[t + 2], o[3]);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < T / 2; ++t) {
+        const float2 ge = make_float2(g[2 * t], g[2 * t]), go = make_float2(g[2 * t + 1], g[2 * t + 1]);
+        o[0] = __ffma2_rn(go, v[t], o[0]);
+        o[1] = __ffma2_rn(ge, v[t], o[1]);
+        o[2] = __ffma2_rn(go, v[t + 1], o[2]);
+        o[3] = __ffma2_rn(ge, v[t + 1], o[3]);
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+      const float2 gk = make_float2(g[k], g[k]);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) o[q] = __ffma2_rn(gk, v[2 * q + k], o[q]);
+    }
+  }
+}
+
+template <int T, bool kUp, int SH>
+__device__ __forceinline__ void sep_hpass(const float* __restrict__ in_s, float* __restrict__ mid, const float (&g)[T], bool oddx, int tid) {
+  using G = SepGeom<T, kUp>;
+  constexpr int NW = (G::NV8 + SH + 3) & ~3;
+  static_assert((kUp ? 4 : 16) * (G::TOW / 8 - 1) + NW <= G::PIN, "an 8-output window leaves the staged row");
+  for (int i = tid; i < G::TIH * (G::TOW / 8); i += 256) {
+    const int a = i & (G::TOW / 8 - 1), r = i / (G::TOW / 8);
+    const float* wsrc = in_s + r * G::PIN + (kUp ? 4 * a : 16 * a);
+    float w[NW];
+#pragma unroll
+    for (int j = 0; j < NW / 4; ++j) {
+      const float4 t4 = *reinterpret_cast<const float4*>(wsrc + 4 * j);
+      w[4 * j] = t4.x; w[4 * j + 1] = t4.y; w[4 * j + 2] = t4.z; w[4 * j + 3] = t4.w;
+    }
+    float o0[4], o1[4];
+    sep_fir4<T, kUp>(w + SH, g, oddx, o0);
+    sep_fir4<T, kUp>(w + SH + (kUp ? 2 : 8), g, oddx, o1);
+    float4* m4 = reinterpret_cast<float4*>(mid + r * G::PMID + 8 * a);
+    m4[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
+    m4[1] = make_float4(o1[0], o1[1], o1[2], o1[3]);
+  }
+}
+
+template <int T, bool kUp, bool kTma>
+__global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap tmap,
+                                                            const float* __restrict__ f, float* __restrict__ y, int inH, int inW,
+                                                            int outH, int outW, int padx0, int pady0, int flip, float gain_axis,
+                                                            int tiles_x, int tiles_y, long nplanes) {
+  using G = SepGeom<T, kUp>;
+  extern __shared__ uint8_t sep_raw[];
+  uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sep_raw) + 127) & ~uintptr_t(127));
+  float* mid = reinterpret_cast<float*>(sbase + 2 * G::IN_STRIDE);      // [TIH][PMID]
+  float* gs = mid + G::TIH * G::PMID;                                   // [T]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(gs + T) + 7) & ~uintptr_t(7));   // [2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < T) gs[tid] = (flip ? f[tid] : f[T - 1 - tid]) * gain_axis;
+  if (kTma && tid == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    fence_mbar_init();
+  }
+  const long ntiles = static_cast<long>(nplanes) * tiles_x * tiles_y;
+  // columns staged in front of the tile so that the box starts on a 16-byte boundary; the same for every tile (a tile step is
+  // 32 / 128 input columns)
+  const int sh = kTma ? (sep_first<kUp>(0, padx0) & 3) : 0;
+  // ---- (1) stage an input tile (zero outside the image = the padding).  The NEXT tile is prefetched while this one is
+  //      filtered and stored.
+  auto prefetch = [&](int tx, int ty, long plane, int buf) {
+    const int ix0 = sep_first<kUp>(tx * G::TOW, padx0) - sh, iy0 = sep_first<kUp>(ty * G::TOH, pady0);
+    float* dst = reinterpret_cast<float*>(sbase + buf * G::IN_STRIDE);
+    if (kTma) {
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bars + buf, G::IN_BYTES);
+        const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        const uint32_t mb = static_cast<uint32_t>(__cvta_generic_to_shared(bars + buf));
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(d), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(ix0), "r"(iy0), "r"(static_cast<int>(plane)), "r"(mb)
+            : "memory");
+      }
+    } else {      // 4-byte cp.async: a warp walks rows, lanes walk columns (coalesced)
+      const float* xp = x + plane * inH * inW;
+      for (int r = warp; r < G::TIH; r += 8) {
+        const int gy = iy0 + r;
+        const bool rowok = gy >= 0 && gy < inH;
+        const float* src = xp + static_cast<long>(rowok ? gy : 0) * inW;
+#pragma unroll
+        for (int c0 = 0; c0 < G::PIN; c0 += 32) {
+          const int c = c0 + lane;
+          if (c < G::PIN) {
+            const int gx = ix0 + c;
+            const bool ok = rowok && c < G::TIW && gx >= 0 && gx < inW;
+            const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * G::PIN + c));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
   };
-  if (blockIdx.x < ntiles) prefetch(blockIdx.x, in_buf);
-  __syncthreads();
+  __syncthreads();                                   // filter taps + barriers initialised
+  // tile -> (plane, ty, tx) is carried incrementally: the 64-bit divisions of the first version cost more instructions per
+  // tile than the two filter passes
+  const int per_plane = tiles_x * tiles_y;
+  const int step_p = static_cast<int>(gridDim.x) / per_plane, step_r = static_cast<int>(gridDim.x) % per_plane;
+  const int step_y = step_r / tiles_x, step_x = step_r % tiles_x;
+  long nplane = static_cast<long>(blockIdx.x) / per_plane;
+  int nty = (static_cast<int>(blockIdx.x) % per_plane) / tiles_x, ntx = static_cast<int>(blockIdx.x) % tiles_x;
+  auto advance = [&]() {
+    ntx += step_x;
+    if (ntx >= tiles_x) { ntx -= tiles_x; ++nty; }
+    nty += step_y;
+    if (nty >= tiles_y) { nty -= tiles_y; ++nplane; }
+    nplane += step_p;
+  };
+  if (blockIdx.x < ntiles) prefetch(ntx, nty, nplane, 0);
   float g[T];
 #pragma unroll
   for (int k = 0; k < T; ++k) g[k] = gs[k];
   int cur = 0;
-  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur ^= 1) {
-  const int tx = static_cast<int>(tile % tiles_x), ty = static_cast<int>((tile / tiles_x) % tiles_y);
-  const long plane = tile / (static_cast<long>(tiles_x) * tiles_y);
-  const int ox0 = tx * G::TOW, oy0 = ty * G::TOH;
-  const float* in_s = in_buf + cur * G::TIH * G::PIN;
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();                                  // this tile's input has landed; everybody is done with the other buffer
-  if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, in_buf + (cur ^ 1) * G::TIH * G::PIN);
-  const bool oddx = ((ox0 - padx0) & 1) != 0, oddy = ((oy0 - pady0) & 1) != 0;
-  // ---- (2) horizontal: item = (input row, group of 4 output columns).  The window of group a starts at column 2a (up) / 8a
-  //      (down) of the staged tile -- even, so it is read as float2 (up) / float4 (down) -- and never leaves the tile.
-  for (int i = tid; i < G::TIH * (G::TOW / 4); i += 256) {
-    const int a = i & (G::TOW / 4 - 1), r = i / (G::TOW / 4);
-    const float* wsrc = in_s + r * G::PIN + (kUp ? 2 * a : 8 * a);
-    float v[G::NV + 3];
-    if (kUp) {
+  uint32_t it = 0;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur ^= 1, ++it) {
+    const int tx = ntx, ty = nty;
+    const long plane = nplane;
+    advance();                                        // (ntx, nty, nplane) = the tile after this one
+    const int ox0 = tx * G::TOW, oy0 = ty * G::TOH;
+    const float* in_s = reinterpret_cast<const float*>(sbase + cur * G::IN_STRIDE);
+    if (kTma) mbar_wait(bars + cur, (it >> 1) & 1);
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                  // this tile's input has landed; everybody is done with the other buffer
+    if (tile + gridDim.x < ntiles) prefetch(ntx, nty, nplane, cur ^ 1);
+    const bool oddx = ((ox0 - padx0) & 1) != 0, oddy = ((oy0 - pady0) & 1) != 0;
+    // ---- (2) horizontal: item = (input row, group of 8 output columns).  Its window starts `sh` columns after column 4a
+    //      (up) / 16a (down) of the staged row: aligned float4 reads, the shift is a compile-time register offset.
+    switch (sh) {
+      case 0: sep_hpass<T, kUp, 0>(in_s, mid, g, oddx, tid); break;
+      case 1: sep_hpass<T, kUp, 1>(in_s, mid, g, oddx, tid); break;
+      case 2: sep_hpass<T, kUp, 2>(in_s, mid, g, oddx, tid); break;
+      default: sep_hpass<T, kUp, 3>(in_s, mid, g, oddx, tid); break;
+    }
+    __syncthreads();
+    // ---- (3) vertical: item = (group of 4 output columns, group of NQ output rows) on two column pairs (FFMA2): float4
+    //      columns of `mid`, float4 stores (rows of the output are 16-byte aligned when outW % 4 == 0)
+    constexpr int NQ = kUp ? 4 : 2;                   // 16 x 16 items (up, 64 rows) / 16 x 16 items (down, 32 rows)
+    constexpr int NW = kUp ? G::NV : G::NV2;
+    float* yp = y + plane * outH * outW;
+    const bool vec_ok = (outW & 3) == 0;
+    for (int i = tid; i < (G::TOW / 4) * (G::TOH / NQ); i += 256) {
+      const int c4 = i & (G::TOW / 4 - 1), a = i / (G::TOW / 4);
+      const float* wsrc = mid + (kUp ? 2 * a : 2 * NQ * a) * G::PMID + 4 * c4;
+      float2 lo[NW], hi[NW];
 #pragma unroll
-      for (int j = 0; j < (G::NV + 1) / 2; ++j) {
-        const float2 t2 = *reinterpret_cast<const float2*>(wsrc + 2 * j);
-        v[2 * j] = t2.x;
-        v[2 * j + 1] = t2.y;
+      for (int j = 0; j < NW; ++j) {
+        const float4 t4 = *reinterpret_cast<const float4*>(wsrc + j * G::PMID);
+        lo[j] = make_float2(t4.x, t4.y);
+        hi[j] = make_float2(t4.z, t4.w);
       }
-    } else {
+      float2 ol[NQ], oh[NQ];
+      sep_fir_pair<T, kUp, NQ>(lo, g, oddy, ol);
+      sep_fir_pair<T, kUp, NQ>(hi, g, oddy, oh);
+      const int ox = ox0 + 4 * c4;
 #pragma unroll
-      for (int j = 0; j < (G::NV + 3) / 4; ++j) {
-        const float4 t4 = *reinterpret_cast<const float4*>(wsrc + 4 * j);
-        v[4 * j] = t4.x; v[4 * j + 1] = t4.y; v[4 * j + 2] = t4.z; v[4 * j + 3] = t4.w;
+      for (int q = 0; q < NQ; ++q) {
+        const int oy = oy0 + NQ * a + q;
+        if (oy >= outH) continue;
+        float* dst = yp + static_cast<long>(oy) * outW + ox;
+        if (vec_ok && ox + 3 < outW) {
+          __stcs(reinterpret_cast<float4*>(dst), make_float4(ol[q].x, ol[q].y, oh[q].x, oh[q].y));
+        } else {
+          if (ox < outW) __stcs(dst, ol[q].x);
+          if (ox + 1 < outW) __stcs(dst + 1, ol[q].y);
+          if (ox + 2 < outW) __stcs(dst + 2, oh[q].x);
+          if (ox + 3 < outW) __stcs(dst + 3, oh[q].y);
+        }
       }
     }
-    float o[4];
-    sep_fir4<T, kUp>(v, g, oddx, o);
-    *reinterpret_cast<float4*>(mid + r * G::PMID + 4 * a) = make_float4(o[0], o[1], o[2], o[3]);
-  }
-  __syncthreads();
-  // ---- (3) vertical: item = (group of 4 output columns, group of 4 output rows): float4 columns of `mid`, 16 outputs,
-  //      float4 stores (rows of the output are 16-byte aligned when outW % 4 == 0)
-  float* yp = y + plane * outH * outW;
-  const bool vec_ok = (outW & 3) == 0;
-  for (int i = tid; i < (G::TOW / 4) * (G::TOH / 4); i += 256) {
-    const int c4 = i & (G::TOW / 4 - 1), a = i / (G::TOW / 4);
-    const float* wsrc = mid + (kUp ? 2 * a : 8 * a) * G::PMID + 4 * c4;
-    float4 v4[G::NV];
-#pragma unroll
-    for (int j = 0; j < G::NV; ++j) v4[j] = *reinterpret_cast<const float4*>(wsrc + j * G::PMID);
-    float col[G::NV], o0[4], o1[4], o2[4], o3[4];
-#pragma unroll
-    for (int j = 0; j < G::NV; ++j) col[j] = v4[j].x;
-    sep_fir4<T, kUp>(col, g, oddy, o0);
-#pragma unroll
-    for (int j = 0; j < G::NV; ++j) col[j] = v4[j].y;
-    sep_fir4<T, kUp>(col, g, oddy, o1);
-#pragma unroll
-    for (int j = 0; j < G::NV; ++j) col[j] = v4[j].z;
-    sep_fir4<T, kUp>(col, g, oddy, o2);
-#pragma unroll
-    for (int j = 0; j < G::NV; ++j) col[j] = v4[j].w;
-    sep_fir4<T, kUp>(col, g, oddy, o3);
-    const int ox = ox0 + 4 * c4;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int oy = oy0 + 4 * a + q;
-      if (oy >= outH) continue;
-      float* dst = yp + static_cast<long>(oy) * outW + ox;
-      if (vec_ok && ox + 3 < outW) {
-        __stcs(reinterpret_cast<float4*>(dst), make_float4(o0[q], o1[q], o2[q], o3[q]));
-      } else {
-        if (ox < outW) __stcs(dst, o0[q]);
-        if (ox + 1 < outW) __stcs(dst + 1, o1[q]);
-        if (ox + 2 < outW) __stcs(dst + 2, o2[q]);
-        if (ox + 3 < outW) __stcs(dst + 3, o3[q]);
-      }
-    }
-  }
   }   // tile loop
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+template <int T, bool kUp>
+static int launch_sep_dir(const float* x, const float* f, float* y, long planes, int inH, int inW, int outH, int outW, int padx0,
+                          int pady0, int flip, float ga, cudaStream_t st) {
+  using G = SepGeom<T, kUp>;
+  const int txn = (outW + G::TOW - 1) / G::TOW, tyn = (outH + G::TOH - 1) / G::TOH;
+  const long nt = planes * txn * tyn, cap = static_cast<long>(num_sms()) * (kUp ? 6 : 2);
+  const unsigned grid = static_cast<unsigned>(nt < cap ? nt : cap);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  bool tma = (inW & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && planes < (1L << 31) && tensor_map_encoder() != nullptr;
+  if (tma) {
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(inW), static_cast<cuuint64_t>(inH), static_cast<cuuint64_t>(planes)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(inW) * 4, static_cast<cuuint64_t>(inW) * inH * 4};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(G::PIN), static_cast<cuuint32_t>(G::TIH), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    tma = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  if (tma) {
+    cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, kUp, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    upfirdn2d_sep_kernel<T, kUp, true><<<grid, 256, G::SMEM, st>>>(x, tmap, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn,
+                                                                    tyn, planes);
+  } else {
+    cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, kUp, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    upfirdn2d_sep_kernel<T, kUp, false><<<grid, 256, G::SMEM, st>>>(x, tmap, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn,
+                                                                     tyn, planes);
+  }
+  return check_launch("hg_upfirdn2d_sep2");
 }
 
 template <int T>
 static int launch_sep(bool up, const float* x, const float* f, float* y, long planes, int inH, int inW, int outH, int outW,
                       int padx0, int pady0, int flip, float gain, cudaStream_t st) {
   const float ga = sqrtf(gain);
-  if (up) {
-    using G = SepGeom<T, true>;
-    const int txn = (outW + G::TOW - 1) / G::TOW, tyn = (outH + G::TOH - 1) / G::TOH;
-    cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-    const long nt = planes * txn * tyn, cap = static_cast<long>(num_sms()) * 6;
-    upfirdn2d_sep_kernel<T, true><<<static_cast<unsigned>(nt < cap ? nt : cap), 256, G::SMEM, st>>>(
-        x, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn, tyn, planes);
-  } else {
-    using G = SepGeom<T, false>;
-    const int txn = (outW + G::TOW - 1) / G::TOW, tyn = (outH + G::TOH - 1) / G::TOH;
-    cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-    const long nt = planes * txn * tyn, cap = static_cast<long>(num_sms()) * 2;
-    upfirdn2d_sep_kernel<T, false><<<static_cast<unsigned>(nt < cap ? nt : cap), 256, G::SMEM, st>>>(
-        x, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn, tyn, planes);
-  }
-  return check_launch("hg_upfirdn2d_sep2");
+  if (up) return launch_sep_dir<T, true>(x, f, y, planes, inH, inW, outH, outW, padx0, pady0, flip, ga, st);
+  return launch_sep_dir<T, false>(x, f, y, planes, inH, inW, outH, outW, padx0, pady0, flip, ga, st);
 }
 
 // 2x2 average pooling / nearest-neighbour 2x up-sampling with a scale factor (each is the other's adjoint up to the

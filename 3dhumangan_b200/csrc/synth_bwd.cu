@@ -25,9 +25,10 @@
 namespace hg {
 
 constexpr int kWC = 256;
-constexpr int kWgThreads = 288;                 // warps 0-7: operand rows, warp 8: MMA issue
+constexpr int kWgThreads = 512;                 // 16 operand warps; lane 0 of warp 0 also issues the MMAs
 constexpr uint32_t kWgImg = 256 * 128;          // [256 rows x 64 px] bf16 = 32 KB
-constexpr uint32_t kWgSmemBytes = 4 * kWgImg + 3 * kWC * 4 + 8 * 8 + 16 + 1024;
+// dout image (hi, lo) double-buffered, x image (hi, lo) single: 6 x 32 KB
+constexpr uint32_t kWgSmemBytes = 6 * kWgImg + 8 * 8 + 16 + 1024;
 
 struct WgradArgs {
   const float* dout;     // [B,T,C,128]
@@ -54,28 +55,31 @@ __device__ __forceinline__ float wg_red(float t) {
 __device__ __forceinline__ float wg_sin(float t) { return __sinf(wg_red(t)); }
 __device__ __forceinline__ float wg_cos(float t) { return __cosf(wg_red(t)); }
 
-template <int kPasses>
+// Schedule (chunk c = 64 pixels of a tile; a thread owns 8 pixels of 4 rows per operand):
+//     convert x(c) -> B image      needs MMA(c-1) done (single buffer)
+//     arrive FULL(c); lane 0 of warp 0 issues MMA(c) on (A[c&1], B)
+//     convert dout(c+1) -> A[(c+1)&1]   while MMA(c) runs (that slot was read last by MMA(c-1))
+// and the global loads of chunk c+1 (x) / c+2 (dout) are issued as soon as their registers are free, so HBM latency is
+// hidden behind the conversions and the MMA wait.  (The first version had 8 operand warps, one image of each operand and
+// loaded x only after converting dout: ncu showed 29 % of the samples waiting for MMA(c-1) and 14 % on the exposed x loads.)
+template <int kPasses, int kAct>
 __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_hi = s;
-  uint8_t* a_lo = s + kWgImg;
-  uint8_t* b_hi = s + 2 * kWgImg;
-  uint8_t* b_lo = s + 3 * kWgImg;
-  float* tab_g1 = reinterpret_cast<float*>(s + 4 * kWgImg);
-  float* tab_g0 = tab_g1 + kWC;
-  float* tab_ps = tab_g0 + kWC;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tab_ps + kWC);
+  uint8_t* a_img = s;                      // [slot][hi, lo]
+  uint8_t* b_hi = s + 4 * kWgImg;
+  uint8_t* b_lo = s + 5 * kWgImg;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s + 6 * kWgImg);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    mbar_init(bars + WG_FULL, 8);
+    mbar_init(bars + WG_FULL, 16);
     mbar_init(bars + WG_EMPTY, 1);
     mbar_init(bars + WG_DONE, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<512>(tmem_slot);
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -84,116 +88,144 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
   const int T = (a.HW + 127) / 128;
   const int total = a.B * T;
   const int count = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int nchunks = 2 * count;
+  const int nq = a.nq, HW = a.HW;
+  const int nst = nq >> 6;                    // row steps of the x operand: 4 (256 rows) or 2 (128)
+  const bool issuer = threadIdx.x == 0;
+  const uint32_t idesc = umma_idesc_bf16(128, nq);
 
-  if (warp < 8) {
-    const int sub = threadIdx.x & 7;          // which 8-pixel group of the 64-pixel chunk
-    const int rsub = threadIdx.x >> 3;        // 0..31: row within a 32-row step
-    float bsum[8];
+  const int sub = threadIdx.x & 7;            // which 8-pixel group of the 64-pixel chunk
+  const int rsub = threadIdx.x >> 3;          // 0..63: row within a 64-row step
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 va[8], vb[8];
+
+  // chunk c -> sample, tile, first pixel of this thread, pixels of the image left from there
+  auto locate = [&](int c, int& b, int& ti, int& p0, int& nvalid) {
+    const int tile = blockIdx.x + (c >> 1) * gridDim.x;
+    b = tile / T;
+    ti = tile - b * T;
+    p0 = (c & 1) * 64 + sub * 8;
+    nvalid = HW - (ti * 128 + p0);
+  };
+  auto load_d = [&](int c) {
+    int b, ti, p0, nv;
+    locate(c, b, ti, p0, nv);
+    const float* base = a.dout + (static_cast<long>(b) * T + ti) * kWC * 128 + rsub * 128 + p0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
-    int cur_b = -1;
-    uint32_t chunk = 0;
-    for (int it = 0; it < count; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int b = tile / T, ti = tile - b * T;
-      if (b != cur_b) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        tab_g1[threadIdx.x] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 0) * kWC + threadIdx.x] : 1.f;   // no table: y = lrelu(x)
-        tab_g0[threadIdx.x] = a.mod ? a.mod[(static_cast<long>(b) * 2 + 1) * kWC + threadIdx.x] : 0.f;
-        tab_ps[threadIdx.x] = a.pscale ? a.pscale[static_cast<long>(b) * kWC + threadIdx.x] : 1.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        cur_b = b;
-      }
-      const float* dbase = a.dout + (static_cast<long>(b) * T + ti) * kWC * 128;
-      const float* xbase = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * a.nq * 128;
-#pragma unroll 1
-      for (int kc = 0; kc < 2; ++kc, ++chunk) {
-        const int p0 = kc * 64 + sub * 8;                 // first pixel (within the tile) of this thread's 8
-        const int nvalid = a.HW - (ti * 128 + p0);        // pixels of the image left from p0 on (may be <= 0)
-        // ---- dout rows -> A image.  The loads are issued before the EMPTY wait: they only fill registers.
-        float4 va[16];
+    for (int st = 0; st < 4; ++st) {
+      const float4* src = reinterpret_cast<const float4*>(base + st * 64 * 128);
+      va[2 * st] = __ldcs(src);
+      va[2 * st + 1] = __ldcs(src + 1);
+    }
+  };
+  auto load_x = [&](int c) {
+    int b, ti, p0, nv;
+    locate(c, b, ti, p0, nv);
+    const float* base = a.x + static_cast<long>(b) * a.x_bstride + static_cast<long>(ti) * nq * 128 + rsub * 128 + p0;
 #pragma unroll
-        for (int st = 0; st < 8; ++st) {
-          const float4* src = reinterpret_cast<const float4*>(dbase + (st * 32 + rsub) * 128 + p0);
-          va[2 * st] = __ldcs(src);
-          va[2 * st + 1] = __ldcs(src + 1);
-        }
-        mbar_wait_sleep(bars + WG_EMPTY, (chunk & 1) ^ 1);
-#pragma unroll
-        for (int st = 0; st < 8; ++st) {
-          float y[8] = {va[2 * st].x, va[2 * st].y, va[2 * st].z, va[2 * st].w,
-                        va[2 * st + 1].x, va[2 * st + 1].y, va[2 * st + 1].z, va[2 * st + 1].w};
-          if (nvalid < 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = j < nvalid ? y[j] : 0.f;
-          }
-          if (a.pscale) {
-            const float ps = tab_ps[st * 32 + rsub];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] *= ps;
-          }
-          bsum[st] += ((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7]));
-          store_a8<kPasses == 3>(a_hi, a_lo, st * 32 + rsub, sub * 8, y);
-        }
-        // ---- x rows -> y = lrelu(x*g1 + g0) -> B image
-        const int nst = a.nq >> 5;
-#pragma unroll
-        for (int st = 0; st < 8; ++st) {
-          if (st < nst) {
-            const float4* src = reinterpret_cast<const float4*>(xbase + (st * 32 + rsub) * 128 + p0);
-            va[2 * st] = __ldcs(src);
-            va[2 * st + 1] = __ldcs(src + 1);
-          }
-        }
-#pragma unroll
-        for (int st = 0; st < 8; ++st) {
-          if (st >= nst) break;
-          const int row = st * 32 + rsub;
-          const float g1 = tab_g1[row], g0 = tab_g0[row];
-          float y[8] = {va[2 * st].x, va[2 * st].y, va[2 * st].z, va[2 * st].w,
-                        va[2 * st + 1].x, va[2 * st + 1].y, va[2 * st + 1].z, va[2 * st + 1].w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float pre = fmaf(y[j], g1, g0);
-            const float v = a.act == 1 ? wg_sin(pre) : (a.act == 2 ? pre : (pre > 0.f ? pre : 0.2f * pre));
-            y[j] = j < nvalid ? v : 0.f;
-          }
-          store_a8<kPasses == 3>(b_hi, b_lo, row, sub * 8, y);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + WG_FULL);
+    for (int st = 0; st < 4; ++st) {
+      if (st < nst) {
+        const float4* src = reinterpret_cast<const float4*>(base + st * 64 * 128);
+        vb[2 * st] = __ldcs(src);
+        vb[2 * st + 1] = __ldcs(src + 1);
       }
     }
-    // bias-gradient partials: row (st*32 + rsub) is shared by the 8 `sub` lanes
+  };
+  auto convert_d = [&](int c) {      // dout rows of chunk c -> A[c & 1]; bias partial sums
+    int b, ti, p0, nvalid;
+    locate(c, b, ti, p0, nvalid);
+    uint8_t* hi = a_img + (c & 1) * 2 * kWgImg;
+    uint8_t* lo = hi + kWgImg;
 #pragma unroll
-    for (int st = 0; st < 8; ++st) {
-      float v = bsum[st];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      if (sub == 0) a.part_b[static_cast<long>(blockIdx.x) * kWC + st * 32 + rsub] = v;
+    for (int st = 0; st < 4; ++st) {
+      const int row = st * 64 + rsub;
+      float y[8] = {va[2 * st].x, va[2 * st].y, va[2 * st].z, va[2 * st].w,
+                    va[2 * st + 1].x, va[2 * st + 1].y, va[2 * st + 1].z, va[2 * st + 1].w};
+      if (nvalid < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = j < nvalid ? y[j] : 0.f;
+      }
+      if (a.pscale) {
+        const float ps = __ldg(a.pscale + static_cast<long>(b) * kWC + row);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] *= ps;
+      }
+      bsum[st] += ((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7]));
+      store_a8<kPasses == 3>(hi, lo, row, sub * 8, y);
     }
-  } else if (lane == 0) {
-    const uint32_t idesc = umma_idesc_bf16(128, a.nq);
-    uint32_t chunk = 0;
-    for (int it = 0; it < count; ++it)
-      for (int kc = 0; kc < 2; ++kc, ++chunk) {
-        mbar_wait_sleep(bars + WG_FULL, chunk & 1);
+  };
+  auto convert_x = [&](int c) {      // x rows of chunk c -> act(x*g1 + g0) -> B
+    int b, ti, p0, nvalid;
+    locate(c, b, ti, p0, nvalid);
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      if (st < nst) {
+        const int row = st * 64 + rsub;
+        float g1 = 1.f, g0 = 0.f;               // no table: y = act(x)
+        if (a.mod) {
+          g1 = __ldg(a.mod + (static_cast<long>(b) * 2 + 0) * kWC + row);
+          g0 = __ldg(a.mod + (static_cast<long>(b) * 2 + 1) * kWC + row);
+        }
+        float y[8] = {vb[2 * st].x, vb[2 * st].y, vb[2 * st].z, vb[2 * st].w,
+                      vb[2 * st + 1].x, vb[2 * st + 1].y, vb[2 * st + 1].z, vb[2 * st + 1].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pre = fmaf(y[j], g1, g0);
+          y[j] = kAct == 1 ? wg_sin(pre) : (kAct == 2 ? pre : (pre > 0.f ? pre : 0.2f * pre));
+        }
+        if (nvalid < 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = j < nvalid ? y[j] : 0.f;
+        }
+        store_a8<kPasses == 3>(b_hi, b_lo, row, sub * 8, y);
+      }
+    }
+  };
+
+  if (nchunks > 0) {
+    load_d(0);
+    load_x(0);
+    convert_d(0);
+    if (nchunks > 1) load_d(1);
+    for (int c = 0; c < nchunks; ++c) {
+      if (c > 0) mbar_wait_sleep(bars + WG_EMPTY, (c - 1) & 1);      // MMA(c-1) done: B and A[(c-1)&1] are free
+      convert_x(c);
+      if (c + 1 < nchunks) load_x(c + 1);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + WG_FULL);
+      if (issuer) {
+        mbar_wait_sleep(bars + WG_FULL, c & 1);
         tc_fence_after();
+        const uint32_t ah0 = smem_u32(a_img + (c & 1) * 2 * kWgImg), al0 = ah0 + kWgImg;
 #pragma unroll
         for (uint32_t mh = 0; mh < 2; ++mh) {
           const uint32_t d = tmem + mh * 256;
-          const uint32_t ah = smem_u32(a_hi) + mh * (kWgImg / 2), al = smem_u32(a_lo) + mh * (kWgImg / 2);
-          umma_k64(d, ah, smem_u32(b_hi), idesc, chunk > 0);
+          const uint32_t ah = ah0 + mh * (kWgImg / 2), al = al0 + mh * (kWgImg / 2);
+          umma_k64(d, ah, smem_u32(b_hi), idesc, c > 0);
           if (kPasses == 3) {
             umma_k64(d, al, smem_u32(b_hi), idesc, true);
             umma_k64(d, ah, smem_u32(b_lo), idesc, true);
           }
         }
         umma_commit(bars + WG_EMPTY);
+        if (c + 1 == nchunks) umma_commit(bars + WG_DONE);
       }
-    umma_commit(bars + WG_DONE);
+      __syncwarp();
+      if (c + 1 < nchunks) {
+        convert_d(c + 1);
+        if (c + 2 < nchunks) load_d(c + 2);
+      }
+    }
+  }
+  // bias-gradient partials: row (st*64 + rsub) is shared by the 8 `sub` lanes
+#pragma unroll
+  for (int st = 0; st < 4; ++st) {
+    float v = bsum[st];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (sub == 0) a.part_b[static_cast<long>(blockIdx.x) * kWC + st * 64 + rsub] = v;
   }
   // ---- drain: warps 0-3 own TMEM lanes 32w..32w+31 (co within the half), 2 x 256 columns (ci)
   if (warp < 4) {
@@ -218,12 +250,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
       for (int i = threadIdx.x; i < kWC * a.nq; i += 128) dst[i] = 0.f;
     }
   }
-  if (count == 0 && warp >= 4 && warp < 8) {     // an idle CTA still owns a (zero) bias partial
-    for (int i = threadIdx.x - 128; i < kWC; i += 128) a.part_b[static_cast<long>(blockIdx.x) * kWC + i] = 0.f;
-  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tmem);
+  if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 // dW[i] = sum over CTAs of part[cta][i] (fp64 accumulation, fixed order -> deterministic), likewise the bias.
@@ -583,13 +612,17 @@ int hg_act_wgrad_blocked(const float* dout, const float* pscale, const float* x,
   hg::WgradArgs a{dout, x, x_bstride, mod, part_w, part_b, B, Hg * Wg, Cx, act, pscale};
   auto st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
+#define HG_WG_LAUNCH(P, A)                                                                                              \
+  do {                                                                                                                  \
+    e = cudaFuncSetAttribute(hg::spade_wgrad_kernel<P, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kWgSmemBytes); \
+    if (e == cudaSuccess) hg::spade_wgrad_kernel<P, A><<<grid, hg::kWgThreads, hg::kWgSmemBytes, st>>>(a);              \
+  } while (0)
   if (passes == 3) {
-    e = cudaFuncSetAttribute(hg::spade_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kWgSmemBytes);
-    if (e == cudaSuccess) hg::spade_wgrad_kernel<3><<<grid, hg::kWgThreads, hg::kWgSmemBytes, st>>>(a);
+    if (act == 0) HG_WG_LAUNCH(3, 0); else if (act == 1) HG_WG_LAUNCH(3, 1); else HG_WG_LAUNCH(3, 2);
   } else {
-    e = cudaFuncSetAttribute(hg::spade_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kWgSmemBytes);
-    if (e == cudaSuccess) hg::spade_wgrad_kernel<1><<<grid, hg::kWgThreads, hg::kWgSmemBytes, st>>>(a);
+    if (act == 0) HG_WG_LAUNCH(1, 0); else if (act == 1) HG_WG_LAUNCH(1, 1); else HG_WG_LAUNCH(1, 2);
   }
+#undef HG_WG_LAUNCH
   if (e != cudaSuccess) { hg::set_error("hg_spade_bwd_wgrad: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; }
   int rc = hg::check_launch("hg_spade_bwd_wgrad");
   if (rc) return rc;

@@ -164,15 +164,18 @@ def test_dense_forward_backward_matches_torch():
         assert rel(xc.grad, xr.grad) < 2e-5 and rel(wc.grad, wr.grad) < 2e-5 and rel(bc.grad, br.grad) < 1e-5, (M, K, N)
 
 
+@pytest.mark.parametrize("width", [201, 204])
 @pytest.mark.parametrize("taps", [4, 8, 12, 16])
-def test_upfirdn2d_fused_separable_multi_tile(port, taps):
+def test_upfirdn2d_fused_separable_multi_tile(port, taps, width):
     """The fused two-axis kernel (hg_upfirdn2d_sep2) over many tiles, both padding parities, negative padding (crop),
-    flip on / off, sizes that are not multiples of the tile -- against the reference's zero-insert / pad / conv / decimate."""
+    flip on / off, sizes that are not multiples of the tile -- against the reference's zero-insert / pad / conv / decimate.
+    width 204: rows are 16-byte aligned, the input tiles are staged by TMA (out-of-bounds zero fill = the padding);
+    width 201: the 4-byte cp.async staging."""
     uf = importlib.import_module("3dhumangan_b200.ops.upfirdn2d")
     g = torch.Generator().manual_seed(10 + taps)
     f = uf.setup_filter(torch.rand(taps, generator=g) - 0.3, separable=True)
     assert f.ndim == 1
-    x = torch.randn(2, 3, 150, 201, generator=g)
+    x = torch.randn(2, 3, 150, width, generator=g)
     cases = []
     for pad in ([taps // 2, taps // 2 - 1] * 2, [taps // 2 + 1, taps // 2, taps // 2 - 2, taps // 2 + 3], [-3, taps, taps - 1, -2]):
         for flip in (False, True):
