@@ -232,7 +232,14 @@ struct SepGeom {
   static constexpr int PMID = TOW + 4;
   static constexpr int IN_BYTES = TIH * PIN * 4;
   static constexpr int IN_STRIDE = (IN_BYTES + 127) & ~127;           // TMA destinations are 128-byte aligned
-  static constexpr int SMEM = 2 * IN_STRIDE + (TIH * PMID + T) * 4 + 16 + 128;   // input tile double-buffered
+  static constexpr int NBUF = kUp ? 3 : 2;                            // input tiles in flight (down: 43 KB each, two CTAs per SM)
+  static constexpr int MID_OFF = NBUF * IN_STRIDE;
+  static constexpr int GS_OFF = MID_OFF + TIH * PMID * 4;
+  static constexpr int BAR_OFF = (GS_OFF + T * 4 + 7) & ~7;
+  static constexpr int SMEM = BAR_OFF + NBUF * 8;
+  // threads: one item each in the vertical pass (256); the horizontal pass has TIH * 8 items -- with 39 rows (up) a 256-thread CTA
+  // left 56 items to a second, mostly empty iteration that every warp then waited for at the barrier
+  static constexpr int THREADS = 320;                                 // down: 74 rows x 8 = 592 items = 2 balanced iterations
 };
 
 // first input index touched by output o (floor semantics for negative values)
@@ -314,41 +321,84 @@ template <int T, bool kUp, int SH>
 __device__ __forceinline__ void sep_hpass(const float* __restrict__ in_s, float* __restrict__ mid, const float (&g)[T], bool oddx, int tid) {
   using G = SepGeom<T, kUp>;
   constexpr int NW = (G::NV8 + SH + 3) & ~3;
+  constexpr int NITEMS = G::TIH * (G::TOW / 8);
   static_assert((kUp ? 4 : 16) * (G::TOW / 8 - 1) + NW <= G::PIN, "an 8-output window leaves the staged row");
-  for (int i = tid; i < G::TIH * (G::TOW / 8); i += 256) {
-    const int a = i & (G::TOW / 8 - 1), r = i / (G::TOW / 8);
-    const float* wsrc = in_s + r * G::PIN + (kUp ? 4 * a : 16 * a);
-    float w[NW];
+  if constexpr (kUp) {
+    for (int i = tid; i < NITEMS; i += G::THREADS) {
+      const int a = i & (G::TOW / 8 - 1), r = i / (G::TOW / 8);
+      const float* wsrc = in_s + r * G::PIN + 4 * a;
+      float w[NW];
 #pragma unroll
-    for (int j = 0; j < NW / 4; ++j) {
-      const float4 t4 = *reinterpret_cast<const float4*>(wsrc + 4 * j);
-      w[4 * j] = t4.x; w[4 * j + 1] = t4.y; w[4 * j + 2] = t4.z; w[4 * j + 3] = t4.w;
+      for (int j = 0; j < NW / 4; ++j) {
+        const float4 t4 = *reinterpret_cast<const float4*>(wsrc + 4 * j);
+        w[4 * j] = t4.x; w[4 * j + 1] = t4.y; w[4 * j + 2] = t4.z; w[4 * j + 3] = t4.w;
+      }
+      float o0[4], o1[4];
+      sep_fir4<T, kUp>(w + SH, g, oddx, o0);
+      sep_fir4<T, kUp>(w + SH + 2, g, oddx, o1);
+      float4* m4 = reinterpret_cast<float4*>(mid + r * G::PMID + 8 * a);
+      m4[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
+      m4[1] = make_float4(o1[0], o1[1], o1[2], o1[3]);
     }
-    float o0[4], o1[4];
-    sep_fir4<T, kUp>(w + SH, g, oddx, o0);
-    sep_fir4<T, kUp>(w + SH + (kUp ? 2 : 8), g, oddx, o1);
-    float4* m4 = reinterpret_cast<float4*>(mid + r * G::PMID + 8 * a);
-    m4[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
-    m4[1] = make_float4(o1[0], o1[1], o1[2], o1[3]);
+  } else {
+    // y[q] = sum_k g[k] * w[SH + 2q + k]: with the window read as pairs W2[i] = (w[2i], w[2i+1]) and the taps as pairs
+    // G2[j] = (g'[M0 + 2j], g'[M0 + 2j + 1]), g'[m] = g[m - SH] (0 outside), M0 = SH & ~1, it is one FFMA2 per tap PAIR and
+    // a final x + y: half the FMA instructions, all register pairs naturally aligned.
+    constexpr int M0 = SH & ~1, NP = T / 2 + (SH & 1);
+    static_assert(2 * (7 + M0 / 2 + NP) <= NW, "pair window");
+    float2 G2[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int ka = M0 + 2 * j - SH, kb = ka + 1;
+      G2[j] = make_float2(ka >= 0 && ka < T ? g[ka] : 0.f, kb >= 0 && kb < T ? g[kb] : 0.f);
+    }
+    // item -> (column group a, row r) with r FASTEST: the 8 threads of an LDS.128 phase then read 8 consecutive rows (pitch
+    // 148 floats = 20 banks apart: conflict-free); with the column group fastest their windows start 16 floats apart -- two
+    // bank groups for 8 threads, a 4-way conflict on every window load (ncu: 64 % of the samples waiting on shared memory,
+    // issue slots 27 % busy)
+    for (int i = tid; i < NITEMS; i += G::THREADS) {
+      const int a = i / G::TIH, r = i - a * G::TIH;
+      const float* wsrc = in_s + r * G::PIN + 16 * a;
+      float2 W2[NW / 2];
+#pragma unroll
+      for (int j = 0; j < NW / 4; ++j) {
+        const float4 t4 = *reinterpret_cast<const float4*>(wsrc + 4 * j);
+        W2[2 * j] = make_float2(t4.x, t4.y);
+        W2[2 * j + 1] = make_float2(t4.z, t4.w);
+      }
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float2 acc = __fmul2_rn(G2[0], W2[q + M0 / 2]);
+#pragma unroll
+        for (int j = 1; j < NP; ++j) acc = __ffma2_rn(G2[j], W2[q + M0 / 2 + j], acc);
+        o[q] = acc.x + acc.y;
+      }
+      float4* m4 = reinterpret_cast<float4*>(mid + r * G::PMID + 8 * a);
+      m4[0] = make_float4(o[0], o[1], o[2], o[3]);
+      m4[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
   }
 }
 
 template <int T, bool kUp, bool kTma>
-__global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(SepGeom<T, kUp>::THREADS, kUp ? 1 : 2) upfirdn2d_sep_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap tmap,
                                                             const float* __restrict__ f, float* __restrict__ y, int inH, int inW,
                                                             int outH, int outW, int padx0, int pady0, int flip, float gain_axis,
                                                             int tiles_x, int tiles_y, long nplanes) {
   using G = SepGeom<T, kUp>;
-  extern __shared__ uint8_t sep_raw[];
-  uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sep_raw) + 127) & ~uintptr_t(127));
-  float* mid = reinterpret_cast<float*>(sbase + 2 * G::IN_STRIDE);      // [TIH][PMID]
-  float* gs = mid + G::TIH * G::PMID;                                   // [T]
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(gs + T) + 7) & ~uintptr_t(7));   // [2]
+  // no static shared memory in this kernel: the dynamic window starts at offset 0 and honours the declared alignment (pointer
+  // arithmetic through integers would turn every access into a generic LD / ST)
+  extern __shared__ __align__(1024) uint8_t sep_raw[];
+  uint8_t* const sbase = sep_raw;
+  float* mid = reinterpret_cast<float*>(sbase + G::MID_OFF);            // [TIH][PMID]
+  float* gs = reinterpret_cast<float*>(sbase + G::GS_OFF);              // [T]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbase + G::BAR_OFF);     // [NBUF]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NWARPS = G::THREADS / 32;
   if (tid < T) gs[tid] = (flip ? f[tid] : f[T - 1 - tid]) * gain_axis;
   if (kTma && tid == 0) {
-    mbar_init(bars, 1);
-    mbar_init(bars + 1, 1);
+    for (int i = 0; i < G::NBUF; ++i) mbar_init(bars + i, 1);
     fence_mbar_init();
   }
   const long ntiles = static_cast<long>(nplanes) * tiles_x * tiles_y;
@@ -372,7 +422,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restr
       }
     } else {      // 4-byte cp.async: a warp walks rows, lanes walk columns (coalesced)
       const float* xp = x + plane * inH * inW;
-      for (int r = warp; r < G::TIH; r += 8) {
+      for (int r = warp; r < G::TIH; r += NWARPS) {
         const int gy = iy0 + r;
         const bool rowok = gy >= 0 && gy < inH;
         const float* src = xp + static_cast<long>(rowok ? gy : 0) * inW;
@@ -396,31 +446,41 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restr
   const int per_plane = tiles_x * tiles_y;
   const int step_p = static_cast<int>(gridDim.x) / per_plane, step_r = static_cast<int>(gridDim.x) % per_plane;
   const int step_y = step_r / tiles_x, step_x = step_r % tiles_x;
-  long nplane = static_cast<long>(blockIdx.x) / per_plane;
-  int nty = (static_cast<int>(blockIdx.x) % per_plane) / tiles_x, ntx = static_cast<int>(blockIdx.x) % tiles_x;
-  auto advance = [&]() {
-    ntx += step_x;
-    if (ntx >= tiles_x) { ntx -= tiles_x; ++nty; }
-    nty += step_y;
-    if (nty >= tiles_y) { nty -= tiles_y; ++nplane; }
-    nplane += step_p;
+  struct TileAt { int tx, ty; long plane; };
+  TileAt at{static_cast<int>(blockIdx.x) % tiles_x, (static_cast<int>(blockIdx.x) % per_plane) / tiles_x,
+            static_cast<long>(blockIdx.x) / per_plane};
+  TileAt pf = at;                                     // the next tile to prefetch (runs NBUF - 1 tiles ahead)
+  auto advance = [&](TileAt& t) {
+    t.tx += step_x;
+    if (t.tx >= tiles_x) { t.tx -= tiles_x; ++t.ty; }
+    t.ty += step_y;
+    if (t.ty >= tiles_y) { t.ty -= tiles_y; ++t.plane; }
+    t.plane += step_p;
   };
-  if (blockIdx.x < ntiles) prefetch(ntx, nty, nplane, 0);
+  long pf_tile = blockIdx.x;
+  auto prefetch_next = [&](int buf) {                 // every thread calls it: the cp.async path counts commit groups
+    if (pf_tile < ntiles) prefetch(pf.tx, pf.ty, pf.plane, buf);
+    else if (!kTma) asm volatile("cp.async.commit_group;" ::: "memory");
+    pf_tile += gridDim.x;
+    advance(pf);
+  };
+#pragma unroll
+  for (int i = 0; i < G::NBUF - 1; ++i) prefetch_next(i);
   float g[T];
 #pragma unroll
   for (int k = 0; k < T; ++k) g[k] = gs[k];
-  int cur = 0;
   uint32_t it = 0;
-  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur ^= 1, ++it) {
-    const int tx = ntx, ty = nty;
-    const long plane = nplane;
-    advance();                                        // (ntx, nty, nplane) = the tile after this one
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int tx = at.tx, ty = at.ty;
+    const long plane = at.plane;
+    advance(at);
+    const int cur = static_cast<int>(it % G::NBUF);
     const int ox0 = tx * G::TOW, oy0 = ty * G::TOH;
     const float* in_s = reinterpret_cast<const float*>(sbase + cur * G::IN_STRIDE);
-    if (kTma) mbar_wait(bars + cur, (it >> 1) & 1);
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                                  // this tile's input has landed; everybody is done with the other buffer
-    if (tile + gridDim.x < ntiles) prefetch(ntx, nty, nplane, cur ^ 1);
+    if (kTma) mbar_wait(bars + cur, (it / G::NBUF) & 1);
+    else asm volatile("cp.async.wait_group %0;" ::"n"(G::NBUF - 2) : "memory");
+    __syncthreads();                                  // this tile's input has landed; everybody is done with the previous buffer
+    prefetch_next(static_cast<int>((it + G::NBUF - 1) % G::NBUF));
     const bool oddx = ((ox0 - padx0) & 1) != 0, oddy = ((oy0 - pady0) & 1) != 0;
     // ---- (2) horizontal: item = (input row, group of 8 output columns).  Its window starts `sh` columns after column 4a
     //      (up) / 16a (down) of the staged row: aligned float4 reads, the shift is a compile-time register offset.
@@ -436,8 +496,9 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restr
     constexpr int NQ = kUp ? 4 : 2;                   // 16 x 16 items (up, 64 rows) / 16 x 16 items (down, 32 rows)
     constexpr int NW = kUp ? G::NV : G::NV2;
     float* yp = y + plane * outH * outW;
-    const bool vec_ok = (outW & 3) == 0;
-    for (int i = tid; i < (G::TOW / 4) * (G::TOH / NQ); i += 256) {
+    const bool vec_ok = (outW & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    const bool vec2_ok = (outW & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
+    for (int i = tid; i < (G::TOW / 4) * (G::TOH / NQ); i += G::THREADS) {
       const int c4 = i & (G::TOW / 4 - 1), a = i / (G::TOW / 4);
       const float* wsrc = mid + (kUp ? 2 * a : 2 * NQ * a) * G::PMID + 4 * c4;
       float2 lo[NW], hi[NW];
@@ -458,6 +519,9 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const float* __restr
         float* dst = yp + static_cast<long>(oy) * outW + ox;
         if (vec_ok && ox + 3 < outW) {
           __stcs(reinterpret_cast<float4*>(dst), make_float4(ol[q].x, ol[q].y, oh[q].x, oh[q].y));
+        } else if (vec2_ok && ox + 3 < outW) {      // even row length (1024 -> 506): rows are 8-byte aligned
+          __stcs(reinterpret_cast<float2*>(dst), ol[q]);
+          __stcs(reinterpret_cast<float2*>(dst) + 1, oh[q]);
         } else {
           if (ox < outW) __stcs(dst, ol[q].x);
           if (ox + 1 < outW) __stcs(dst + 1, ol[q].y);
@@ -504,11 +568,11 @@ static int launch_sep_dir(const float* x, const float* f, float* y, long planes,
   }
   if (tma) {
     cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, kUp, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-    upfirdn2d_sep_kernel<T, kUp, true><<<grid, 256, G::SMEM, st>>>(x, tmap, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn,
+    upfirdn2d_sep_kernel<T, kUp, true><<<grid, G::THREADS, G::SMEM, st>>>(x, tmap, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn,
                                                                     tyn, planes);
   } else {
     cudaFuncSetAttribute(upfirdn2d_sep_kernel<T, kUp, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-    upfirdn2d_sep_kernel<T, kUp, false><<<grid, 256, G::SMEM, st>>>(x, tmap, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn,
+    upfirdn2d_sep_kernel<T, kUp, false><<<grid, G::THREADS, G::SMEM, st>>>(x, tmap, f, y, inH, inW, outH, outW, padx0, pady0, flip, ga, txn,
                                                                      tyn, planes);
   }
   return check_launch("hg_upfirdn2d_sep2");

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--split", type=int, default=2)
     ap.add_argument("--r1", action="store_true", help="time a do_r1 iteration instead of a plain one")
+    ap.add_argument("--native", action="store_true", help="instead: torch.profiler over one iteration, kernels that are NOT this library's")
     args = ap.parse_args()
     pkg = importlib.import_module("3dhumangan_b200")
     abi = importlib.import_module("3dhumangan_b200.abi")
@@ -43,6 +44,23 @@ def main():
         trainer.iteration(batch)
     while bool(cfg["phases"][D.step % len(cfg["phases"])]["do_r1"]) != args.r1:
         trainer.iteration(batch)
+    if args.native:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            trainer.iteration(batch)
+            torch.cuda.synchronize()
+        rows = []
+        for ev in prof.key_averages():
+            t = getattr(ev, "self_device_time_total", 0) or getattr(ev, "self_cuda_time_total", 0)
+            if t > 0:
+                rows.append({"name": ev.key[:120], "ms": round(t / 1e3, 3), "calls": ev.count})
+        rows.sort(key=lambda r: -r["ms"])
+        ours = [r for r in rows if "hg::" in r["name"]]
+        other = [r for r in rows if "hg::" not in r["name"]]
+        print(json.dumps({"library_ms": sum(r["ms"] for r in ours), "other_ms": sum(r["ms"] for r in other), "other": other[:40],
+                          "library": ours[:12]}))
+        return
     abi.TIMING_TAGS = True
     abi.TIMING = []
     torch.cuda.synchronize()
