@@ -57,6 +57,8 @@ SIGNATURES = {
     "hg_bilinear_adjoint": (c_int, [c_void_p, c_void_p, c_long] + [c_int] * 5 + [c_void_p]),
     "hg_conv2d_wgrad_workspace_bytes": (c_size_t, []),
     "hg_conv2d_wgrad_taps": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p, c_void_p, c_int, c_void_p]),
+    "hg_conv2d_wgrad_layer_workspace_bytes": (c_size_t, [c_int] * 6),
+    "hg_conv2d_wgrad_layer": (c_int, [c_void_p] * 5 + [c_size_t] + [c_int] * 7 + [c_void_p]),
     "hg_synth_input_bwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p]),
     "hg_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hg_bias_act_grad": (c_int, [c_void_p] * 6 + [c_long, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
@@ -505,44 +507,24 @@ def _conv3x3_wgrad_halo(dy, x, passes):
 
 def conv2d_wgrad(dy, x, ksize, passes=3):
     """dW [Cout,Cin,k,k], dbias [Cout] of a stride-1 'same' convolution.  3x3 on rows of >= 128 pixels: the haloed kernel
-    (csrc/dconv_wgrad_halo.cu); otherwise csrc/dconv_bwd.cu: one launch per (256 output, 256 input)-channel chunk and per
-    group of taps that fits the 512 TMEM columns."""
+    (csrc/dconv_wgrad_halo.cu); otherwise csrc/dconv_bwd.cu: ONE launch per layer whose grid enumerates the (256 output,
+    256 input)-channel chunks and the groups of taps that fit the 512 TMEM columns (`hg_conv2d_wgrad_layer`; the per-group
+    entry point `hg_conv2d_wgrad_taps` stays exported)."""
     B, Cout, H, W = dy.shape
     Cin = x.shape[1]
     dev = dy.device
     dy, x = dy.contiguous(), x.contiguous()
     if ksize == 3 and W % 128 == 0 and os.environ.get("HG3D_WGRAD_HALO", "1") != "0":
         return _conv3x3_wgrad_halo(dy, x, passes)
+    need = int(lib().hg_conv2d_wgrad_layer_workspace_bytes(B, H, W, Cout, Cin, ksize))
     ws = _CONV_WS.get(dev)
-    if ws is None:
-        ws = _CONV_WS[dev] = torch.empty(int(lib().hg_conv2d_wgrad_workspace_bytes()) // 4, dtype=torch.float32, device=dev)
+    if ws is None or ws.numel() * 4 < need:
+        ws = _CONV_WS[dev] = torch.empty(max(need, 64 << 20) // 4 + 4, dtype=torch.float32, device=dev)
     dW = torch.empty(Cout, Cin, ksize, ksize, dtype=torch.float32, device=dev)
     db = torch.empty(Cout, dtype=torch.float32, device=dev)
-    pad = ksize // 2
-    taps = [(ky, kx) for ky in range(ksize) for kx in range(ksize)]
-    for co0 in range(0, Cout, 256):
-        nco = min(256, Cout - co0)
-        nmh = 2 if nco > 128 else 1
-        for ci0 in range(0, Cin, 256):
-            nci = min(256, Cin - ci0)
-            nq = (nci + 31) // 32 * 32
-            per = max(1, 512 // (nmh * nq))
-            for t0 in range(0, len(taps), per):
-                grp = taps[t0:t0 + per]
-                n = len(grp)
-                oy = (ctypes.c_int * n)(*[ky - pad for ky, _ in grp])
-                ox = (ctypes.c_int * n)(*[kx - pad for _, kx in grp])
-                dw = torch.empty(n, 256, nq, dtype=torch.float32, device=dev)
-                first = ci0 == 0 and t0 == 0
-                dbt = torch.empty(256, dtype=torch.float32, device=dev) if first else None
-                with torch.cuda.device_of(dy):
-                    call("hg_conv2d_wgrad_taps", ptr(dy), ptr(x), ptr(dw), ptr(dbt), ptr(ws), B, H, W, Cout, Cin, co0, nco,
-                         ci0, nci, n, ctypes.cast(oy, c_void_p), ctypes.cast(ox, c_void_p), passes, stream(),
-                         tag=f"{Cin}->{Cout} k{ksize} {H}x{W} B{B}" if TIMING_TAGS else None)
-                for i, (ky, kx) in enumerate(grp):
-                    dW[co0:co0 + nco, ci0:ci0 + nci, ky, kx] = dw[i, :nco, :nci]
-                if first:
-                    db[co0:co0 + nco] = dbt[:nco]
+    with torch.cuda.device_of(dy):
+        call("hg_conv2d_wgrad_layer", ptr(dy), ptr(x), ptr(dW), ptr(db), ptr(ws), ws.numel() * 4, B, H, W, Cout, Cin, ksize, passes,
+             stream(), tag=f"{Cin}->{Cout} k{ksize} {H}x{W} B{B}" if TIMING_TAGS else None)
     return dW, db
 
 

@@ -25,7 +25,30 @@ struct ConvWgradArgs {
   int ci0, nci, nq;      // rows of x (nci valid, nq = nci rounded up to 32, <= 256)
   int ntaps;             // taps of this launch; tap t reads x at (h + oy[t], w + ox[t])
   int oy[9], ox[9];
+  // whole-layer mode (hg_conv2d_wgrad_layer): blockIdx.y enumerates (256-row chunk of dy, 256-row chunk of x, group of `per`
+  // taps) and the fields above are derived from it; every item owns `item_stride` floats of part_w (gridDim.x partials)
+  int layer, ksize, per;
+  long item_stride;
 };
+
+// item index -> chunk / tap-group geometry, shared by the GEMM kernel and its reduction
+struct ConvWgradItem {
+  int co0, nco, ci0, nci, nq, ntaps, t0;
+};
+__device__ __forceinline__ ConvWgradItem conv_wgrad_item(int idx, int Cout, int Cin, int ksize, int per) {
+  const int kk = ksize * ksize;
+  const int ngrp = (kk + per - 1) / per, nci_chunks = (Cin + 255) / 256;
+  const int grp = idx % ngrp, cii = (idx / ngrp) % nci_chunks, coi = idx / (ngrp * nci_chunks);
+  ConvWgradItem it;
+  it.co0 = coi * 256;
+  it.nco = Cout - it.co0 < 256 ? Cout - it.co0 : 256;
+  it.ci0 = cii * 256;
+  it.nci = Cin - it.ci0 < 256 ? Cin - it.ci0 : 256;
+  it.nq = (it.nci + 31) / 32 * 32;
+  it.t0 = grp * per;
+  it.ntaps = kk - it.t0 < per ? kk - it.t0 : per;
+  return it;
+}
 
 enum { DW_AFULL = 0, DW_AEMPTY = 1, DW_BFULL = 2, DW_BEMPTY = 3, DW_DONE = 4 };
 
@@ -54,6 +77,17 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  if (a.layer) {
+    const ConvWgradItem it = conv_wgrad_item(blockIdx.y, a.Cout, a.Cin, a.ksize, a.per);
+    a.co0 = it.co0; a.nco = it.nco; a.ci0 = it.ci0; a.nci = it.nci; a.nq = it.nq; a.ntaps = it.ntaps;
+    const int pad = a.ksize >> 1;
+    for (int t = 0; t < it.ntaps; ++t) {
+      a.oy[t] = (it.t0 + t) / a.ksize - pad;
+      a.ox[t] = (it.t0 + t) % a.ksize - pad;
+    }
+    a.part_w += static_cast<long>(blockIdx.y) * a.item_stride;
+    a.part_b += static_cast<long>(blockIdx.y) * gridDim.x * 256;
+  }
   const int HW = a.H * a.W, T = (HW + 127) / 128;
   const int total = a.B * T;
   const int count = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -235,6 +269,31 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ part_w, const
   }
 }
 
+// whole-layer reduction: item partials -> dW [Cout, Cin, k, k] (and dbias from the items of the first x chunk / tap group), fp64,
+// partials in ascending CTA order (deterministic)
+__global__ void conv_wgrad_reduce_layer_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int nparts,
+                                               long item_stride, int Cout, int Cin, int ksize, int per, float* __restrict__ dW,
+                                               float* __restrict__ db) {
+  const ConvWgradItem it = conv_wgrad_item(blockIdx.y, Cout, Cin, ksize, per);
+  const int nw = it.ntaps * 256 * it.nq;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* pw = part_w + static_cast<long>(blockIdx.y) * item_stride;
+  if (i < nw) {
+    const int t = i / (256 * it.nq), r = (i / it.nq) % 256, c = i % it.nq;
+    if (r < it.nco && c < it.nci) {
+      double acc = 0.0;
+      for (int p = 0; p < nparts; ++p) acc += static_cast<double>(pw[static_cast<long>(p) * nw + i]);
+      dW[(static_cast<long>(it.co0 + r) * Cin + it.ci0 + c) * (ksize * ksize) + it.t0 + t] = static_cast<float>(acc);
+    }
+  }
+  if (db && it.ci0 == 0 && it.t0 == 0 && i < it.nco) {
+    const float* pb = part_b + static_cast<long>(blockIdx.y) * nparts * 256;
+    double acc = 0.0;
+    for (int p = 0; p < nparts; ++p) acc += static_cast<double>(pb[static_cast<long>(p) * 256 + i]);
+    db[it.co0 + i] = static_cast<float>(acc);
+  }
+}
+
 }  // namespace hg
 
 extern "C" {
@@ -288,6 +347,72 @@ int hg_conv2d_wgrad_taps(const float* dy, const float* x, float* dw, float* dbia
   const int nw = ntaps * 256 * nq;
   hg::conv_wgrad_reduce_kernel<<<(nw + 255) / 256, 256, 0, st>>>(part_w, part_b, grid, nw, dw, dbias);
   return hg::check_launch("hg_conv2d_wgrad_taps(reduce)");
+}
+
+// ---- one launch per layer: every (dy chunk, x chunk, tap group) as blockIdx.y of the same grid.  The low-resolution layers
+// (16^2 .. 64^2 pixels: 2 .. 32 tiles per image) needed 9 .. 36 launches of 16-128 CTAs each with hg_conv2d_wgrad_taps.
+static void wgrad_layer_geometry(int B, int H, int W, int Cout, int Cin, int ksize, int* per, int* nitems, int* gx, long* item_stride) {
+  const int kk = ksize * ksize;
+  const int nmh = Cout > 128 ? 2 : 1;
+  const int nq_max = ((Cin < 256 ? Cin : 256) + 31) / 32 * 32;
+  *per = 512 / (nmh * nq_max) < 1 ? 1 : 512 / (nmh * nq_max);
+  if (*per > kk) *per = kk;
+  const int ngrp = (kk + *per - 1) / *per;
+  *nitems = ((Cout + 255) / 256) * ((Cin + 255) / 256) * ngrp;
+  const int tiles = B * ((H * W + 127) / 128);
+  // CTAs in flight: one per SM for a single item (every extra CTA is one more partial to drain and reduce), ~4 waves when the
+  // grid is many small items of different cost
+  int g = *nitems == 1 ? hg::num_sms() : 4 * hg::num_sms() / *nitems;
+  if (g < 1) g = 1;
+  *gx = tiles < g ? tiles : g;
+  *item_stride = static_cast<long>(*gx) * *per * 256 * nq_max;
+}
+
+size_t hg_conv2d_wgrad_layer_workspace_bytes(int B, int H, int W, int Cout, int Cin, int ksize) {
+  int per, nitems, gx;
+  long stride;
+  wgrad_layer_geometry(B, H, W, Cout, Cin, ksize, &per, &nitems, &gx, &stride);
+  return (static_cast<size_t>(nitems) * stride + static_cast<size_t>(nitems) * gx * 256) * sizeof(float);
+}
+
+int hg_conv2d_wgrad_layer(const float* dy, const float* x, float* dW, float* dbias, void* workspace, size_t workspace_bytes, int B,
+                          int H, int W, int Cout, int Cin, int ksize, int passes, void* stream) {
+  HG_REQUIRE(dy && x && dW && workspace, "hg_conv2d_wgrad_layer: null pointer");
+  HG_REQUIRE(ksize == 1 || ksize == 3, "hg_conv2d_wgrad_layer: kernel size must be 1 or 3");
+  HG_REQUIRE(B > 0 && H > 0 && W > 0 && (H * W) % 4 == 0, "hg_conv2d_wgrad_layer: bad image shape (H*W must be a multiple of 4)");
+  HG_REQUIRE(Cout > 0 && Cin > 0, "hg_conv2d_wgrad_layer: bad channel counts");
+  HG_REQUIRE(passes == 1 || passes == 3, "hg_conv2d_wgrad_layer: passes must be 1 or 3");
+  HG_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
+             "hg_conv2d_wgrad_layer: dy / workspace must be 16-byte aligned");
+  int per, nitems, gx;
+  long stride;
+  wgrad_layer_geometry(B, H, W, Cout, Cin, ksize, &per, &nitems, &gx, &stride);
+  HG_REQUIRE(workspace_bytes >= hg_conv2d_wgrad_layer_workspace_bytes(B, H, W, Cout, Cin, ksize),
+             "hg_conv2d_wgrad_layer: workspace too small (%zu bytes)", workspace_bytes);
+  HG_REQUIRE(nitems <= 65535, "hg_conv2d_wgrad_layer: too many work items");
+  hg::ConvWgradArgs a{};
+  float* part_w = static_cast<float*>(workspace);
+  float* part_b = part_w + static_cast<size_t>(nitems) * stride;
+  a.dy = dy; a.x = x; a.part_w = part_w; a.part_b = part_b;
+  a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.Cin = Cin;
+  a.layer = 1; a.ksize = ksize; a.per = per; a.item_stride = stride;
+  auto st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(gx, nitems);
+  cudaError_t e;
+  if (passes == 3) {
+    e = cudaFuncSetAttribute(hg::conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kDwSmemBytes);
+    if (e == cudaSuccess) hg::conv_wgrad_kernel<3><<<grid, hg::kDwThreads, hg::kDwSmemBytes, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(hg::conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hg::kDwSmemBytes);
+    if (e == cudaSuccess) hg::conv_wgrad_kernel<1><<<grid, hg::kDwThreads, hg::kDwSmemBytes, st>>>(a);
+  }
+  if (e != cudaSuccess) { hg::set_error("hg_conv2d_wgrad_layer: smem opt-in failed: %s", cudaGetErrorString(e)); return 2; }
+  int rc = hg::check_launch("hg_conv2d_wgrad_layer");
+  if (rc) return rc;
+  const int nw_max = per * 256 * 256;
+  hg::conv_wgrad_reduce_layer_kernel<<<dim3((nw_max + 255) / 256, nitems), 256, 0, st>>>(part_w, part_b, gx, stride, Cout, Cin, ksize,
+                                                                                          per, dW, dbias);
+  return hg::check_launch("hg_conv2d_wgrad_layer(reduce)");
 }
 
 }  // extern "C"

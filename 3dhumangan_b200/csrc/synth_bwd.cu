@@ -551,19 +551,59 @@ __global__ void __launch_bounds__(128) bilinear_adjoint_kernel(const float* __re
   yhi = yhi > Hg - 1 ? Hg - 1 : yhi; xhi = xhi > Wg - 1 ? Wg - 1 : xhi;
   const float* src = da1 + static_cast<long>(b) * Hg * Wg * 128 + threadIdx.x;
   float acc = 0.f;
-  for (int py = ylo; py <= yhi; ++py) {
-    int y0, y1;
-    float ly0, ly1;
-    bilin_src(py, Rh, ry, y0, y1, ly0, ly1);
-    const float wy = (y0 == sy ? ly0 : 0.f) + (y1 == sy ? ly1 : 0.f);
-    if (wy == 0.f) continue;
-    for (int px = xlo; px <= xhi; ++px) {
-      int x0, x1;
-      float lx0, lx1;
-      bilin_src(px, Rw, rx, x0, x1, lx0, lx1);
-      const float wx = (x0 == sx ? lx0 : 0.f) + (x1 == sx ? lx1 : 0.f);
-      if (wx == 0.f) continue;
-      acc = fmaf(wy * wx, src[(static_cast<long>(py) * Wg + px) * 128], acc);
+  // The footprint weights depend on the row / column only: 2 x <= 64 of them are computed once per block (the first version
+  // evaluated both source-index formulas per candidate pixel in every one of the 128 channel threads: ~10 K instructions per
+  // thread for ~120 useful loads).  Same candidates, same order, same products: bit-identical sums.
+  __shared__ float s_wy[64], s_wx[64];
+  const int ny = yhi - ylo + 1, nx = xhi - xlo + 1;
+  if (ny <= 64 && nx <= 64) {
+    if (threadIdx.x < 64) {
+      const int k = threadIdx.x;
+      float w = 0.f;
+      if (k < ny) {
+        int y0, y1;
+        float ly0, ly1;
+        bilin_src(ylo + k, Rh, ry, y0, y1, ly0, ly1);
+        w = (y0 == sy ? ly0 : 0.f) + (y1 == sy ? ly1 : 0.f);
+      }
+      s_wy[k] = w;
+    } else {
+      const int k = threadIdx.x - 64;
+      float w = 0.f;
+      if (k < nx) {
+        int x0, x1;
+        float lx0, lx1;
+        bilin_src(xlo + k, Rw, rx, x0, x1, lx0, lx1);
+        w = (x0 == sx ? lx0 : 0.f) + (x1 == sx ? lx1 : 0.f);
+      }
+      s_wx[k] = w;
+    }
+    __syncthreads();
+    for (int ky = 0; ky < ny; ++ky) {
+      const float wy = s_wy[ky];
+      if (wy == 0.f) continue;
+      const float* row = src + (static_cast<long>(ylo + ky) * Wg + xlo) * 128;
+      for (int kx = 0; kx < nx; ++kx) {
+        const float wx = s_wx[kx];
+        if (wx == 0.f) continue;
+        acc = fmaf(wy * wx, row[static_cast<long>(kx) * 128], acc);
+      }
+    }
+  } else {
+    for (int py = ylo; py <= yhi; ++py) {
+      int y0, y1;
+      float ly0, ly1;
+      bilin_src(py, Rh, ry, y0, y1, ly0, ly1);
+      const float wy = (y0 == sy ? ly0 : 0.f) + (y1 == sy ? ly1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int px = xlo; px <= xhi; ++px) {
+        int x0, x1;
+        float lx0, lx1;
+        bilin_src(px, Rw, rx, x0, x1, lx0, lx1);
+        const float wx = (x0 == sx ? lx0 : 0.f) + (x1 == sx ? lx1 : 0.f);
+        if (wx == 0.f) continue;
+        acc = fmaf(wy * wx, src[(static_cast<long>(py) * Wg + px) * 128], acc);
+      }
     }
   }
   dp[static_cast<long>(s) * dp_stride + threadIdx.x] = acc;

@@ -212,6 +212,12 @@ size_t hg_conv2d_wgrad_workspace_bytes(void);
 int hg_conv2d_wgrad_taps(const float* dy, const float* x, float* dw, float* dbias, void* workspace, int B, int H, int W,
                          int Cout, int Cin, int co0, int nco, int ci0, int nci, int ntaps, const int* oy, const int* ox,
                          int passes, void* stream);
+/* The same gradient for a WHOLE layer in one launch: every (256-row chunk of dy, 256-row chunk of x, group of taps) is a
+ * blockIdx.y of one grid, the partials are reduced straight into dW [Cout,Cin,k,k] and dbias [Cout] (NULL = skip).  k = 1 or 3.
+ * workspace: hg_conv2d_wgrad_layer_workspace_bytes(B,H,W,Cout,Cin,k) bytes (its size is passed for the check). */
+size_t hg_conv2d_wgrad_layer_workspace_bytes(int B, int H, int W, int Cout, int Cin, int ksize);
+int hg_conv2d_wgrad_layer(const float* dy, const float* x, float* dW, float* dbias, void* workspace, size_t workspace_bytes, int B,
+                          int H, int W, int Cout, int Cin, int ksize, int passes, void* stream);
 /* 3x3 weight gradient on image rows of >= 128 pixels (W % 128 == 0): the input is converted once per image row into the
  * forward kernel's pixel-major operand image and read as an MN-major B operand, a tap being a row offset of the descriptor.
  * dw [ntaps,128,64] for output channels co0..co0+nco (<= 128) x input channels ci0..ci0+nci (<= 64), ntaps <= 8 taps with
