@@ -285,6 +285,18 @@ class GeneratorCore(torch.autograd.Function):
         with torch.enable_grad():
             dfreq, dphase = mlp_backward(rtape, dray, grads=grads)
         ctx.tapes = None
-        out = [grads.get(n) for n in names]
-        return (None, None, None, None, None, None, None, dfreq.detach(), dphase.detach(), dfs.detach().reshape(B, -1),
-                *[None if g is None else g.detach() for g in out])
+        # Every returned gradient must own its storage: autograd's AccumulateGrad steals a returned tensor as `.grad` when
+        # nobody else holds the TensorImpl, so two parameters whose gradients are views of one buffer (the nine ToRGB biases
+        # all receive sum(d_rgb)) would end up with ALIASED `.grad`s -- and every in-place pass over the gradients
+        # (GradScaler.unscale_, clip_grad_norm_) would then hit that buffer once per alias, concurrently in the foreach kernels.
+        out, seen = [], set()
+        for n in names:
+            g = grads.get(n)
+            if g is not None:
+                g = g.detach()
+                key = g.untyped_storage().data_ptr()
+                if key in seen or g.untyped_storage().nbytes() != g.numel() * g.element_size():
+                    g = g.clone()
+                seen.add(g.untyped_storage().data_ptr())
+            out.append(g)
+        return (None, None, None, None, None, None, None, dfreq.detach(), dphase.detach(), dfs.detach().reshape(B, -1), *out)

@@ -181,13 +181,16 @@ def _trainer_worker(rank, world, port_no, out_path):
     losses = [tuple(float(x) for x in t.iteration(batch)) for _ in range(2)]
     torch.cuda.synchronize()
     # after identical updates from averaged gradients the replicas must still be identical
-    chk = torch.stack([p.detach().double().sum() for p in list(G.parameters()) + list(D.parameters())])
+    named = [("G." + n, p) for n, p in G.named_parameters()] + [("D." + n, p) for n, p in D.named_parameters()]
+    chk = torch.stack([p.detach().double().sum() for _, p in named])
     both = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(both, chk)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        torch.save({"losses": losses, "replica_diff": float((both[0] - both[1]).abs().max()),
+        diff = (both[0] - both[1]).abs()
+        torch.save({"losses": losses, "replica_diff": float(diff.max()),
+                    "differing": [(named[i][0], float(diff[i])) for i in torch.nonzero(diff).flatten().tolist()][:40],
                     "finite": bool(all(torch.isfinite(p).all() for p in list(G.parameters()) + list(D.parameters()))),
                     "scale": t.scaler.get_scale()}, out_path)
 
@@ -200,4 +203,6 @@ def test_trainer_iterations_under_ddp_amp_r1(tmp_path):
     r = torch.load(out)
     assert r["finite"], r
     assert all(math.isfinite(x) for pair in r["losses"] for x in pair), r
+    if r["replica_diff"] != 0.0:
+        print("replicas differ in:", *r["differing"], sep="\n  ")
     assert r["replica_diff"] == 0.0, r

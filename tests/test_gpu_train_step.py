@@ -40,6 +40,11 @@ def test_train_iteration_updates_both_networks(pkg):
         assert torch.isfinite(p).all()
     # the discriminator loss on fixed data goes down under its own updates
     assert losses[-1][0] < losses[0][0]
+    # no two gradients share a buffer: in-place passes over the gradients (GradScaler.unscale_, clip_grad_norm_) would hit an
+    # aliased buffer once per alias -- the nine ToRGB biases all receive sum(d_rgb), once returned as views of one tensor
+    for net in (G, D):
+        ptrs = [p.grad.untyped_storage().data_ptr() for p in net.parameters() if p.grad is not None]
+        assert len(ptrs) > 0 and len(ptrs) == len(set(ptrs))
 
 
 def _oracle_d_step(port, ts, pg, pd, batch, cfg, u, noise, do_r1):
