@@ -332,7 +332,10 @@ int hg_conv2d(const float* x1, int C1, const float* x2, int C2, int B, int H, in
   HG_REQUIRE(passes == 1 || passes == 3, "hg_conv2d: passes must be 1 or 3");
   HG_REQUIRE(Nb >= 16 && Nb <= 256 && Nb % 16 == 0, "hg_conv2d: Nb=%d must be a multiple of 16 in [16,256]", Nb);
   const int Cin = C1 + C2, taps = ksize * ksize;
-  const int small = (taps * Cin <= 64) ? 1 : 0;
+  // single-chunk contractions: the 3-channel stem and the 64 -> 1 / 26 heads.  A 64 -> 256 1x1 layer (the data gradient of an
+  // up-sampling shortcut) also has taps * Cin == 64 but is an ordinary K = 64, N = 256 GEMM: tensor-core path (the SIMT kernel
+  // re-read x once per 32 output channels: 1.02 ms at B = 16, 256^2)
+  const int small = (taps * Cin <= 64 && !(Cin % 64 == 0 && Cout > 32)) ? 1 : 0;
   HG_REQUIRE(small || (C1 % 64 == 0 && C2 % 64 == 0), "hg_conv2d: channel counts must be multiples of 64 (or taps*Cin <= 64)");
   HG_REQUIRE(!small || C2 == 0, "hg_conv2d: the small-Cin path takes a single input");
   const int nblocks = (Cout + Nb - 1) / Nb;

@@ -10,11 +10,12 @@ pytestmark = pytest.mark.gpu
 C = 256
 
 
-def _blocked(t):
-    """[B,C,HW] -> tile-blocked [B,T,C,128] (zero padded)."""
+def _blocked(t, fill=0.0):
+    """[B,C,HW] -> tile-blocked [B,T,C,128]; the rows past the image hold `fill` (zero; NaN = what an uninitialised
+    activation buffer may hold there in production: nothing may leak from them)."""
     B, Cc, HW = t.shape
     T = (HW + 127) // 128
-    pad = torch.zeros(B, Cc, T * 128, dtype=t.dtype, device=t.device)
+    pad = torch.full((B, Cc, T * 128), fill, dtype=t.dtype, device=t.device)
     pad[:, :, :HW] = t
     return pad.reshape(B, Cc, T, 128).permute(0, 2, 1, 3).contiguous()
 
@@ -47,7 +48,7 @@ def test_dgrad(B, Hg, Wg, passes, tol):
     s1_ref, s2_ref = dpre_ref.sum(2), (dpre_ref * xd).sum(2)
 
     wimg_t, _ = abi.pack_weight(W.t().contiguous().cuda(), Nb=256)
-    xb, db_ = _blocked(x).cuda(), _blocked(dout).cuda()
+    xb, db_ = _blocked(x, float("nan")).cuda(), _blocked(dout, float("nan")).cuda()
     dpre = torch.full_like(xb, float("nan"))
     sums = torch.zeros(B, 2, C, dtype=torch.float64, device="cuda")
     T = xb.shape[1]
@@ -88,9 +89,9 @@ def test_wgrad(B, Hg, Wg, passes, tol):
     y = torch.where(pre > 0, pre, 0.2 * pre)
     dw_ref = torch.einsum("bop,bcp->oc", dout.double(), y)
     db_ref = dout.double().sum((0, 2))
-    xb = _blocked(x).cuda()
-    dw, db = abi.spade_bwd_wgrad(_blocked(dout).cuda(), xb, xb.shape[1] * C * 128, mod.cuda().contiguous(), B=B, Hg=Hg, Wg=Wg,
-                                 passes=passes)
+    xb = _blocked(x, float("nan")).cuda()
+    dw, db = abi.spade_bwd_wgrad(_blocked(dout, float("nan")).cuda(), xb, xb.shape[1] * C * 128, mod.cuda().contiguous(), B=B, Hg=Hg,
+                                 Wg=Wg, passes=passes)
     torch.cuda.synchronize()
     assert (dw.cpu().double() - dw_ref).abs().max() / dw_ref.abs().max() < tol
     assert (db.cpu().double() - db_ref).abs().max() / db_ref.abs().max() < 1e-5
