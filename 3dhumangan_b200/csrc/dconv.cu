@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(kDcThreads, 1) conv_kernel(ConvArgs a) {
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {      // the warp walks the loops, one elected lane issues (umma.cuh: elect_one_sync)
+      const bool leader = elect_one_sync();
       const uint32_t idesc = umma_idesc_bf16(128, a.Nb);
       uint32_t st = 0, ph = 0, cnt = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -210,21 +211,21 @@ __global__ void __launch_bounds__(kDcThreads, 1) conv_kernel(ConvArgs a) {
             const uint32_t d = tmem + nb * 256;
             mbar_wait(bars + DB_FULL + st, ph);
             tc_fence_after();
-            umma_k64(d, ahi, smem_u32(b_st + st * kDcB), idesc, ck > 0);
-            if (kPasses == 3) umma_k64(d, alo, smem_u32(b_st + st * kDcB), idesc, true);
-            umma_commit(bars + DB_EMPTY + st);
+            umma_k64_if(leader, d, ahi, smem_u32(b_st + st * kDcB), idesc, ck > 0);
+            if (kPasses == 3) umma_k64_if(leader, d, alo, smem_u32(b_st + st * kDcB), idesc, true);
+            umma_commit_if(leader, bars + DB_EMPTY + st);
             if (++st == kDcStages) { st = 0; ph ^= 1; }
             if (kPasses == 3) {
               mbar_wait(bars + DB_FULL + st, ph);
               tc_fence_after();
-              umma_k64(d, ahi, smem_u32(b_st + st * kDcB), idesc, true);
-              umma_commit(bars + DB_EMPTY + st);
+              umma_k64_if(leader, d, ahi, smem_u32(b_st + st * kDcB), idesc, true);
+              umma_commit_if(leader, bars + DB_EMPTY + st);
               if (++st == kDcStages) { st = 0; ph ^= 1; }
             }
           }
-          umma_commit(bars + DA_EMPTY + slot);
+          umma_commit_if(leader, bars + DA_EMPTY + slot);
         }
-        umma_commit(bars + DACC_FULL);
+        umma_commit_if(leader, bars + DACC_FULL);
       }
     }
   } else {

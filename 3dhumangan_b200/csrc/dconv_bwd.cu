@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       if (sub == 0) a.part_b[static_cast<long>(blockIdx.x) * 256 + st * 32 + rsub] = v;
     }
-  } else if (lane == 0) {
+  } else {      // MMA issuer: the warp walks the loops, one elected lane issues (umma.cuh: elect_one_sync)
+    const bool leader = elect_one_sync();
     const uint32_t idesc = umma_idesc_bf16(128, a.nq);
     uint32_t chunk = 0, bcnt = 0;
     for (int it = 0; it < count; ++it)
@@ -204,17 +205,17 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
           for (int mh = 0; mh < nmh; ++mh) {
             const uint32_t d = tmem + (t * nmh + mh) * a.nq;
             const uint32_t ah = smem_u32(a_hi) + mh * (kDwImg / 2), al = smem_u32(a_lo) + mh * (kDwImg / 2);
-            umma_k64(d, ah, smem_u32(b_hi), idesc, chunk > 0);
+            umma_k64_if(leader, d, ah, smem_u32(b_hi), idesc, chunk > 0);
             if (kPasses == 3) {
-              umma_k64(d, al, smem_u32(b_hi), idesc, true);
-              umma_k64(d, ah, smem_u32(b_lo), idesc, true);
+              umma_k64_if(leader, d, al, smem_u32(b_hi), idesc, true);
+              umma_k64_if(leader, d, ah, smem_u32(b_lo), idesc, true);
             }
           }
-          umma_commit(bars + DW_BEMPTY);
+          umma_commit_if(leader, bars + DW_BEMPTY);
         }
-        umma_commit(bars + DW_AEMPTY);
+        umma_commit_if(leader, bars + DW_AEMPTY);
       }
-    umma_commit(bars + DW_DONE);
+    umma_commit_if(leader, bars + DW_DONE);
   }
   if (warp < 4) {
     float* dst0 = a.part_w + static_cast<long>(blockIdx.x) * a.ntaps * 256 * a.nq;

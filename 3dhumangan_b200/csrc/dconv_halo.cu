@@ -235,7 +235,12 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
     }
   } else if (warp == 12) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loops and polls the barriers; one elected lane issues.  With the loops inside `if (lane == 0)`
+    // every loop variable lived in vector registers of a divergent region and each tcgen05.mma cost 17.5 instructions
+    // (5 R2UR, 3 PLOP3, ELECT, ...; ncu: the issuing warp busy 80 % of the time, ~135 cycles per MMA whose tensor work is
+    // 64 (N = 128) or 32 (N = 64) cycles); in convergent code descriptors and addresses stay in uniform registers.
+    {
+      const bool leader = elect_one_sync();
       const uint32_t idesc = umma_idesc_bf16(128, a.nsubw);
       const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
       uint32_t st = 0, ph = 0, n = 0;
@@ -259,31 +264,38 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
               mbar_wait(bars + HB_FULL + st, ph);
               tc_fence_after();
               uint32_t bt = smem_u32(b_st + st * kHcB);
-              umma_k64(d0, ahi + r0, bt, idesc, !first);
-              umma_k64(d1, ahi + r1, bt, idesc, !first);
-              if (kPasses == 3) {
-                umma_k64(d0, alo + r0, bt, idesc, true);
-                umma_k64(d1, alo + r1, bt, idesc, true);
+              if (leader) {
+                umma_k64(d0, ahi + r0, bt, idesc, !first);
+                umma_k64(d1, ahi + r1, bt, idesc, !first);
+                if (kPasses == 3) {
+                  umma_k64(d0, alo + r0, bt, idesc, true);
+                  umma_k64(d1, alo + r1, bt, idesc, true);
+                }
+                umma_commit(bars + HB_EMPTY + st);
               }
-              umma_commit(bars + HB_EMPTY + st);
+              __syncwarp();
               if (++st == kHcBStages) { st = 0; ph ^= 1; }
               if (kPasses == 3) {
                 mbar_wait(bars + HB_FULL + st, ph);
                 tc_fence_after();
                 bt = smem_u32(b_st + st * kHcB);
-                umma_k64(d0, ahi + r0, bt, idesc, true);
-                umma_k64(d1, ahi + r1, bt, idesc, true);
-                umma_commit(bars + HB_EMPTY + st);
+                if (leader) {
+                  umma_k64(d0, ahi + r0, bt, idesc, true);
+                  umma_k64(d1, ahi + r1, bt, idesc, true);
+                  umma_commit(bars + HB_EMPTY + st);
+                }
+                __syncwarp();
                 if (++st == kHcBStages) { st = 0; ph ^= 1; }
               }
             }
-            if (dx == 1) {        // last tap of a filter row: segment dy + 1 is not read again (dy = +1: nor is segment 3)
+            if (dx == 1 && leader) {   // last tap of a filter row: segment dy + 1 is not read again (dy = +1: nor is segment 3)
               umma_commit(bars + HA_EMPTY + dy + 1);
               if (dy == 1) umma_commit(bars + HA_EMPTY + 3);
             }
           }
         }
-        umma_commit(bars + HACC_FULL + set);
+        if (leader) umma_commit(bars + HACC_FULL + set);
+        __syncwarp();
       }
     }
   } else {

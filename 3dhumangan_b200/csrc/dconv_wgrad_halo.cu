@@ -181,8 +181,10 @@ __global__ void __launch_bounds__(kWhThreads, 1) conv3x3_wgrad_halo_kernel(WgHal
       if (sub == 0) a.part_b[static_cast<long>(blockIdx.x) * 128 + rsub + 32 * i] = v;
     }
   } else if (warp == 12) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer: the warp walks the loops, one elected lane
+    // issues (umma.cuh: elect_one_sync)
+    {
+      const bool leader = elect_one_sync();
       const uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 16);          // B operand MN-major
       const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo);
       uint32_t xbase = 0, xwaited = 0, dcnt = 0;
@@ -207,24 +209,24 @@ __global__ void __launch_bounds__(kWhThreads, 1) conv3x3_wgrad_halo_kernel(WgHal
               for (uint32_t ks = 0; ks < 4; ++ks) {
                 const uint64_t da_h = umma_desc_sw128(ah) + 2 * ks, da_l = umma_desc_sw128(al) + 2 * ks;
                 const uint64_t db_h = umma_desc_sw128(xh + brow + ks * 2048u), db_l = umma_desc_sw128(xl + brow + ks * 2048u);
-                umma_bf16(d, da_h, db_h, idesc, (started || ks > 0) ? 1u : 0u);
+                umma_bf16_if(leader, d, da_h, db_h, idesc, (started || ks > 0) ? 1u : 0u);
                 if (kPasses == 3) {
-                  umma_bf16(d, da_l, db_h, idesc, 1u);
-                  umma_bf16(d, da_h, db_l, idesc, 1u);
+                  umma_bf16_if(leader, d, da_l, db_h, idesc, 1u);
+                  umma_bf16_if(leader, d, da_h, db_l, idesc, 1u);
                 }
               }
             }
             started = true;
-            umma_commit(bars + WD_EMPTY + buf);
+            umma_commit_if(leader, bars + WD_EMPTY + buf);
           }
-          umma_commit(bars + WX_EMPTY + ((xbase + i) & 3));      // input row y-1 is not needed below this output row
+          umma_commit_if(leader, bars + WX_EMPTY + ((xbase + i) & 3));      // input row y-1 is not needed below this output row
         }
         // the last two ring entries of the unit (rows y0+S-1, y0+S) are free once its MMAs have completed
-        umma_commit(bars + WX_EMPTY + ((xbase + S) & 3));
-        umma_commit(bars + WX_EMPTY + ((xbase + S + 1) & 3));
+        umma_commit_if(leader, bars + WX_EMPTY + ((xbase + S) & 3));
+        umma_commit_if(leader, bars + WX_EMPTY + ((xbase + S + 1) & 3));
         xbase += S + 2;
       }
-      umma_commit(bars + WH_DONE);
+      umma_commit_if(leader, bars + WH_DONE);
     }
   } else {
     // ------------------------------------------------------------------ epilogue (once, at the end)

@@ -150,7 +150,8 @@ linear_kernel(const float* __restrict__ X, int ldx, int M, int K, const uint8_t*
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {      // the warp walks the loops, one elected lane issues (umma.cuh: elect_one_sync)
+      const bool leader = elect_one_sync();
       const uint32_t idesc = umma_idesc_bf16(128, Nb);
       uint32_t st = 0, ph = 0, acc_use = 0, it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -164,22 +165,22 @@ linear_kernel(const float* __restrict__ X, int ldx, int M, int K, const uint8_t*
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(b_full + st, ph);
             tc_fence_after();
-            umma_k64(d, smem_u32(a_hi + kc * kChunkBytesA), smem_u32(b_st + st * kStageBytesB), idesc, kc > 0);
+            umma_k64_if(leader, d, smem_u32(a_hi + kc * kChunkBytesA), smem_u32(b_st + st * kStageBytesB), idesc, kc > 0);
             if (kPasses == 3)
-              umma_k64(d, smem_u32(a_lo + kc * kChunkBytesA), smem_u32(b_st + st * kStageBytesB), idesc, true);
-            umma_commit(b_empty + st);
+              umma_k64_if(leader, d, smem_u32(a_lo + kc * kChunkBytesA), smem_u32(b_st + st * kStageBytesB), idesc, true);
+            umma_commit_if(leader, b_empty + st);
             if (++st == kLinStages) { st = 0; ph ^= 1; }
             if (kPasses == 3) {
               mbar_wait(b_full + st, ph);
               tc_fence_after();
-              umma_k64(d, smem_u32(a_hi + kc * kChunkBytesA), smem_u32(b_st + st * kStageBytesB), idesc, true);
-              umma_commit(b_empty + st);
+              umma_k64_if(leader, d, smem_u32(a_hi + kc * kChunkBytesA), smem_u32(b_st + st * kStageBytesB), idesc, true);
+              umma_commit_if(leader, b_empty + st);
               if (++st == kLinStages) { st = 0; ph ^= 1; }
             }
           }
-          umma_commit(acc_full + buf);
+          umma_commit_if(leader, acc_full + buf);
         }
-        umma_commit(a_empty);
+        umma_commit_if(leader, a_empty);
       }
     }
   } else {

@@ -125,19 +125,19 @@ __device__ __forceinline__ float transpose_reduce32r(float (&v)[32], int lane) {
 }
 
 template <int kPasses>
-__device__ __forceinline__ void ren_mma_chunk(const RenSmem& m, uint32_t& st, uint32_t& ph, uint32_t tmem_d,
+__device__ __forceinline__ void ren_mma_chunk(const RenSmem& m, bool leader, uint32_t& st, uint32_t& ph, uint32_t tmem_d,
                                               uint32_t a_hi, uint32_t a_lo, uint32_t idesc, bool accumulate) {
   mbar_wait(m.bars + RB_FULL + st, ph);
   tc_fence_after();
-  umma_k64(tmem_d, a_hi, smem_u32(m.b_st + st * kRB), idesc, accumulate);
-  if (kPasses == 3) umma_k64(tmem_d, a_lo, smem_u32(m.b_st + st * kRB), idesc, true);
-  umma_commit(m.bars + RB_EMPTY + st);
+  umma_k64_if(leader, tmem_d, a_hi, smem_u32(m.b_st + st * kRB), idesc, accumulate);
+  if (kPasses == 3) umma_k64_if(leader, tmem_d, a_lo, smem_u32(m.b_st + st * kRB), idesc, true);
+  umma_commit_if(leader, m.bars + RB_EMPTY + st);
   if (++st == kRenStages) { st = 0; ph ^= 1; }
   if (kPasses == 3) {
     mbar_wait(m.bars + RB_FULL + st, ph);
     tc_fence_after();
-    umma_k64(tmem_d, a_hi, smem_u32(m.b_st + st * kRB), idesc, true);
-    umma_commit(m.bars + RB_EMPTY + st);
+    umma_k64_if(leader, tmem_d, a_hi, smem_u32(m.b_st + st * kRB), idesc, true);
+    umma_commit_if(leader, m.bars + RB_EMPTY + st);
     if (++st == kRenStages) { st = 0; ph ^= 1; }
   }
 }
@@ -445,7 +445,8 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
       }
     }
   } else if (warp == 8) {
-    if (lane == 0) {
+    {      // the warp walks the loops, one elected lane issues (umma.cuh: elect_one_sync)
+      const bool leader = elect_one_sync();
       const uint32_t idesc = umma_idesc_bf16(128, 256);
       uint32_t st = 0, ph = 0;
       uint32_t aph[4] = {0, 0, 0, 0};
@@ -459,29 +460,29 @@ __global__ void __launch_bounds__(kRenThreads, 1) render_mlp_kernel(RenderArgs a
       for (int it = 0; it < my_tiles; ++it) {
         // L0: coord -> A, geo -> B (both read operand chunk 0)
         wait_a(0);
-        ren_mma_chunk<kPasses>(m, st, ph, accA, A_hi(0), A_lo(0), idesc, false);
-        ren_mma_chunk<kPasses>(m, st, ph, accB, A_hi(0), A_lo(0), idesc, false);
-        umma_commit(m.bars + RL_FULL);
+        ren_mma_chunk<kPasses>(m, leader, st, ph, accA, A_hi(0), A_lo(0), idesc, false);
+        ren_mma_chunk<kPasses>(m, leader, st, ph, accB, A_hi(0), A_lo(0), idesc, false);
+        umma_commit_if(leader, m.bars + RL_FULL);
         // L1a: a x Wn0[:, :256] -> A
         for (int kc = 0; kc < 4; ++kc) {
           wait_a(kc);
-          ren_mma_chunk<kPasses>(m, st, ph, accA, A_hi(kc), A_lo(kc), idesc, kc > 0);
+          ren_mma_chunk<kPasses>(m, leader, st, ph, accA, A_hi(kc), A_lo(kc), idesc, kc > 0);
         }
-        umma_commit(m.bars + RL_FULL);
+        umma_commit_if(leader, m.bars + RL_FULL);
         // L1b: g x Wn0[:, 256:] -> A (accumulate)
         for (int kc = 0; kc < 4; ++kc) {
           wait_a(kc);
-          ren_mma_chunk<kPasses>(m, st, ph, accA, A_hi(kc), A_lo(kc), idesc, true);
+          ren_mma_chunk<kPasses>(m, leader, st, ph, accA, A_hi(kc), A_lo(kc), idesc, true);
         }
-        umma_commit(m.bars + RL_FULL);
+        umma_commit_if(leader, m.bars + RL_FULL);
         // network.1, .2, .3, color, feature: B, A, B, A, B
         for (int l = 0; l < 5; ++l) {
           const uint32_t acc = (l & 1) ? accA : accB;
           for (int kc = 0; kc < 4; ++kc) {
             wait_a(kc);
-            ren_mma_chunk<kPasses>(m, st, ph, acc, A_hi(kc), A_lo(kc), idesc, kc > 0);
+            ren_mma_chunk<kPasses>(m, leader, st, ph, acc, A_hi(kc), A_lo(kc), idesc, kc > 0);
           }
-          umma_commit(m.bars + RL_FULL);
+          umma_commit_if(leader, m.bars + RL_FULL);
         }
       }
     }

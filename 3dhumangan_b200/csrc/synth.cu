@@ -243,20 +243,21 @@ struct MmaPipe {
 };
 
 // One K=64 chunk of a 3-pass (or 1-pass) product against the next weight stage(s).
+// `leader`: the elected lane of the (converged) MMA warp -- the whole warp walks the issue loops (umma.cuh: elect_one_sync).
 template <int kPasses>
-__device__ __forceinline__ void mma_chunk(const SynSmem& m, MmaPipe& p, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
+__device__ __forceinline__ void mma_chunk(const SynSmem& m, MmaPipe& p, bool leader, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
                                           uint32_t idesc, bool accumulate) {
   mbar_wait(m.bars + B_FULL + p.st, p.ph);
   tc_fence_after();
-  umma_k64(tmem_d, a_hi, smem_u32(m.b_st + p.st * kBStage), idesc, accumulate);
-  if (kPasses == 3) umma_k64(tmem_d, a_lo, smem_u32(m.b_st + p.st * kBStage), idesc, true);
-  umma_commit(m.bars + B_EMPTY + p.st);
+  umma_k64_if(leader, tmem_d, a_hi, smem_u32(m.b_st + p.st * kBStage), idesc, accumulate);
+  if (kPasses == 3) umma_k64_if(leader, tmem_d, a_lo, smem_u32(m.b_st + p.st * kBStage), idesc, true);
+  umma_commit_if(leader, m.bars + B_EMPTY + p.st);
   if (++p.st == kSynStages) { p.st = 0; p.ph ^= 1; }
   if (kPasses == 3) {
     mbar_wait(m.bars + B_FULL + p.st, p.ph);
     tc_fence_after();
-    umma_k64(tmem_d, a_hi, smem_u32(m.b_st + p.st * kBStage), idesc, true);
-    umma_commit(m.bars + B_EMPTY + p.st);
+    umma_k64_if(leader, tmem_d, a_hi, smem_u32(m.b_st + p.st * kBStage), idesc, true);
+    umma_commit_if(leader, m.bars + B_EMPTY + p.st);
     if (++p.st == kSynStages) { p.st = 0; p.ph ^= 1; }
   }
 }
@@ -702,7 +703,8 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
       epilogue_team_loop(a, m, tm, tmem, warp - 8, lane);
     }
   } else if (warp == 12) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one_sync();
       const uint32_t idesc = umma_idesc_bf16(128, 256);
       MmaPipe p;
       uint32_t acnt = 0;
@@ -714,11 +716,11 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
           const uint32_t slot = acnt & 1;
           mbar_wait_sleep(m.bars + A_FULL + slot, (acnt >> 1) & 1);
           tc_fence_after();
-          mma_chunk<kPasses>(m, p, tmem + buf * 256, smem_u32(m.a_hi + slot * kAChunk), smem_u32(m.a_lo + slot * kAChunk),
+          mma_chunk<kPasses>(m, p, leader, tmem + buf * 256, smem_u32(m.a_hi + slot * kAChunk), smem_u32(m.a_lo + slot * kAChunk),
                              idesc, kc > 0);
-          umma_commit(m.bars + A_EMPTY + slot);
+          umma_commit_if(leader, m.bars + A_EMPTY + slot);
         }
-        umma_commit(m.bars + ACC_FULL + buf);
+        umma_commit_if(leader, m.bars + ACC_FULL + buf);
       }
     }
   } else if (warp == 13) {
@@ -871,7 +873,8 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
   } else if (warp < 12) {
     epilogue_team_loop(a, m, tm, tmem, warp - 8, lane);
   } else if (warp == 12) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one_sync();
       const uint32_t idesc = umma_idesc_bf16(128, 256);
       MmaPipe p;
       uint32_t acnt = 0;
@@ -883,13 +886,13 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
         tc_fence_after();
         // gamma|beta of channels 0..127 -> half R: free since the previous tile read its chunks 2,3 from it
         // (that tile's A_FULL arrivals for chunks 2,3 precede this tile's A1_FULL)
-        for (int kc = 0; kc < 2; ++kc) mma_chunk<kPasses>(m, p, tmem + R, a1_hi(kc), a1_lo(kc), idesc, kc > 0);
-        umma_commit(m.bars + G1A_FULL);
+        for (int kc = 0; kc < 2; ++kc) mma_chunk<kPasses>(m, p, leader, tmem + R, a1_hi(kc), a1_lo(kc), idesc, kc > 0);
+        umma_commit_if(leader, m.bars + G1A_FULL);
         // gamma|beta of channels 128..255 -> half R': holds the previous tile's conv accumulator until drained
         if (it > 0) mbar_wait_sleep(m.bars + ACC_EMPTY + ((it - 1) & 1), ((it - 1) >> 1) & 1);
         tc_fence_after();
-        for (int kc = 0; kc < 2; ++kc) mma_chunk<kPasses>(m, p, tmem + Rp, a1_hi(kc), a1_lo(kc), idesc, kc > 0);
-        umma_commit(m.bars + G1B_FULL);
+        for (int kc = 0; kc < 2; ++kc) mma_chunk<kPasses>(m, p, leader, tmem + Rp, a1_hi(kc), a1_lo(kc), idesc, kc > 0);
+        umma_commit_if(leader, m.bars + G1B_FULL);
         // conv -> half R: y chunks 0 and 1 must BOTH exist first (their gamma/beta live in R)
         const uint32_t ph0 = (acnt >> 1) & 1;
         mbar_wait_sleep(m.bars + A_FULL + 0, ph0);
@@ -901,10 +904,10 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
             mbar_wait_sleep(m.bars + A_FULL + slot, (acnt >> 1) & 1);
             tc_fence_after();
           }
-          mma_chunk<kPasses>(m, p, tmem + R, smem_u32(m.a_hi + slot * kAChunk), smem_u32(m.a_lo + slot * kAChunk), idesc, kc > 0);
-          umma_commit(m.bars + A_EMPTY + slot);
+          mma_chunk<kPasses>(m, p, leader, tmem + R, smem_u32(m.a_hi + slot * kAChunk), smem_u32(m.a_lo + slot * kAChunk), idesc, kc > 0);
+          umma_commit_if(leader, m.bars + A_EMPTY + slot);
         }
-        umma_commit(m.bars + ACC_FULL + (it & 1));
+        umma_commit_if(leader, m.bars + ACC_FULL + (it & 1));
       }
     }
   } else if (warp == 13) {

@@ -25,7 +25,7 @@
 namespace hg {
 
 constexpr int kWC = 256;
-constexpr int kWgThreads = 512;                 // 16 operand warps; lane 0 of warp 0 also issues the MMAs
+constexpr int kWgThreads = 512;                 // 16 operand warps; warp 0 also issues the MMAs (one elected lane)
 constexpr uint32_t kWgImg = 256 * 128;          // [256 rows x 64 px] bf16 = 32 KB
 // dout image (hi, lo) double-buffered, x image (hi, lo) single: 6 x 32 KB
 constexpr uint32_t kWgSmemBytes = 6 * kWgImg + 8 * 8 + 16 + 1024;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
   const int nchunks = 2 * count;
   const int nq = a.nq, HW = a.HW;
   const int nst = nq >> 6;                    // row steps of the x operand: 4 (256 rows) or 2 (128)
-  const bool issuer = threadIdx.x == 0;
+  const bool leader = warp == 0 && elect_one_sync();     // warp-uniform condition first: only warp 0 executes the elect
   const uint32_t idesc = umma_idesc_bf16(128, nq);
 
   const int sub = threadIdx.x & 7;            // which 8-pixel group of the 64-pixel chunk
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + WG_FULL);
-      if (issuer) {
+      if (warp == 0) {      // the whole warp waits; its elected lane issues (convergent code: descriptors in uniform registers)
         mbar_wait_sleep(bars + WG_FULL, c & 1);
         tc_fence_after();
         const uint32_t ah0 = smem_u32(a_img + (c & 1) * 2 * kWgImg), al0 = ah0 + kWgImg;
@@ -202,16 +202,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
         for (uint32_t mh = 0; mh < 2; ++mh) {
           const uint32_t d = tmem + mh * 256;
           const uint32_t ah = ah0 + mh * (kWgImg / 2), al = al0 + mh * (kWgImg / 2);
-          umma_k64(d, ah, smem_u32(b_hi), idesc, c > 0);
+          umma_k64_if(leader, d, ah, smem_u32(b_hi), idesc, c > 0);
           if (kPasses == 3) {
-            umma_k64(d, al, smem_u32(b_hi), idesc, true);
-            umma_k64(d, ah, smem_u32(b_lo), idesc, true);
+            umma_k64_if(leader, d, al, smem_u32(b_hi), idesc, true);
+            umma_k64_if(leader, d, ah, smem_u32(b_lo), idesc, true);
           }
         }
-        umma_commit(bars + WG_EMPTY);
-        if (c + 1 == nchunks) umma_commit(bars + WG_DONE);
+        umma_commit_if(leader, bars + WG_EMPTY);
+        if (c + 1 == nchunks) umma_commit_if(leader, bars + WG_DONE);
       }
-      __syncwarp();
       if (c + 1 < nchunks) {
         convert_d(c + 1);
         if (c + 2 < nchunks) load_d(c + 2);

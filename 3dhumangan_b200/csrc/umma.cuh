@@ -173,11 +173,51 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One leader lane of a CONVERGED warp (the same lane every call).  Loops that issue tcgen05.mma belong in convergent code with
+// only the issue itself under `if (leader)`: inside a divergent `if (lane == 0)` region every descriptor lives in vector
+// registers and each MMA pays ~5 R2UR + predicate shuffling (measured 17.5 instructions per MMA in the haloed convolution).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // mbarrier arrives once every MMA issued so far by this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// Predicated forms for issue loops that the WHOLE warp walks (see elect_one_sync): no branch around the instruction.
+__device__ __forceinline__ void umma_bf16_if(bool leader, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(leader))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(bool leader, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(static_cast<uint32_t>(leader))
+      : "memory");
+}
+__device__ __forceinline__ void umma_k64_if(bool leader, uint32_t tmem_d, uint32_t a_tile, uint32_t b_tile, uint32_t idesc,
+                                            bool accumulate) {
+  const uint64_t da = umma_desc_sw128(a_tile);
+  const uint64_t db = umma_desc_sw128(b_tile);
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) umma_bf16_if(leader, tmem_d, da + 2 * k, db + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
 }
 
 // One K-chunk of 64: four K=16 MMAs.  a_tile / b_tile: shared addresses of [rows x 64] SW128 tiles.
