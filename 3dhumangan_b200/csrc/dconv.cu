@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(kDcThreads, 1) conv_kernel(ConvArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // LeakyReLU in front of the convolution as max(v, slope * v), slope 1 = none: no run-time flag inside the unrolled loops
+  const float lslope = a.pre_lrelu ? 0.2f : 1.f;
   for (int i = threadIdx.x; i < 512; i += blockDim.x) tab_bias[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bars + DA_FULL + i, 8); mbar_init(bars + DA_EMPTY + i, 1); }
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(kDcThreads, 1) conv_kernel(ConvArgs a) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float v = in ? cur[g * 8 + j] : 0.f;
-            if (a.pre_lrelu) v = v > 0.f ? v : 0.2f * v;
+            v = fmaxf(v, lslope * v);
             y[j] = v;
           }
           store_a8<kPasses == 3>(a_hi + slot * kDcA, a_lo + slot * kDcA, row, h * 32 + g * 8, y);

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // LeakyReLU in front of the convolution as max(v, slope * v), slope 1 = none: no run-time flag inside the unrolled loops
+  const float lslope = a.pre_lrelu ? 0.2f : 1.f;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) tab_bias[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bars + HA_FULL + i, 8); mbar_init(bars + HA_EMPTY + i, 1); }
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float val = ok ? cur[g * 8 + j] : 0.f;
-              if (a.pre_lrelu) val = val > 0.f ? val : 0.2f * val;
+              val = fmaxf(val, lslope * val);
               y[j] = val;
             }
             store_a8<kPasses == 3>(a_hi, a_lo, row, half * 32 + (bi & 1) * 16 + g * 8, y);
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kHcThreads, 1) conv3x3_halo_kernel(HaloArgs a)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float val = hok ? hv[j] : 0.f;
-              if (a.pre_lrelu) val = val > 0.f ? val : 0.2f * val;
+              val = fmaxf(val, lslope * val);
               y[j] = val;
             }
             store_a8<kPasses == 3>(a_hi, a_lo, s * kHcSeg + (hside ? kHcSeg - 1 : 0), hg8 * 8, y);

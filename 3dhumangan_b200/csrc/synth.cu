@@ -673,11 +673,7 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = sin_red(fmaf(cur[g * 8 + j], t1[j], t0[j]));
           } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float v = fmaf(cur[g * 8 + j], t1[j], t0[j]);
-              y[j] = v > 0.f ? v : slope * v;
-            }
+            affine_lrelu8(cur + g * 8, t1, t0, slope, y);
           }
           if (!valid) {   // only the last, partial tile of an image
 #pragma unroll
@@ -860,7 +856,8 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
             const float gam = __uint_as_float(gr[jj]) + bg[j];        // 1 + gamma
             const float bet = __uint_as_float(br[jj]) + bb[j];        // beta
             const float xn = fmaf(cur[jj], t1[j], t0[j]);
-            y[j] = valid ? lrelu02(fmaf(xn, gam, bet)) : 0.f;
+            const float v = fmaf(xn, gam, bet);
+            y[j] = valid ? fmaxf(v, 0.2f * v) : 0.f;
           }
           store_a8<kPasses == 3>(m.a_hi + slot * kAChunk, m.a_lo + slot * kAChunk, row, h * 32 + g * 8, y);
         }

@@ -168,10 +168,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) spade_wgrad_kernel(WgradArgs a)
         }
         float y[8] = {vb[2 * st].x, vb[2 * st].y, vb[2 * st].z, vb[2 * st].w,
                       vb[2 * st + 1].x, vb[2 * st + 1].y, vb[2 * st + 1].z, vb[2 * st + 1].w};
+        if (kAct == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float pre = fmaf(y[j], g1, g0);
-          y[j] = kAct == 1 ? wg_sin(pre) : (kAct == 2 ? pre : (pre > 0.f ? pre : 0.2f * pre));
+          for (int j = 0; j < 8; ++j) y[j] = wg_sin(fmaf(y[j], g1, g0));
+        } else {      // packed fp32 on pixel pairs: affine (+ LeakyReLU as max(v, 0.2 v))
+          const float2 g1p = make_float2(g1, g1), g0p = make_float2(g0, g0);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float2 v = __ffma2_rn(make_float2(y[j], y[j + 1]), g1p, g0p);
+            if (kAct == 2) {
+              y[j] = v.x;
+              y[j + 1] = v.y;
+            } else {
+              const float2 sv = __fmul2_rn(v, make_float2(0.2f, 0.2f));
+              y[j] = fmaxf(v.x, sv.x);
+              y[j + 1] = fmaxf(v.y, sv.y);
+            }
+          }
         }
         if (nvalid < 8) {
 #pragma unroll

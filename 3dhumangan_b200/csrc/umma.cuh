@@ -238,14 +238,32 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 3) ^ row) & 7u) << 4) + ((k & 7u) << 1);
 }
 
-// split two fp32 into (hi, lo) bf16x2 pairs: x ~= hi + lo with |lo| <= 2^-9 |hi|
+// split two fp32 into (hi, lo) bf16x2 pairs: x ~= hi + lo with |lo| <= 2^-9 |hi|.  The residual x - float(hi) is one packed
+// FFMA2 (hi * -1 + x: a single rounding, the same value as the subtraction), the unpack a shift and a mask: 5 instructions per
+// pair instead of 6 -- the operand producers of every kernel run this once per element pair and are issue / power bound.
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-  float r0 = x0 - __bfloat162float(h.x);
-  float r1 = x1 - __bfloat162float(h.y);
-  __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
-  hi = *reinterpret_cast<uint32_t*>(&h);
+  const uint32_t hb = *reinterpret_cast<uint32_t*>(&h);
+  const float2 hf = make_float2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xffff0000u));
+  const float2 r = __ffma2_rn(hf, make_float2(-1.f, -1.f), make_float2(x0, x1));
+  __nv_bfloat162 l = __floats2bfloat162_rn(r.x, r.y);
+  hi = hb;
   lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// y[j] = LeakyReLU_slope(x[j] * g1[j] + g0[j]) for 8 values on packed fp32 (FFMA2 / FMUL2 + FMNMX): max(v, slope * v) is the
+// LeakyReLU for 0 <= slope <= 1 (0.2, the identity 1 and ReLU 0 are the slopes this library uses), bit-identical to the
+// compare-and-select form for every finite and infinite v (and NaN stays NaN).
+__device__ __forceinline__ void affine_lrelu8(const float* __restrict__ x, const float (&g1)[8], const float (&g0)[8], float slope,
+                                              float (&y)[8]) {
+  const float2 sl = make_float2(slope, slope);
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const float2 v = __ffma2_rn(make_float2(x[j], x[j + 1]), make_float2(g1[j], g1[j + 1]), make_float2(g0[j], g0[j + 1]));
+    const float2 s = __fmul2_rn(v, sl);
+    y[j] = fmaxf(v.x, s.x);
+    y[j + 1] = fmaxf(v.y, s.y);
+  }
 }
 
 // Write 8 consecutive-k fp32 values (k0 % 8 == 0) of one row into the hi (and lo) operand tiles.
