@@ -342,7 +342,7 @@ __device__ __forceinline__ void epilogue_team_variant(const SpadeArgs& a, const 
     float* const orow = outp + (static_cast<long>(b) * tm.T + ti) * cout * 128 + row;
     mbar_wait_sleep(m.bars + ACC_FULL + buf, (it >> 1) & 1);
     tc_fence_after();
-    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    float2 r0 = make_float2(0.f, 0.f), r1 = r0, r2 = r0;
 #pragma unroll 1
     for (int cg = 0; cg < ncg; ++cg) {
       const int c0 = cg * 32;
@@ -366,10 +366,12 @@ __device__ __forceinline__ void epilogue_team_variant(const SpadeArgs& a, const 
         float bs[8];
         lds8(tbias + (c0 + g * 8) * 4, bs);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+        for (int jj = 0; jj < 8; jj += 2) {      // packed fp32 adds on channel pairs (same operations, half the instructions)
           const int j = g * 8 + jj;
-          v[j] = __uint_as_float(raw[j]) + bs[jj];
-          if (kSkip) v[j] += sk[j];
+          float2 p = __fadd2_rn(make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])), make_float2(bs[jj], bs[jj + 1]));
+          if (kSkip) p = __fadd2_rn(p, make_float2(sk[j], sk[j + 1]));
+          v[j] = p.x;
+          v[j + 1] = p.y;
         }
       }
       float* const o = orow + c0 * 128;
@@ -391,10 +393,11 @@ __device__ __forceinline__ void epilogue_team_variant(const SpadeArgs& a, const 
           lds8(trgb + (kC + c0 + g * 8) * 4, w1);
           lds8(trgb + (2 * kC + c0 + g * 8) * 4, w2);
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            r0 = fmaf(v[g * 8 + jj], w0[jj], r0);
-            r1 = fmaf(v[g * 8 + jj], w1[jj], r1);
-            r2 = fmaf(v[g * 8 + jj], w2[jj], r2);
+          for (int jj = 0; jj < 8; jj += 2) {      // even / odd channels in the two lanes of a packed accumulator
+            const float2 vv = make_float2(v[g * 8 + jj], v[g * 8 + jj + 1]);
+            r0 = __ffma2_rn(vv, make_float2(w0[jj], w0[jj + 1]), r0);
+            r1 = __ffma2_rn(vv, make_float2(w1[jj], w1[jj + 1]), r1);
+            r2 = __ffma2_rn(vv, make_float2(w2[jj], w2[jj + 1]), r2);
           }
         }
       }
@@ -411,18 +414,15 @@ __device__ __forceinline__ void epilogue_team_variant(const SpadeArgs& a, const 
 #pragma unroll
           for (int j = 0; j < 32; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + (lane * 33 + j) * 4), "f"(v[j]) : "memory");
           __syncwarp();
-          float ta = 0.f, tb = 0.f, qa = 0.f, qb = 0.f;      // two chains each: the loop is latency bound on one
+          float2 ts = make_float2(0.f, 0.f), qs = make_float2(0.f, 0.f);      // two chains each, as one packed pair
 #pragma unroll
           for (int r = 0; r < 32; r += 2) {
-            const float x0 = lds_f32(scratch + (r * 33 + lane) * 4);
-            const float x1 = lds_f32(scratch + ((r + 1) * 33 + lane) * 4);
-            ta += x0;
-            tb += x1;
-            qa = fmaf(x0, x0, qa);
-            qb = fmaf(x1, x1, qb);
+            const float2 x = make_float2(lds_f32(scratch + (r * 33 + lane) * 4), lds_f32(scratch + ((r + 1) * 33 + lane) * 4));
+            ts = __fadd2_rn(ts, x);
+            qs = __ffma2_rn(x, x, qs);
           }
-          t1 = ta + tb;
-          t2 = qa + qb;
+          t1 = ts.x + ts.y;
+          t2 = qs.x + qs.y;
         }
         atomicAdd(m.st_sum + c0 + lane, t1);
         atomicAdd(m.st_sq + c0 + lane, t2);
@@ -432,7 +432,7 @@ __device__ __forceinline__ void epilogue_team_variant(const SpadeArgs& a, const 
     __syncwarp();
     if (lane == 0) mbar_arrive(m.bars + ACC_EMPTY + buf);
     if (kRgb && valid) {   // this thread saw all 256 channels of its pixel
-      const float r[3] = {r0, r1, r2};
+      const float r[3] = {r0.x + r0.y, r1.x + r1.y, r2.x + r2.y};
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const long idx = (static_cast<long>(b) * 3 + j) * HW + pix;
@@ -569,15 +569,28 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
           lds8(trk + (2 * kC + c0 + g * 8) * 4, k2);
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+        for (int jj = 0; jj < 8; jj += 2) {      // channel pairs on packed fp32 (same operations)
           const int j = g * 8 + jj;
-          const float pre = fmaf(xs_[j], t1[jj], t0[jj]);
-          float acc = __uint_as_float(raw[j]);      // 0 for rows past the image (their operand rows are zero)
-          if (kRk) acc = fmaf(rv2, k2[jj], fmaf(rv1, k1[jj], fmaf(rv0, k0[jj], acc)));
-          const float d = acc * (kSine ? cos_red(pre) : (pre > 0.f ? 1.f : mslope));
-          if (!kPm && valid) o[j * 128] = d;
-          v[j] = d;
-          w[j] = d * xs_[j];
+          const float2 x2 = make_float2(xs_[j], xs_[j + 1]);
+          const float2 pre = __ffma2_rn(x2, make_float2(t1[jj], t1[jj + 1]), make_float2(t0[jj], t0[jj + 1]));
+          float2 acc = make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]));   // 0 for rows past the image
+          if (kRk) {
+            const float2 a0 = make_float2(rv0, rv0), a1 = make_float2(rv1, rv1), a2 = make_float2(rv2, rv2);
+            acc = __ffma2_rn(a2, make_float2(k2[jj], k2[jj + 1]),
+                             __ffma2_rn(a1, make_float2(k1[jj], k1[jj + 1]), __ffma2_rn(a0, make_float2(k0[jj], k0[jj + 1]), acc)));
+          }
+          const float2 mask = kSine ? make_float2(cos_red(pre.x), cos_red(pre.y))
+                                    : make_float2(pre.x > 0.f ? 1.f : mslope, pre.y > 0.f ? 1.f : mslope);
+          const float2 d = __fmul2_rn(acc, mask);
+          const float2 dx = __fmul2_rn(d, x2);
+          if (!kPm && valid) {
+            o[j * 128] = d.x;
+            o[(j + 1) * 128] = d.y;
+          }
+          v[j] = d.x;
+          v[j + 1] = d.y;
+          w[j] = dx.x;
+          w[j + 1] = dx.y;
         }
       }
       if (kPm && valid) {
