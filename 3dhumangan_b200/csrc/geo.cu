@@ -210,6 +210,13 @@ struct GeoArgs {
 
 constexpr int kGeoThreads = 512;
 
+// value barrier for a packed fp32 pair: keeps ptxas from contracting a packed product with the packed sum that follows
+__device__ __forceinline__ float2 keep2(float2 v) {
+  unsigned long long u = (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x);
+  asm volatile("" : "+l"(u));
+  return make_float2(__uint_as_float(static_cast<uint32_t>(u)), __uint_as_float(static_cast<uint32_t>(u >> 32)));
+}
+
 __global__ void __launch_bounds__(kGeoThreads, 1) geo_kernel(GeoArgs a) {
   extern __shared__ float4 sv[];  // [Vn] posed vertices (x,y,z,index), then [M][2] cluster boxes
   __shared__ float sk[kJoints * 3];
@@ -219,7 +226,17 @@ __global__ void __launch_bounds__(kGeoThreads, 1) geo_kernel(GeoArgs a) {
   const int M = a.sorted ? a.Vp / kCluster : 0;
   float4* sbox = sv + Vn;
   if (a.sorted) {
-    for (int v = threadIdx.x; v < Vn; v += blockDim.x) sv[v] = a.sorted[static_cast<long>(b) * Vn + v];
+    // pair layout for the packed-fp32 distance loop: vertices 2p, 2p+1 -> sv[2p] = (x0, x1, y0, y1), sv[2p+1] = (z0, z1, i0, i1)
+    // (Vp is a multiple of the cluster size 32)
+    for (int v = threadIdx.x; v < Vn; v += blockDim.x) {
+      const float4 q = a.sorted[static_cast<long>(b) * Vn + v];
+      float* pr = reinterpret_cast<float*>(sv + (v & ~1));
+      const int e = v & 1;
+      pr[0 + e] = q.x;
+      pr[2 + e] = q.y;
+      pr[4 + e] = q.z;
+      pr[6 + e] = q.w;
+    }
     for (int v = threadIdx.x; v < 2 * M; v += blockDim.x) sbox[v] = a.boxes[static_cast<long>(b) * 2 * M + v];
   } else {
     for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
@@ -283,9 +300,27 @@ __global__ void __launch_bounds__(kGeoThreads, 1) geo_kernel(GeoArgs a) {
 #pragma unroll 4
       for (int v = 0; v < Vn; ++v) consider(sv[v]);
     } else {
+      // two vertices per step on packed fp32 (FFMA2 / FMUL2 / FADD2 lanes are the same IEEE operations as the scalar ones:
+      // p - q as fma(q, -1, p) rounds the exact difference once, like the subtraction; products and sums are NOT contracted),
+      // candidates still examined in index order: bit-identical distances and the same tie-breaking as `consider`
+      const float2 px2 = make_float2(px, px), py2 = make_float2(py, py), pz2 = make_float2(pz, pz), neg1 = make_float2(-1.f, -1.f);
+      auto consider2 = [&](const float4 xy, const float4 zw) {
+        const float2 ex = __ffma2_rn(make_float2(xy.x, xy.y), neg1, px2);
+        const float2 ey = __ffma2_rn(make_float2(xy.z, xy.w), neg1, py2);
+        const float2 ez = __ffma2_rn(make_float2(zw.x, zw.y), neg1, pz2);
+        // ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it never does that to the scalar .rn forms): the products go
+        // through an opaque register so that they are rounded before the sums, as in the oracle
+        const float2 d2 = __fadd2_rn(__fadd2_rn(keep2(__fmul2_rn(ex, ex)), keep2(__fmul2_rn(ey, ey))), keep2(__fmul2_rn(ez, ez)));
+        const int v0 = __float_as_int(zw.z), v1 = __float_as_int(zw.w);
+        if (d2.x < best || (d2.x == best && v0 < bi)) { best = d2.x; bi = v0; }
+        if (d2.y < best || (d2.y == best && v1 < bi)) { best = d2.y; bi = v1; }
+      };
       // pass 1: one real candidate per cluster tightens the bound
 #pragma unroll 4
-      for (int m = 0; m < M; ++m) consider(sv[m * kCluster]);
+      for (int m = 0; m < M; ++m) {
+        const float4 xy = sv[m * kCluster], zw = sv[m * kCluster + 1];
+        consider(make_float4(xy.x, xy.z, zw.x, zw.z));
+      }
       // pass 2: scan the clusters whose box can still contain a vertex at distance <= best.  The box
       // distance uses the same rounded operations as `consider`, so it never exceeds a member's d2.
       for (int m = 0; m < M; ++m) {
@@ -296,7 +331,7 @@ __global__ void __launch_bounds__(kGeoThreads, 1) geo_kernel(GeoArgs a) {
         const float lb = __fadd_rn(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), __fmul_rn(bz, bz));
         if (lb <= best) {
 #pragma unroll 8
-          for (int i = 0; i < kCluster; ++i) consider(sv[m * kCluster + i]);
+          for (int i = 0; i < kCluster; i += 2) consider2(sv[m * kCluster + i], sv[m * kCluster + i + 1]);
         }
       }
     }

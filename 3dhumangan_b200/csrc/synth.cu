@@ -155,6 +155,15 @@ __device__ __forceinline__ float reduce_2pi(float t) {
 }
 __device__ __forceinline__ float sin_red(float t) { return __sinf(reduce_2pi(t)); }
 __device__ __forceinline__ float cos_red(float t) { return __cosf(reduce_2pi(t)); }
+// the same reduction on a pair (packed fp32: identical operations per lane)
+__device__ __forceinline__ float2 reduce_2pi2(float2 t) {
+  const float2 y = __fmul2_rn(t, make_float2(0.15915494309189535f, 0.15915494309189535f));
+  const float2 k = __fadd2_rn(__fadd2_rn(y, make_float2(12582912.f, 12582912.f)), make_float2(-12582912.f, -12582912.f));
+  const float2 r = __ffma2_rn(k, make_float2(-6.2831854820251465f, -6.2831854820251465f), t);
+  return __ffma2_rn(k, make_float2(1.7484555314695172e-07f, 1.7484555314695172e-07f), r);
+}
+__device__ __forceinline__ float2 sin_red2(float2 t) { const float2 r = reduce_2pi2(t); return make_float2(__sinf(r.x), __sinf(r.y)); }
+__device__ __forceinline__ float2 cos_red2(float2 t) { const float2 r = reduce_2pi2(t); return make_float2(__cosf(r.x), __cosf(r.y)); }
 
 // 32 lanes x 32 values: after the call lane j holds sum over lanes of v[j].
 __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
@@ -579,7 +588,7 @@ __device__ __forceinline__ void epilogue_bwd_loop(const SpadeArgs& a, const SynS
             acc = __ffma2_rn(a2, make_float2(k2[jj], k2[jj + 1]),
                              __ffma2_rn(a1, make_float2(k1[jj], k1[jj + 1]), __ffma2_rn(a0, make_float2(k0[jj], k0[jj + 1]), acc)));
           }
-          const float2 mask = kSine ? make_float2(cos_red(pre.x), cos_red(pre.y))
+          const float2 mask = kSine ? cos_red2(pre)
                                     : make_float2(pre.x > 0.f ? 1.f : mslope, pre.y > 0.f ? 1.f : mslope);
           const float2 d = __fmul2_rn(acc, mask);
           const float2 dx = __fmul2_rn(d, x2);
@@ -684,7 +693,12 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_const_kernel(SpadeArgs a
             for (int j = 0; j < 8; ++j) y[j] = scaled ? cur[g * 8 + j] * t1[j] : cur[g * 8 + j];
           } else if (sine) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = sin_red(fmaf(cur[g * 8 + j], t1[j], t0[j]));
+            for (int j = 0; j < 8; j += 2) {
+              const float2 sv = sin_red2(__ffma2_rn(make_float2(cur[g * 8 + j], cur[g * 8 + j + 1]), make_float2(t1[j], t1[j + 1]),
+                                                    make_float2(t0[j], t0[j + 1])));
+              y[j] = sv.x;
+              y[j + 1] = sv.y;
+            }
           } else {
             affine_lrelu8(cur + g * 8, t1, t0, slope, y);
           }
@@ -811,6 +825,7 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
         const float4* n10 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * a.Rw + x0) * a.p_stride);
         const float4* n11 = reinterpret_cast<const float4*>(base + (static_cast<long>(y1) * a.Rw + x1) * a.p_stride);
         const float4* pb = a.p_bias ? reinterpret_cast<const float4*>(a.p_bias + static_cast<long>(b) * 128) : nullptr;
+        const float2 lx0p = make_float2(lx0, lx0), lx1p = make_float2(lx1, lx1), ly0p = make_float2(ly0, ly0), ly1p = make_float2(ly1, ly1);
 #pragma unroll 2
         for (int g = 0; g < 8; ++g) {
           float y[8];
@@ -818,15 +833,21 @@ __global__ void __launch_bounds__(kSynThreads, 1) spade_pixel_kernel(SpadeArgs a
           for (int u = 0; u < 2; ++u) {
             const int f4 = h * 16 + g * 2 + u;
             const float4 v00 = __ldg(n00 + f4), v01 = __ldg(n01 + f4), v10 = __ldg(n10 + f4), v11 = __ldg(n11 + f4);
-            // same association as upsample_bilinear2d: ly0*(lx0*a + lx1*b) + ly1*(lx0*c + lx1*d)
-            y[u * 4 + 0] = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
-            y[u * 4 + 1] = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
-            y[u * 4 + 2] = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
-            y[u * 4 + 3] = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+            // same association as upsample_bilinear2d: ly0*(lx0*a + lx1*b) + ly1*(lx0*c + lx1*d), on channel pairs (packed fp32:
+            // this loop is on the critical chain of the tile -- the gamma/beta GEMM cannot start before it)
+            auto lerp2 = [&](float2 a, float2 b, float2 c, float2 d) {
+              const float2 top = __ffma2_rn(b, lx1p, __fmul2_rn(a, lx0p));
+              const float2 bot = __ffma2_rn(d, lx1p, __fmul2_rn(c, lx0p));
+              return __ffma2_rn(top, ly0p, __fmul2_rn(bot, ly1p));
+            };
+            float2 lo2 = lerp2(make_float2(v00.x, v00.y), make_float2(v01.x, v01.y), make_float2(v10.x, v10.y), make_float2(v11.x, v11.y));
+            float2 hi2 = lerp2(make_float2(v00.z, v00.w), make_float2(v01.z, v01.w), make_float2(v10.z, v10.w), make_float2(v11.z, v11.w));
             if (pb) {
               const float4 c4 = __ldg(pb + f4);
-              y[u * 4 + 0] += c4.x; y[u * 4 + 1] += c4.y; y[u * 4 + 2] += c4.z; y[u * 4 + 3] += c4.w;
+              lo2 = __fadd2_rn(lo2, make_float2(c4.x, c4.y));
+              hi2 = __fadd2_rn(hi2, make_float2(c4.z, c4.w));
             }
+            y[u * 4 + 0] = lo2.x; y[u * 4 + 1] = lo2.y; y[u * 4 + 2] = hi2.x; y[u * 4 + 3] = hi2.y;
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) y[j] = valid ? fmaxf(y[j], 0.f) : 0.f;

@@ -461,16 +461,22 @@ __global__ void __launch_bounds__(128) a1_gather_kernel(const float* __restrict_
 #pragma unroll 4
   for (int f4 = 0; f4 < 32; ++f4) {
     const float4 v00 = __ldg(n00 + f4), v01 = __ldg(n01 + f4), v10 = __ldg(n10 + f4), v11 = __ldg(n11 + f4);
-    // same association as the forward kernel (csrc/synth.cu) and upsample_bilinear2d
-    float4 y;
-    y.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
-    y.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
-    y.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
-    y.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+    // the SAME packed operation sequence as the forward kernel (csrc/synth.cu phase 0), so that the recomputed A1 and its ReLU mask
+    // are bit-identical to what the forward multiplied with
+    const float2 lx0p = make_float2(lx0, lx0), lx1p = make_float2(lx1, lx1), ly0p = make_float2(ly0, ly0), ly1p = make_float2(ly1, ly1);
+    auto lerp2 = [&](float2 a, float2 b, float2 c, float2 d) {
+      const float2 top = __ffma2_rn(b, lx1p, __fmul2_rn(a, lx0p));
+      const float2 bot = __ffma2_rn(d, lx1p, __fmul2_rn(c, lx0p));
+      return __ffma2_rn(top, ly0p, __fmul2_rn(bot, ly1p));
+    };
+    float2 lo2 = lerp2(make_float2(v00.x, v00.y), make_float2(v01.x, v01.y), make_float2(v10.x, v10.y), make_float2(v11.x, v11.y));
+    float2 hi2 = lerp2(make_float2(v00.z, v00.w), make_float2(v01.z, v01.w), make_float2(v10.z, v10.w), make_float2(v11.z, v11.w));
     if (pb) {
       const float4 c4 = __ldg(pb + f4);
-      y.x += c4.x; y.y += c4.y; y.z += c4.z; y.w += c4.w;
+      lo2 = __fadd2_rn(lo2, make_float2(c4.x, c4.y));
+      hi2 = __fadd2_rn(hi2, make_float2(c4.z, c4.w));
     }
+    const float4 y = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
     dst[(f4 * 4 + 0) * 128] = valid ? fmaxf(y.x, 0.f) : 0.f;
     dst[(f4 * 4 + 1) * 128] = valid ? fmaxf(y.y, 0.f) : 0.f;
     dst[(f4 * 4 + 2) * 128] = valid ? fmaxf(y.z, 0.f) : 0.f;
