@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) conv_wgrad_kernel(ConvWgradArgs
   if (warp < 4) {
     float* dst0 = a.part_w + static_cast<long>(blockIdx.x) * a.ntaps * 256 * a.nq;
     if (count > 0) {
-      mbar_wait_sleep(bars + DW_DONE, 0);
+      mbar_wait_long(bars + DW_DONE, 0);
       tc_fence_after();
       for (int t = 0; t < a.ntaps; ++t) {
         float* dst = dst0 + static_cast<long>(t) * 256 * a.nq;

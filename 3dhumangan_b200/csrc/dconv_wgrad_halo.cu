@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) conv3x3_wgrad_halo_kernel(WgHal
     const int q = warp - 8;
     float* dst0 = a.part_w + static_cast<long>(blockIdx.x) * a.ntaps * 128 * 64;
     if (my_units > 0) {
-      mbar_wait_sleep(bars + WH_DONE, 0);
+      mbar_wait_long(bars + WH_DONE, 0);
       tc_fence_after();
       for (int tp = 0; tp < a.ntaps; ++tp) {
         float* dst = dst0 + (static_cast<long>(tp) * 128 + q * 32 + lane) * 64;

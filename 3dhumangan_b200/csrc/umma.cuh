@@ -60,6 +60,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   while (!mbar_try_wait(bar, parity)) __nanosleep(128);
 }
 
+// once-per-kernel waits (a drain team that idles until the CTA's last MMA has completed): poll every microsecond
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(1000);
+}
+
 // ---------------------------------------------------------------- explicit shared-space accesses
 // (pointers that went through integer alignment arithmetic compile to GENERIC LD/ST, which cost extra
 //  latency on the hot operand paths; these keep them LDS/STS)
