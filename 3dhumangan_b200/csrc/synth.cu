@@ -13,7 +13,8 @@
 //   warps 8-11  epilogue team: drain the fp32 accumulator of the PREVIOUS tile from TMEM (warp 8+q owns lanes
 //               32q..32q+31, all 256 columns): bias, residual, ToRGB, per-channel sum / sum-of-squares for the
 //               next BatchNorm (so SyncBN statistics never need their own pass), plane stores
-//   warp 12     one thread issues tcgen05.mma (M=128, N=256, K=16; bf16x3 split or plain bf16)
+//   warp 12     MMA issuer: the warp walks the tile / chunk loops in convergent code, its elected lane issues tcgen05.mma
+//               (M=128, N=256, K=16; bf16x3 split or plain bf16)
 //   warp 13     one thread streams the packed weight tiles from L2 (cp.async.bulk, 2 x 32 KB stages)
 //   warp 14     one thread streams activation slices (ring slots 0-2, operand team) from HBM with cp.async.bulk
 //   warp 15     one thread streams residual slices (ring slots 3-4, epilogue team).  Two threads, not one: with a
