@@ -1,6 +1,6 @@
 """Stand-alone GPU probe (not collected by pytest): graph vs eager divergence, call by call."""
 import importlib, sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(_ROOT, 'tests')); sys.path.insert(0, _ROOT)
 import torch
 from golden_util import generator_case, manifest, rel_l2
 pkg = importlib.import_module("3dhumangan_b200")

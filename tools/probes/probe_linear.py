@@ -1,6 +1,6 @@
 """Stand-alone GPU probe (not collected by pytest): prints per-block error maps for hg_linear."""
 import importlib, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 abi = importlib.import_module("3dhumangan_b200.abi")
 abi.require_device()

@@ -1,6 +1,6 @@
 """Stand-alone GPU probe (not collected): per-block error of the synthesis network on a multi-tile-per-CTA case."""
 import importlib, os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(_ROOT, 'tests')); sys.path.insert(0, _ROOT)
 import torch, torch.nn.functional as F
 from golden_util import rel_l2
 from oracle import port

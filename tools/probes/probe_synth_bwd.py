@@ -1,6 +1,6 @@
 """Debug helper (not a test): per-parameter gradient error table of the synthesis backward."""
 import importlib, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import port
 pkg = importlib.import_module("3dhumangan_b200")
