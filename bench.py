@@ -498,6 +498,19 @@ def run_gpu(args, pkg):
             import traceback
             traceback.print_exc()
             line["train_step"] = {"error": f"{type(err).__name__}: {str(err)[:300]}"}
+        # BASELINE.json pins the training configuration at bf16: the same iteration with single-pass bf16 products (fp32
+        # storage and accumulation; the analogue of the reference's autocast mode), next to the fp32x3 headline
+        if args.precision == "fp32x3" and not args.no_train_bf16 and isinstance(line["train_step"], dict) \
+                and "error" not in line["train_step"]:
+            try:
+                leg = train_leg(args, pkg, dev, rank, world, args.train_batch, args.train_steps, 2, "bf16", args.train_split)
+                if leg is not None:
+                    leg.pop("kernels", None)
+                line["train_step_bf16"] = leg
+            except Exception as err:
+                import traceback
+                traceback.print_exc()
+                line["train_step_bf16"] = {"error": f"{type(err).__name__}: {str(err)[:300]}"}
         dog.cancel()
     emit(line)
     _leave(world, G)
@@ -674,6 +687,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate (profiling runs)")
     ap.add_argument("--no-train", action="store_true", help="skip the G+D training-iteration leg of the default run")
+    ap.add_argument("--no-train-bf16", action="store_true", help="skip the additional bf16 training-iteration leg")
     ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per training iteration (config C3: 16)")
     ap.add_argument("--train-split", type=int, default=2, help="micro-batches per iteration (the reference's batch_split)")
     ap.add_argument("--train-steps", type=int, default=4, help="timed training iterations in the default run")
