@@ -500,7 +500,9 @@ def run_gpu(args, pkg):
             line["train_step"] = {"error": f"{type(err).__name__}: {str(err)[:300]}"}
         # BASELINE.json pins the training configuration at bf16: the same iteration with single-pass bf16 products (fp32
         # storage and accumulation; the analogue of the reference's autocast mode), next to the fp32x3 headline
-        if args.precision == "fp32x3" and not args.no_train_bf16 and isinstance(line["train_step"], dict) \
+        # Single-GPU runs only: the decision to enter a leg must be identical on every rank (it builds DDP wrappers, i.e.
+        # collectives), and only rank 0 holds the first leg's result.
+        if world == 1 and args.precision == "fp32x3" and not args.no_train_bf16 and isinstance(line["train_step"], dict) \
                 and "error" not in line["train_step"]:
             try:
                 leg = train_leg(args, pkg, dev, rank, world, args.train_batch, args.train_steps, 2, "bf16", args.train_split)
