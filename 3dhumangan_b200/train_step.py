@@ -55,8 +55,13 @@ def segmentation_loss(segments, gt, label_dim, prior_weights=None, with_stats=Fa
 
 
 def r1_penalty(disc_input_real, out_real, scaler, meta):
-    """phase_trainer.py:259-294: 0.5 * r1_lambda * E_b |d f / d x_b|^2 with f = sum(prediction) (gan_lambda > 0) or
-    sum(softmax(segments)) (segmentation only); differentiated again by `d_loss.backward()` (create_graph=True)."""
+    """phase_trainer.py:259-294, arithmetic as the reference EXECUTES it: the gradient of f = sum(prediction) (gan_lambda > 0) or
+    sum(softmax(segments)) (segmentation only) w.r.t. the real images is taken for the whole batch, but
+    `[p * inv_scale for p in grad_real][0]` (:281-282) iterates over the batch dimension of that tensor and keeps entry 0, and
+    `grad_real.view(grad_real.size(0), -1).pow(2).sum(dim=1).mean()` (:287-288) then averages over its CHANNELS:
+        penalty = 0.5 * r1_lambda * |d f / d x_0|^2 / C          (first sample of the batch, C = 3)
+    -- not the batch mean of the textbook R1.  Pinned against the reference's method by tests/test_cpu_trainer_pin.py.
+    Differentiated again by `d_loss.backward()` (create_graph=True)."""
     if meta["gan_lambda"] > 0:
         target = out_real["prediction"].sum()
     elif meta["segmentation_lambda"] > 0:
@@ -64,7 +69,7 @@ def r1_penalty(disc_input_real, out_real, scaler, meta):
     else:
         raise RuntimeError("cannot do r1 regularization when segmentation_lambda == 0 and gan_lambda == 0")
     grad_real = torch.autograd.grad(outputs=scaler.scale(target), inputs=disc_input_real, create_graph=True)[0]
-    grad_real = grad_real * (1.0 / scaler.get_scale())
+    grad_real = grad_real[0] * (1.0 / scaler.get_scale())
     pen = grad_real.reshape(grad_real.shape[0], -1).pow(2).sum(dim=1).mean()
     pen = 0.5 * meta["r1_lambda"] * pen
     if bool(torch.isnan(pen).any()):

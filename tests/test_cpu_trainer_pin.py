@@ -1,0 +1,126 @@
+"""Host-side trainer logic pinned LIVE against the reference's own code (build container only: needs /root/reference; skipped on
+the GPU box): the five Adam parameter groups of `PhaseTrainer.init_optimizer` (phase_trainer.py:57-76) and the EMA update of
+`lib/components/ema.py:29-48`, executed by the unmodified reference functions on THIS package's modules (same parameter names
+by the state_dict contract)."""
+import copy
+import importlib
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("HG_REFERENCE", "/root/reference")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "lib")), reason="needs the reference checkout")
+
+
+def _reference(modname):
+    for p in (os.path.join(ROOT, "oracle", "shims"), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    return importlib.import_module(modname)
+
+
+def _modules(pkg):
+    gen = importlib.import_module("3dhumangan_b200.modules.generator")
+    disc = importlib.import_module("3dhumangan_b200.modules.discriminator")
+    cfg = pkg.configs.baseline_config("tiny")
+    torch.manual_seed(0)
+    return gen.Map3DGenerator(**cfg), disc.UNetDiscriminator(**cfg), cfg
+
+
+def test_optimizer_groups_match_phase_trainer_init_optimizer(pkg, tmp_path):
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    pt = _reference("lib.trainers.phase_trainer")
+    G, D, cfg = _modules(pkg)
+    meta = dict(cfg, gen_lr=2e-5, disc_lr=2e-4, betas=(0.0, 0.9),      # (0, 0.9) in configs/map3d.py; this torch wants two floats
+                weight_decay=0, appearance_codes_lr_mul=3.0, mapping_net_lr_mul=0.5,
+                neural_field_lr_mul=0.25)
+    me = types.SimpleNamespace(generator_ddp=G, discriminator_ddp=D, output_dir=str(tmp_path), device="cpu")
+    pt.PhaseTrainer.init_optimizer(me, meta)                       # the reference's own method, unmodified
+    og, od = ts.make_optimizers(G, D, meta, fused=False)
+    og_f, od_f = ts.make_optimizers(G, D, meta, fused=True)         # the multi-tensor optimiser keeps the same groups
+    for mine in (og, og_f):
+        assert len(mine.param_groups) == len(me.optimizer_G.param_groups) == 5
+        for a, b in zip(mine.param_groups, me.optimizer_G.param_groups):
+            assert a["name"] == b["name"]
+            assert a["lr"] == pytest.approx(b["lr"], rel=0, abs=0) and tuple(a["betas"]) == tuple(b["betas"])
+            assert a["weight_decay"] == b["weight_decay"] and a["eps"] == b["eps"]
+            assert [id(p) for p in a["params"]] == [id(p) for p in b["params"]], a["name"]      # same tensors, same order
+    for mine in (od, od_f):
+        a, b = mine.param_groups[0], me.optimizer_D.param_groups[0]
+        assert len(mine.param_groups) == 1 and a["lr"] == b["lr"] and tuple(a["betas"]) == tuple(b["betas"])
+        assert [id(p) for p in a["params"]] == [id(p) for p in b["params"]]
+    # every generator parameter is in exactly one group
+    ids = [id(p) for g in og.param_groups for p in g["params"]]
+    assert len(ids) == len(set(ids)) == len(list(G.parameters()))
+
+
+def test_parameter_ema_matches_reference_ema(pkg):
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    ema_ref = _reference("lib.components.ema")
+    G, _, _ = _modules(pkg)
+    G2 = copy.deepcopy(G)
+    a = ts.ParameterEMA(G.parameters(), decay=0.999)
+    b = ema_ref.ExponentialMovingAverage(G2.parameters(), decay=0.999)
+    gen = torch.Generator().manual_seed(3)
+    for step in range(12):                                          # the num_updates ramp (1+n)/(10+n) and the plateau
+        with torch.no_grad():
+            for p, q in zip(G.parameters(), G2.parameters()):
+                d = torch.randn(p.shape, generator=gen) * 0.01
+                p.add_(d)
+                q.add_(d)
+        a.update(list(G.parameters()))
+        b.update(list(G2.parameters()))
+        assert a.num_updates == b.num_updates
+    assert len(a.shadow_params) == len(b.shadow_params)
+    for s, t in zip(a.shadow_params, b.shadow_params):
+        assert torch.allclose(s, t, rtol=1e-6, atol=1e-8)
+    # copy_to writes the averages into the parameters that require grad, in order
+    a.copy_to(G.parameters())
+    b.copy_to(G2.parameters())
+    for p, q in zip(G.parameters(), G2.parameters()):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("gan_lambda", [1.0, 0.0])
+def test_r1_penalty_matches_phase_trainer(gan_lambda):
+    """`train_step.r1_penalty` against the reference's `_calculate_r1_regularization` (phase_trainer.py:259-294) on a small
+    differentiable stand-in for the discriminator: value and the gradient the penalty sends into the parameters (the double
+    backward), with an enabled-style scale factor going through `scaler.scale` / `get_scale`."""
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    pt = _reference("lib.trainers.phase_trainer")
+
+    class Scaler:                     # GradScaler's two calls used there, with a non-trivial scale
+        def scale(self, t):
+            return t * 1024.0
+
+        def get_scale(self):
+            return 1024.0
+
+    g = torch.Generator().manual_seed(9)
+    w1 = torch.randn(6, 3, 3, 3, generator=g, dtype=torch.float64) * 0.3
+    w2 = torch.randn(5, 6, 1, 1, generator=g, dtype=torch.float64) * 0.3
+    x0 = torch.randn(3, 3, 8, 8, generator=g, dtype=torch.float64)
+    meta = dict(gan_lambda=gan_lambda, segmentation_lambda=1.0, r1_lambda=0.25)
+
+    def run(fn):
+        a, b = w1.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+        x = x0.clone().requires_grad_(True)
+        h = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x, a, padding=1), 0.2)
+        seg = torch.nn.functional.conv2d(torch.tanh(h), b)
+        out = {"prediction": (h * h).mean(dim=(1, 2, 3)), "segments": seg}
+        pen = fn(x, out)
+        pen.backward()
+        return float(pen), a.grad.clone(), b.grad.clone() if b.grad is not None else torch.zeros_like(b)
+
+    me = types.SimpleNamespace(scaler=Scaler(), amp=False)
+    ref = run(lambda x, out: pt.PhaseTrainer._calculate_r1_regularization(me, x, out, {"do_r1": True}, meta))
+    got = run(lambda x, out: ts.r1_penalty(x, out, Scaler(), meta))
+    assert got[0] == pytest.approx(ref[0], rel=1e-12, abs=1e-18)
+    assert torch.allclose(got[1], ref[1], rtol=1e-10, atol=1e-16) and torch.allclose(got[2], ref[2], rtol=1e-10, atol=1e-16)
+    if gan_lambda > 0:
+        assert ref[0] > 0
