@@ -124,3 +124,94 @@ def test_r1_penalty_matches_phase_trainer(gan_lambda):
     assert torch.allclose(got[1], ref[1], rtol=1e-10, atol=1e-16) and torch.allclose(got[2], ref[2], rtol=1e-10, atol=1e-16)
     if gan_lambda > 0:
         assert ref[0] > 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the composition of the two steps: the reference's own `_train_discriminator` / `_train_generator` (phase_trainer.py:344-560),
+# unmodified, against `train_step.Trainer.train_discriminator / train_generator` on the same stand-in networks
+# ----------------------------------------------------------------------------------------------------------------------
+class _StandInG(torch.nn.Module):
+    """A generator with the call signature the trainer uses (z, conditions, latent_indices=..., **meta) -> {'rgbs', 'rgbs_render'}."""
+
+    def __init__(self, L):
+        super().__init__()
+        g = torch.Generator().manual_seed(21)
+        self.neural_field_mapping_network = torch.nn.Linear(L, 6)
+        self.synthesis_network = torch.nn.Conv2d(6, 3, 3, padding=1)
+        with torch.no_grad():
+            for p in self.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+
+    def forward(self, z, conditions, latent_indices=None, disable_synthesis=False, **kwargs):
+        h = torch.tanh(self.neural_field_mapping_network(z))[:, :, None, None] + conditions["x"]
+        rgb = torch.tanh(self.synthesis_network(h))
+        return {"rgbs": rgb, "rgbs_render": torch.nn.functional.avg_pool2d(rgb, 2)}
+
+
+class _StandInD(torch.nn.Module):
+    def __init__(self, label_dim):
+        super().__init__()
+        g = torch.Generator().manual_seed(22)
+        self.c1 = torch.nn.Conv2d(3, 8, 3, padding=1)
+        self.seg = torch.nn.Conv2d(8, label_dim, 1)
+        self.pred = torch.nn.Linear(8, 1)
+        self.step = 0
+        with torch.no_grad():
+            for p in self.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+
+    def forward(self, x, conditions, alpha=1.0, mode="real", **kwargs):
+        h = torch.nn.functional.leaky_relu(self.c1(x), 0.2) + (0.1 if mode == "real" else -0.1) * conditions["x"][:, :1]
+        return {"prediction": self.pred(h.mean(dim=(2, 3))), "segments": self.seg(h), "latents": h.mean(dim=(2, 3))}
+
+
+@pytest.mark.parametrize("gan_lambda,do_r1", [(0.0, False), (0.0, True), (1.0, True)])
+def test_step_composition_matches_phase_trainer(pkg, gan_lambda, do_r1, monkeypatch):
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    pt = _reference("lib.trainers.phase_trainer")
+    L, LD, B, H = 5, 7, 4, 8
+    phase = {"name": "uncond", "uncond": True, "rotate": True, "gen_modal": "rgbs", "do_r1": do_r1}
+    meta = dict(latent_dim=L, label_dim=LD, z_dist="gaussian", gan_lambda=gan_lambda, segmentation_lambda=1.0, latent_lambda=0,
+                perceptual_lambda=[0, 0, 0, 0], photometric_lambda=0, r1_lambda=0.25, grad_clip=1e9, gen_lr=0.0, disc_lr=0.0,
+                betas=(0.0, 0.9), weight_decay=0, appearance_codes_lr_mul=1.0, mapping_net_lr_mul=1.0, neural_field_lr_mul=1.0,
+                batch_split=2, phases=[phase], render_height=4, render_width=4, gen_height=H, gen_width=H)
+    g = torch.Generator().manual_seed(23)
+    images = torch.randn(B, 3, H, H, generator=g).clamp_(-1, 1)
+    labels = torch.randint(0, LD, (B, H, H), generator=g)
+    x = torch.randn(B, 6, H, H, generator=g) * 0.2
+    z_d, z_g = torch.randn(B, L, generator=g), torch.randn(B, L, generator=g)
+
+    # ---- the reference's methods on a bare namespace
+    Gr, Dr = _StandInG(L), _StandInD(LD)
+    me = types.SimpleNamespace(amp=False, device="cpu", batch_split=2, rank=0, generator_ddp=Gr, discriminator_ddp=Dr, discriminator=Dr,
+                               scaler=torch.amp.GradScaler("cuda", enabled=False))
+    for name in ("_train_discriminator", "_train_generator", "_get_disc_input_real", "_get_disc_input_gen",
+                 "_calculate_r1_regularization", "_calculate_segmentation_loss"):
+        setattr(me, name, types.MethodType(getattr(pt.PhaseTrainer, name), me))
+    zs = [z_d, z_g]
+    monkeypatch.setattr(pt, "z_sampler", lambda *a, **k: zs.pop(0))
+    monkeypatch.setattr(pt.training_stats, "report", lambda *a, **k: None)
+    data = {"images": images, "body_segments": labels, "rasterized_segments": labels, "latents": torch.zeros(B, L), "x": x}
+    d_ref = me._train_discriminator(data, 1.0, meta, phase)
+    d_ref.backward()
+    dgrads = [p.grad.clone() for p in Dr.parameters()]
+    Gr.zero_grad()
+    Dr.zero_grad()
+    g_ref, _ = me._train_generator(data, 1.0, meta, phase)
+    ggrads = [p.grad.clone() for p in Gr.parameters()]
+
+    # ---- this package's trainer on identical stand-ins
+    Gm, Dm = _StandInG(L), _StandInD(LD)
+    t = ts.Trainer(Gm, Dm, meta, amp=False, ddp=False, fused=False)
+    batch = dict(images=images, labels=labels, cond={"x": x}, z_d=z_d, z_g=z_g)
+    d_mine = t.train_discriminator(batch)
+    for p, r in zip(Dm.parameters(), dgrads):
+        assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-7), float((p.grad - r).abs().max())
+    assert float(d_mine) == pytest.approx(float(d_ref), rel=1e-6)
+    g_mine = t.train_generator(batch)
+    for p, r in zip(Gm.parameters(), ggrads):
+        assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-7), float((p.grad - r).abs().max())
+    assert float(g_mine) == pytest.approx(float(g_ref), rel=1e-6, abs=1e-12)
+    # learning rate 0, no clipping: both steps ran their optimiser / EMA tail without moving a parameter
+    for p, q in zip(list(Gm.parameters()) + list(Dm.parameters()), list(Gr.parameters()) + list(Dr.parameters())):
+        assert torch.equal(p.detach(), q.detach())
