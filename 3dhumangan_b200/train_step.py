@@ -249,8 +249,16 @@ class Trainer:
         return torch.rand(B, self.meta["latent_dim"], device=device) * 2 - 1
 
     # -- phase_trainer.py:297-318 + :344-444
+    def _check_phase(self, phase):
+        """The input selection of `_get_disc_input_real / _gen` (phase_trainer.py:162-200) has two more branches (dual discrimination,
+        render-resolution modalities) that no shipped curriculum reaches: refuse them instead of training on the wrong tensors."""
+        if self.meta.get("dual_discrimination", False) or "render" in phase["gen_modal"] or not phase.get("uncond", True):
+            raise RuntimeError("hg3d: dual_discrimination / gen_modal '%s' / conditional phases are not used by any shipped "
+                               "curriculum and are not built" % phase["gen_modal"])
+
     def train_discriminator(self, batch, alpha=1.0):
         meta, phase = self.meta, self._phase()
+        self._check_phase(phase)
         self.optimizer_D.zero_grad()
         real_images, labels, cond = batch["images"], batch["labels"], batch["cond"]
         B = real_images.shape[0]
@@ -292,6 +300,7 @@ class Trainer:
     # -- phase_trainer.py:321-341 + :446-560
     def train_generator(self, batch, alpha=1.0):
         meta, phase = self.meta, self._phase()
+        self._check_phase(phase)
         self.optimizer_G.zero_grad()
         real_images, labels, cond = batch["images"], batch["labels"], batch["cond"]
         B = real_images.shape[0]

@@ -215,3 +215,37 @@ def test_step_composition_matches_phase_trainer(pkg, gan_lambda, do_r1, monkeypa
     # learning rate 0, no clipping: both steps ran their optimiser / EMA tail without moving a parameter
     for p, q in zip(list(Gm.parameters()) + list(Dm.parameters()), list(Gr.parameters()) + list(Dr.parameters())):
         assert torch.equal(p.detach(), q.detach())
+
+
+@pytest.mark.parametrize("name", ["MAP3DBN", "MAP3DBN512", "MAP3DBN512L"])
+def test_curricula_match_reference_configs(pkg, name):
+    """`3dhumangan_b200.configs` (the drop-in `configs` package) against the reference's `configs/map3d.py` + `extract_metadata`
+    (configs/__init__.py) for every shipped curriculum at steps on both sides of every schedule boundary."""
+    ref = _reference("configs")
+    mine = pkg.configs
+    cur_r, cur_m = getattr(ref, name), getattr(mine, name)
+    steps = sorted({0, 1, 999, 1000, 200000, 200001, 300000, 300001, 300002, 10 ** 6} | {int(k) for k in cur_r if isinstance(k, int)} |
+                   {int(k) + 1 for k in cur_r if isinstance(k, int)})
+    for step in steps:
+        a, b = ref.extract_metadata(cur_r, step), mine.extract_metadata(cur_m, step)
+        for k, v in a.items():
+            assert k in b, (name, step, k)
+            if k == "neural_field_cls":
+                assert (v if isinstance(v, str) else v.__name__) == (b[k] if isinstance(b[k], str) else b[k].__name__)
+            else:
+                assert b[k] == v, (name, step, k, v, b[k])
+        extra = set(b) - set(a)
+        assert all(k.startswith("hg_") for k in extra), (name, step, extra)
+
+
+def test_trainer_refuses_the_branches_it_does_not_mirror():
+    ts = importlib.import_module("3dhumangan_b200.train_step")
+    meta = dict(latent_dim=5, label_dim=7, gan_lambda=0.0, segmentation_lambda=1.0, r1_lambda=0.0, grad_clip=1.0, gen_lr=0.0, disc_lr=0.0,
+                betas=(0.0, 0.9), weight_decay=0, appearance_codes_lr_mul=1.0, mapping_net_lr_mul=1.0, neural_field_lr_mul=1.0,
+                phases=[{"name": "uncond", "uncond": True, "rotate": True, "gen_modal": "rgbs_render", "do_r1": False}])
+    t = ts.Trainer(_StandInG(5), _StandInD(7), meta, amp=False, ddp=False, fused=False)
+    batch = dict(images=torch.zeros(2, 3, 8, 8), labels=torch.zeros(2, 8, 8, dtype=torch.long), cond={"x": torch.zeros(2, 6, 8, 8)})
+    with pytest.raises(RuntimeError, match="not built"):
+        t.train_discriminator(batch)
+    with pytest.raises(RuntimeError, match="not built"):
+        t.train_generator(batch)
