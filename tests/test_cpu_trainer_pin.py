@@ -249,3 +249,38 @@ def test_trainer_refuses_the_branches_it_does_not_mirror():
         t.train_discriminator(batch)
     with pytest.raises(RuntimeError, match="not built"):
         t.train_generator(batch)
+
+
+def test_activation_table_matches_reference_bias_act():
+    """ops/bias_act.ACTIVATIONS (id, default alpha, default gain, which tensor the backward keeps, second derivative) against the
+    reference's `activation_funcs` (lib/components/ops/bias_act.py:22-32) -- the ids are what the C ABI's `act` argument means."""
+    mine = importlib.import_module("3dhumangan_b200.ops.bias_act").ACTIVATIONS
+    ref = _reference("lib.components.ops.bias_act").activation_funcs
+    cuda_acts = {k: v for k, v in ref.items() if v.cuda_idx is not None}
+    assert set(mine) == set(cuda_acts)
+    for k, spec in cuda_acts.items():
+        aid, alpha, gain, keep, second = mine[k]
+        assert aid == spec.cuda_idx and alpha == pytest.approx(spec.def_alpha) and gain == pytest.approx(float(spec.def_gain))
+        assert keep == spec.ref and second == spec.has_2nd_grad
+
+
+@pytest.mark.parametrize("tune,variant", [("", 0), ("lr", 0), ("lr", 3), ("map3d_mode", 0), ("map3d_mode", 2)])
+def test_get_config_matches_reference(pkg, tune, variant):
+    """`configs.get_config(opt)` (configs/__init__.py:49-76: curriculum lookup, neural-field class resolution, the two `--tune`
+    sweeps) on deep copies of both packages' curricula."""
+    ref = _reference("configs")
+    mine = pkg.configs
+    name = "MAP3DBN512"
+    saved_r, saved_m = copy.deepcopy(getattr(ref, name)), copy.deepcopy(getattr(mine, name))
+    try:
+        opt = types.SimpleNamespace(config=name, tune=tune, variant=variant)
+        a, b = ref.get_config(opt), mine.get_config(opt)
+        assert a["name"] == b["name"] and a["map3d_mode"] == b["map3d_mode"]
+        assert a["neural_field_cls"].__name__ == b["neural_field_cls"].__name__
+        for k in a:
+            if isinstance(k, int):
+                assert a[k] == b[k], (k, a[k], b[k])
+    finally:
+        setattr(ref, name, saved_r)
+        ref.__dict__[name] = saved_r
+        setattr(mine, name, saved_m)
